@@ -1,0 +1,143 @@
+"""ctypes binding of libhsolve_cuda (include/hsolve_cuda.h).  There is no CPU fallback: if the shared library
+is missing this module raises on import, and every compute entry point fails without a B200."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhsolve_cuda.so")
+
+HS_OK, HS_EARG, HS_EDIM, HS_ETREE, HS_ESINGULAR, HS_ECUDA, HS_ENOMEM, HS_ENOTIMPL, HS_ESIZE = range(9)
+HS_F64, HS_C64 = 0, 1
+HS_GET_D, HS_GET_S, HS_GET_L, HS_GET_R, HS_GET_FRONT, HS_GET_PIV = range(6)
+
+i64p = C.POINTER(C.c_int64)
+
+
+class hs_opts(C.Structure):
+    _fields_ = [("swlevel", C.c_int64), ("swsize", C.c_int64), ("atol", C.c_double), ("rtol", C.c_double),
+                ("c_tol", C.c_double), ("leafsize", C.c_int64), ("kest", C.c_int64), ("stepsize", C.c_int64),
+                ("verbose", C.c_int32), ("keep_schur", C.c_int32)]
+
+
+class hs_elimtree(C.Structure):
+    _fields_ = [("nnodes", C.c_int64), ("fathers", i64p), ("lsons", i64p), ("rsons", i64p), ("inter_ptr", i64p),
+                ("inter_idx", i64p), ("bound_ptr", i64p), ("bound_idx", i64p), ("index_base", C.c_int32)]
+
+
+class hs_tree(C.Structure):
+    _fields_ = [("nnodes", C.c_int64), ("left", i64p), ("right", i64p), ("int_ptr", i64p), ("int_idx", i64p),
+                ("bnd_ptr", i64p), ("bnd_idx", i64p), ("iloc_ptr", i64p), ("iloc_idx", i64p), ("bloc_ptr", i64p),
+                ("bloc_idx", i64p), ("index_base", C.c_int32)]
+
+
+class hs_stats_t(C.Structure):
+    _fields_ = [("nnodes", C.c_int64), ("nlevels", C.c_int64), ("n", C.c_int64), ("max_ni", C.c_int64),
+                ("max_nb", C.c_int64), ("factor_flops", C.c_double), ("solve_bytes", C.c_double),
+                ("extadd_bytes", C.c_double), ("front_bytes", C.c_double), ("ms_analyze", C.c_double),
+                ("ms_h2d", C.c_double), ("ms_assemble", C.c_double), ("ms_panel", C.c_double), ("ms_trsm", C.c_double),
+                ("ms_gemm", C.c_double), ("ms_factor_total", C.c_double), ("ms_solve_fwd", C.c_double),
+                ("ms_solve_bwd", C.c_double), ("ms_solve_total", C.c_double), ("launches_factor", C.c_int64),
+                ("launches_solve", C.c_int64), ("singular_front", C.c_int64), ("singular_col", C.c_int64),
+                ("maxrank", C.c_int64)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+# every symbol include/hsolve_cuda.h declares: (name, restype, argtypes)
+PROTOTYPES = [
+    ("hs_version", C.c_int32, []),
+    ("hs_last_error", C.c_char_p, []),
+    ("hs_create", C.c_int32, [C.POINTER(C.c_void_p), C.c_int32]),
+    ("hs_set_stream", C.c_int32, [C.c_void_p, C.c_void_p]),
+    ("hs_destroy", C.c_int32, [C.c_void_p]),
+    ("hs_device_count", C.c_int32, []),
+    ("hs_symfact", C.c_int32, [C.POINTER(hs_elimtree), C.c_int32, C.POINTER(C.c_void_p)]),
+    ("hs_symbolic_tree", C.c_int32, [C.c_void_p, C.POINTER(hs_tree)]),
+    ("hs_symbolic_perm", C.c_int32, [C.c_void_p, C.POINTER(i64p), i64p]),
+    ("hs_symbolic_depth", C.c_int32, [C.c_void_p, i64p]),
+    ("hs_symbolic_free", C.c_int32, [C.c_void_p]),
+    ("hs_factor", C.c_int32, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(hs_tree),
+                              C.POINTER(hs_opts), C.c_int32, C.POINTER(C.c_void_p)]),
+    ("hs_refactor", C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32]),
+    ("hs_factor_free", C.c_int32, [C.c_void_p]),
+    ("hs_solve", C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32]),
+    ("hs_node_get", C.c_int32, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, i64p]),
+    ("hs_maxrank", C.c_int32, [C.c_void_p, i64p]),
+    ("hs_stats", C.c_int32, [C.c_void_p, C.POINTER(hs_stats_t)]),
+    ("hs_resolved_swlevel", C.c_int32, [C.c_void_p, i64p]),
+    ("hs_gmres", C.c_int32, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                             C.c_void_p, C.c_void_p, C.c_double, C.c_int64, C.c_int64, C.POINTER(C.c_double), i64p,
+                             C.POINTER(C.c_int32), C.c_int32]),
+]
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+        "(nvcc, sm_100a).  This package has no CPU fallback.")
+
+lib = C.CDLL(LIB_PATH)
+for _name, _res, _args in PROTOTYPES:
+    _fn = getattr(lib, _name)
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+class HSolveError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(msg)
+        self.code = code
+
+
+class SingularException(HSolveError, np.linalg.LinAlgError):
+    pass
+
+
+class DimensionMismatch(HSolveError, ValueError):
+    pass
+
+
+class ArgumentError(HSolveError, ValueError):
+    pass
+
+
+def check(code: int) -> None:
+    """Map a status code to the exception the reference would raise."""
+    if code == HS_OK:
+        return
+    msg = (lib.hs_last_error() or b"").decode("utf-8", "replace")
+    if code == HS_ESINGULAR:
+        raise SingularException(code, msg)
+    if code == HS_EDIM:
+        raise DimensionMismatch(code, msg)
+    if code == HS_EARG:
+        raise ArgumentError(code, msg)
+    if code == HS_ENOMEM:
+        raise MemoryError(msg)
+    if code == HS_ENOTIMPL:
+        raise NotImplementedError(msg)
+    raise HSolveError(code, msg)
+
+
+def as_i64(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+def ptr(a: np.ndarray, typ=i64p):
+    return a.ctypes.data_as(typ)
+
+
+_ctx_cache = {}
+
+
+def default_context(device: int = 0) -> C.c_void_p:
+    """One hs_ctx per device per process."""
+    if device not in _ctx_cache:
+        h = C.c_void_p()
+        check(lib.hs_create(C.byref(h), device))
+        _ctx_cache[device] = h
+    return _ctx_cache[device]

@@ -1,0 +1,685 @@
+// libhsolve_cuda: C ABI, level-batched plan construction and kernel orchestration.
+// Reference call sites each entry point replaces are listed in include/hsolve_cuda.h.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+
+#include "hs_fac.cuh"
+#include "hs_internal.h"
+#include "hs_kernels.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+int32_t hs_fail(int32_t code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+extern "C" const char* hs_last_error(void) { return g_last_error.c_str(); }
+extern "C" int32_t hs_version(void) { return HS_VERSION; }
+
+extern "C" int32_t hs_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+extern "C" int32_t hs_create(hs_ctx** out, int32_t device) {
+  HS_TRY_BEGIN
+  if (!out) return hs_fail(HS_EARG, "hs_create: null argument");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return hs_fail(HS_ECUDA, "hs_create: no CUDA device available (this library has no CPU fallback)");
+  }
+  if (device < 0 || device >= ndev) return hs_fail(HS_EARG, "hs_create: device out of range");
+  CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return hs_fail(HS_ECUDA, std::string("hs_create: built for sm_100a, found ") + prop.name);
+  auto* c = new hs_ctx();
+  c->device = device;
+  CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  c->own_stream = true;
+  c->profile = getenv("HS_PROFILE") != nullptr;
+  // opt in to 16-CTA clusters for the tall panels, and to >48 KB dynamic shared memory for the DMMA tiles
+  hs_panel_setup_f64();
+  hs_panel_setup_c64();
+  c->max_cluster = getenv("HS_MAX_CLUSTER") ? atoi(getenv("HS_MAX_CLUSTER")) : 16;
+  CUDA_OK(cudaFuncSetAttribute(k_gemm<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (GemmCfg<double>::KC * GemmCfg<double>::LDA + 64 * GemmCfg<double>::LDB) * (int)sizeof(double)));
+  CUDA_OK(cudaFuncSetAttribute(k_gemm<cplx>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (GemmCfg<cplx>::KC * GemmCfg<cplx>::LDA + 64 * GemmCfg<cplx>::LDB) * (int)sizeof(cplx)));
+  CUDA_OK(cudaFuncSetAttribute(k_rperm, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  *out = c;
+  return HS_OK;
+  HS_TRY_END
+}
+
+extern "C" int32_t hs_set_stream(hs_ctx* ctx, void* s) {
+  if (!ctx) return hs_fail(HS_EARG, "hs_set_stream: null context");
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  ctx->stream = (cudaStream_t)s;
+  ctx->own_stream = false;
+  return HS_OK;
+}
+
+extern "C" int32_t hs_destroy(hs_ctx* ctx) {
+  if (!ctx) return HS_OK;
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return HS_OK;
+}
+
+// accumulate the time of a phase only when HS_PROFILE is set (it serialises the stream)
+struct PhaseTimer {
+  hs_fac* f;
+  double* acc;
+  cudaEvent_t a = nullptr, b = nullptr;
+  PhaseTimer(hs_fac* f_, double* acc_) : f(f_), acc(acc_) {
+    if (f->ctx->profile) {
+      cudaEventCreate(&a); cudaEventCreate(&b);
+      cudaEventRecord(a, f->ctx->stream);
+    }
+  }
+  ~PhaseTimer() {
+    if (f->ctx->profile) {
+      cudaEventRecord(b, f->ctx->stream);
+      cudaEventSynchronize(b);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, a, b);
+      *acc += ms;
+      cudaEventDestroy(a); cudaEventDestroy(b);
+    }
+  }
+};
+
+template <typename T> struct PanelW;  // widest register tile per scalar type
+template <> struct PanelW<double> { static constexpr int W0 = 64; };
+template <> struct PanelW<cplx> { static constexpr int W0 = 32; };
+
+template <typename T, int W> static void launch_trsm_w(hs_fac* f, int f0, int nact, int j0, int max_n) {
+  dim3 grid(nact, (max_n + 127) / 128);
+  k_swap_trsm<T, W><<<grid, 128, 0, f->ctx->stream>>>(f->d_fronts, (T*)f->pool, f->d_ipiv, f0, j0);
+  CUDA_OK(cudaGetLastError());
+}
+
+template <typename T> static void trsm_dispatch(hs_fac* f, int W, int f0, int nact, int j0, int max_n) {
+  constexpr int W0 = PanelW<T>::W0;
+  if (W == W0) launch_trsm_w<T, W0>(f, f0, nact, j0, max_n);
+  else if (W == W0 / 2) launch_trsm_w<T, W0 / 2>(f, f0, nact, j0, max_n);
+  else if (W == W0 / 4) launch_trsm_w<T, W0 / 4>(f, f0, nact, j0, max_n);
+  else launch_trsm_w<T, W0 / 8>(f, f0, nact, j0, max_n);
+}
+
+// partial LU of all fronts of one level (pivot block + Schur update), batched over the level
+template <typename T> static void factor_level(hs_fac* f, const Level& L) {
+  cudaStream_t st = f->ctx->stream;
+  const int W = hs_panel_width(f, L.max_n);
+  if (W < 0) throw hs_error(HS_ESIZE, "front with " + std::to_string(L.max_n) + " rows exceeds the panel kernels");
+  constexpr int smem_gemm = (GemmCfg<T>::KC * GemmCfg<T>::LDA + 64 * GemmCfg<T>::LDB) * (int)sizeof(T);
+  for (int j0 = 0; j0 < L.max_ni; j0 += W) {
+    // fronts are sorted by ni descending: the active ones (ni > j0) are a prefix
+    const int nact = (int)(std::partition_point(L.ni_sorted.begin(), L.ni_sorted.end(), [&](int v) { return v > j0; }) -
+                           L.ni_sorted.begin());
+    if (nact == 0) break;
+    const int m = L.max_n - j0;
+    {
+      PhaseTimer t(f, &f->stats.ms_panel);
+      hs_panel_launch(f, W, L.f0, nact, j0, m);
+    }
+    if (m > 1) {
+      PhaseTimer t(f, &f->stats.ms_trsm);
+      trsm_dispatch<T>(f, W, L.f0, nact, j0, L.max_n);
+    }
+    if (m > 1) {
+      PhaseTimer t(f, &f->stats.ms_gemm);
+      const int tiles = (m + 63) / 64;
+      dim3 grid(nact, tiles, tiles);
+      k_gemm<T><<<grid, 128, smem_gemm, st>>>(f->d_fronts, (T*)f->pool, L.f0, j0, W);
+      CUDA_OK(cudaGetLastError());
+    }
+    f->stats.launches_factor += 3;
+  }
+  if (L.max_ni > 0) {
+    const size_t sm = (size_t)L.max_ni * sizeof(int);
+    if (sm > 200 * 1024) throw hs_error(HS_ESIZE, "pivot block too large for k_rperm");
+    k_rperm<<<L.f1 - L.f0, 256, sm, st>>>(f->d_fronts, f->d_ipiv, f->d_rperm, L.f0);
+    CUDA_OK(cudaGetLastError());
+    f->stats.launches_factor += 1;
+  }
+}
+
+template <typename T> static void numeric(hs_fac* f) {
+  cudaStream_t st = f->ctx->stream;
+  T* pool = (T*)f->pool;
+  hs_stats_t& s = f->stats;
+  s.ms_assemble = s.ms_panel = s.ms_trsm = s.ms_gemm = 0;
+  s.launches_factor = 0;
+  CUDA_OK(cudaEventRecord(f->ev0, st));
+  CUDA_OK(cudaMemsetAsync(f->d_info, 0, 4 * sizeof(int), st));
+  for (size_t li = 0; li < f->levels.size(); ++li) {
+    const Level& L = f->levels[li];
+    const int nf = L.f1 - L.f0;
+    if (!L.pseudo) {
+      PhaseTimer t(f, &s.ms_assemble);
+      CUDA_OK(cudaMemsetAsync(pool + L.poff0, 0, (size_t)(L.poff1 - L.poff0) * sizeof(T), st));
+      dim3 grid(nf, (L.max_n + 255) / 256);
+      k_fill_owner<<<grid, 256, 0, st>>>(f->d_fronts, f->d_gidx, f->d_own, f->d_pos, L.f0);
+      k_scatter_A<T><<<grid, 256, 0, st>>>(f->d_fronts, pool, f->d_gidx, f->d_own, f->d_pos, f->d_colptr,
+                                            f->d_rowval, (const T*)f->d_nzval, L.f0);
+      s.launches_factor += 3;
+      if (li > 0 && !f->levels[li - 1].pseudo) {
+        const Level& Lc = f->levels[li - 1];
+        if (Lc.max_nb > 0) {
+          constexpr int CB = 8;
+          dim3 g2(Lc.f1 - Lc.f0, (Lc.max_nb + CB - 1) / CB);
+          k_extend_add<T, CB><<<g2, 256, 0, st>>>(f->d_fronts, pool, f->d_cmap, Lc.f0);
+          s.launches_factor += 1;
+        }
+      }
+      CUDA_OK(cudaGetLastError());
+    }
+    factor_level<T>(f, L);
+  }
+  CUDA_OK(cudaEventRecord(f->ev1, st));
+  int info[4];
+  CUDA_OK(cudaMemcpyAsync(info, f->d_info, sizeof(info), cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  float ms = 0;
+  CUDA_OK(cudaEventElapsedTime(&ms, f->ev0, f->ev1));
+  s.ms_factor_total = ms;
+  s.singular_front = -1;
+  s.singular_col = -1;
+  if (info[0]) {
+    s.singular_front = f->fronts[info[1]].flags & 1 ? f->nnodes - 1 : -1;
+    for (int64_t k = 0; k < f->nnodes; ++k)
+      if (f->node2front[k] == info[1]) s.singular_front = k;
+    s.singular_col = info[2];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// hs_factor
+// ------------------------------------------------------------------------------------------------
+static void check_opts(const hs_opts& o) {  // chkopts! HierarchicalSolvers.jl:73-79
+  if (o.swsize < 1) throw hs_error(HS_EARG, "swsize");
+  if (!(o.atol >= 0.)) throw hs_error(HS_EARG, "atol");
+  if (!(o.rtol >= 0.)) throw hs_error(HS_EARG, "rtol");
+  if (!(0. < o.c_tol && o.c_tol <= 1.)) throw hs_error(HS_EARG, "c_tol");
+  if (o.leafsize < 1) throw hs_error(HS_EARG, "leafsize");
+}
+
+template <typename V> static void dev_upload(V** dst, const V* src, size_t count, cudaStream_t st) {
+  CUDA_OK(cudaMalloc((void**)dst, std::max<size_t>(count, 1) * sizeof(V)));
+  if (count) CUDA_OK(cudaMemcpyAsync(*dst, src, count * sizeof(V), cudaMemcpyHostToDevice, st));
+}
+
+static void build_plan(hs_fac* f, const hs_tree* t) {
+  const int64_t nn = t->nnodes, base = t->index_base;
+  if (nn <= 0) throw hs_error(HS_EARG, "hs_factor: empty tree");
+  f->nnodes = nn;
+  f->left.assign(t->left, t->left + nn);
+  f->right.assign(t->right, t->right + nn);
+  f->parent.assign(nn, -1);
+  for (int64_t k = 0; k < nn; ++k) {
+    for (int side = 0; side < 2; ++side) {
+      int64_t& c = side ? f->right[k] : f->left[k];
+      if (c == -1) continue;
+      c -= base;
+      if (c < 0 || c >= nn || c == k) throw hs_error(HS_EARG, "hs_factor: child id out of range");
+      if (f->parent[c] != -1) throw hs_error(HS_EARG, "hs_factor: node has two parents");
+      f->parent[c] = k;
+    }
+    // factorization.jl:24-26
+    if ((f->left[k] == -1) != (f->right[k] == -1))
+      throw hs_error(HS_ETREE, "Expected nested dissection to be a binary tree. Found a node with only one child.");
+  }
+  int64_t root = -1;
+  for (int64_t k = 0; k < nn; ++k)
+    if (f->parent[k] == -1) {
+      if (root != -1) throw hs_error(HS_EARG, "hs_factor: more than one root");
+      root = k;
+    }
+  if (root < 0) throw hs_error(HS_EARG, "hs_factor: no root");
+  // levels: root = 1 as `_factor(..., 1)` (factorization.jl:9)
+  f->level.assign(nn, 0);
+  {
+    std::vector<int64_t> st{root};
+    f->level[root] = 1;
+    int64_t seen = 0;
+    while (!st.empty()) {
+      int64_t k = st.back(); st.pop_back(); ++seen;
+      for (int64_t c : {f->left[k], f->right[k]})
+        if (c >= 0) { f->level[c] = f->level[k] + 1; st.push_back(c); }
+    }
+    if (seen != nn) throw hs_error(HS_EARG, "hs_factor: tree is not connected");
+  }
+  const int64_t maxlev = *std::max_element(f->level.begin(), f->level.end());
+  f->depth = maxlev;
+  auto copy0 = [&](const int64_t* ptr, const int64_t* idx, std::vector<int64_t>& p, std::vector<int64_t>& v) {
+    p.assign(ptr, ptr + nn + 1);
+    v.assign(idx, idx + p[nn]);
+    for (auto& x : v) x -= base;
+  };
+  std::vector<int64_t> int_ptr, int_idx, bnd_ptr, bnd_idx;
+  copy0(t->int_ptr, t->int_idx, int_ptr, int_idx);
+  copy0(t->bnd_ptr, t->bnd_idx, bnd_ptr, bnd_idx);
+  copy0(t->iloc_ptr, t->iloc_idx, f->iloc_ptr, f->iloc_idx);
+  copy0(t->bloc_ptr, t->bloc_idx, f->bloc_ptr, f->bloc_idx);
+  f->node_ni.resize(nn);
+  f->node_nb.resize(nn);
+  for (int64_t k = 0; k < nn; ++k) {
+    f->node_ni[k] = (int)(int_ptr[k + 1] - int_ptr[k]);
+    f->node_nb[k] = (int)(bnd_ptr[k + 1] - bnd_ptr[k]);
+    if ((int64_t)f->node_ni[k] + f->node_nb[k] > (1 << 30)) throw hs_error(HS_ESIZE, "front too large");
+  }
+  for (int64_t v : int_idx) if (v < 0 || v >= f->n) throw hs_error(HS_EARG, "hs_factor: DOF index out of range in int");
+  for (int64_t v : bnd_idx) if (v < 0 || v >= f->n) throw hs_error(HS_EARG, "hs_factor: DOF index out of range in bnd");
+  // consistency of (nd, nd_loc): a branch's sets are the concatenation of its children's selected boundary rows
+  // (nesteddissection.jl:64-65, factorization.jl:63-64)
+  auto nloc = [&](const std::vector<int64_t>& p, int64_t k) { return p[k + 1] - p[k]; };
+  for (int64_t k = 0; k < nn; ++k) {
+    if (f->left[k] < 0) continue;
+    const int64_t l = f->left[k], r = f->right[k];
+    const int64_t nil = nloc(f->iloc_ptr, l), nir = nloc(f->iloc_ptr, r), nbl = nloc(f->bloc_ptr, l), nbr = nloc(f->bloc_ptr, r);
+    if (nil + nir != f->node_ni[k] || nbl + nbr != f->node_nb[k])
+      throw hs_error(HS_EDIM, "hs_factor: node " + std::to_string(k) + " int/bnd sizes do not match its children's nd_loc");
+    auto chk = [&](int64_t c, const std::vector<int64_t>& lp, const std::vector<int64_t>& li, const int64_t* dst) {
+      for (int64_t q = lp[c]; q < lp[c + 1]; ++q) {
+        const int64_t a = li[q];
+        if (a < 0 || a >= f->node_nb[c]) throw hs_error(HS_EARG, "hs_factor: nd_loc position out of range");
+        if (bnd_idx[bnd_ptr[c] + a] != dst[q - lp[c]])
+          throw hs_error(HS_EARG, "hs_factor: (nd, nd_loc) inconsistent — was the tree produced by symfact!?");
+      }
+    };
+    chk(l, f->iloc_ptr, f->iloc_idx, int_idx.data() + int_ptr[k]);
+    chk(r, f->iloc_ptr, f->iloc_idx, int_idx.data() + int_ptr[k] + nil);
+    chk(l, f->bloc_ptr, f->bloc_idx, bnd_idx.data() + bnd_ptr[k]);
+    chk(r, f->bloc_ptr, f->bloc_idx, bnd_idx.data() + bnd_ptr[k] + nbl);
+  }
+  // front order: deepest level first; inside a level by ni descending (active panels form a prefix)
+  std::vector<int64_t> order(nn);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
+    if (f->level[a] != f->level[b]) return f->level[a] > f->level[b];
+    return f->node_ni[a] > f->node_ni[b];
+  });
+  const bool pseudo = f->node_nb[root] > 0;
+  const int nfr = (int)nn + (pseudo ? 1 : 0);
+  f->fronts.assign(nfr, Front{});
+  f->node2front.assign(nn, -1);
+  for (int i = 0; i < (int)nn; ++i) f->node2front[order[i]] = i;
+  f->root_front = f->node2front[root];
+  std::vector<int> gidx, cmap;
+  long long poff = 0, ioff = 0;
+  const long long align = 32;
+  f->levels.clear();
+  double flops = 0, sbytes = 0, ebytes = 0;
+  int64_t max_ni = 0, max_nb = 0;
+  for (int i = 0; i < (int)nn; ++i) {
+    const int64_t k = order[i];
+    Front& fr = f->fronts[i];
+    fr.ni = f->node_ni[k];
+    fr.n = fr.ni + f->node_nb[k];
+    fr.ld = (fr.n + 1) & ~1;
+    if (fr.ld == 0) fr.ld = 2;
+    fr.off = poff;
+    fr.ioff = ioff;
+    fr.parent = f->parent[k] >= 0 ? f->node2front[f->parent[k]] : -1;
+    fr.flags = 0;
+    if (f->left[k] < 0) { fr.ni_l = -1; fr.nb_l = 0; }
+    else { fr.ni_l = (int)nloc(f->iloc_ptr, f->left[k]); fr.nb_l = (int)nloc(f->bloc_ptr, f->left[k]); }
+    if (f->levels.empty() || f->level[k] != f->level[order[f->levels.back().f0]]) {
+      Level L; L.f0 = i; L.f1 = i; L.ioff0 = ioff; L.poff0 = poff;
+      f->levels.push_back(L);
+    }
+    Level& L = f->levels.back();
+    L.f1 = i + 1;
+    L.max_n = std::max(L.max_n, fr.n);
+    L.max_ni = std::max(L.max_ni, fr.ni);
+    L.max_nb = std::max(L.max_nb, fr.n - fr.ni);
+    L.ni_sorted.push_back(fr.ni);
+    poff += ((long long)fr.ld * fr.n + align - 1) / align * align;
+    ioff += fr.n;
+    L.ioff1 = ioff; L.poff1 = poff;
+    // per-row tables
+    gidx.insert(gidx.end(), int_idx.begin() + int_ptr[k], int_idx.begin() + int_ptr[k + 1]);
+    gidx.insert(gidx.end(), bnd_idx.begin() + bnd_ptr[k], bnd_idx.begin() + bnd_ptr[k + 1]);
+    cmap.resize(ioff, -1);
+    const double ni = fr.ni, nb = fr.n - fr.ni;
+    flops += 2.0 / 3.0 * ni * ni * ni + 2.0 * ni * ni * nb + 2.0 * ni * nb * nb;
+    sbytes += ni * ni + 2.0 * ni * nb;
+    ebytes += 2.0 * nb * nb;
+    max_ni = std::max<int64_t>(max_ni, fr.ni);
+    max_nb = std::max<int64_t>(max_nb, fr.n - fr.ni);
+  }
+  // child → parent row maps: the children's S[perm,perm] lands as diagonal blocks of the parent front
+  // (factorization.jl:41,74 and :118-121)
+  for (int64_t k = 0; k < nn; ++k) {
+    if (f->left[k] < 0) continue;
+    const int64_t l = f->left[k], r = f->right[k];
+    const int nil = (int)nloc(f->iloc_ptr, l), nbl = (int)nloc(f->bloc_ptr, l), nip = f->node_ni[k];
+    auto fill = [&](int64_t c, int ioffset, int boffset) {
+      const Front& fc = f->fronts[f->node2front[c]];
+      int* m = cmap.data() + fc.ioff + fc.ni;
+      for (int64_t q = f->iloc_ptr[c]; q < f->iloc_ptr[c + 1]; ++q) m[f->iloc_idx[q]] = ioffset + (int)(q - f->iloc_ptr[c]);
+      for (int64_t q = f->bloc_ptr[c]; q < f->bloc_ptr[c + 1]; ++q) m[f->bloc_idx[q]] = nip + boffset + (int)(q - f->bloc_ptr[c]);
+    };
+    fill(l, 0, 0);
+    fill(r, nil, nbl);
+  }
+  if (pseudo) {  // root boundary solve `F.S \ C[F.bnd,:]` (factornode.jl:72) as one more dense front
+    const Front& rf = f->fronts[f->root_front];
+    Front& pf = f->fronts[nn];
+    pf.n = pf.ni = rf.n - rf.ni;
+    pf.ld = rf.ld;
+    pf.off = rf.off + (long long)rf.ni * rf.ld + rf.ni;
+    pf.ioff = ioff;
+    pf.parent = -1;
+    pf.ni_l = -1; pf.nb_l = 0;
+    pf.flags = 1;
+    Level L; L.f0 = (int)nn; L.f1 = (int)nn + 1; L.max_n = L.max_ni = pf.n; L.max_nb = 0;
+    L.ioff0 = ioff; L.ioff1 = ioff + pf.n; L.poff0 = L.poff1 = poff; L.pseudo = true;
+    L.ni_sorted.push_back(pf.ni);
+    f->levels.push_back(L);
+    f->pseudo_front = (int)nn;
+    gidx.insert(gidx.end(), bnd_idx.begin() + bnd_ptr[root], bnd_idx.begin() + bnd_ptr[root + 1]);
+    ioff += pf.n;
+    cmap.resize(ioff, -1);
+    const double ni = pf.ni;
+    flops += 2.0 / 3.0 * ni * ni * ni;
+    sbytes += ni * ni;
+  }
+  f->pool_elems = poff;
+  f->idx_total = ioff;
+  f->max_level_idx = 0;
+  for (auto& L : f->levels) f->max_level_idx = std::max(f->max_level_idx, L.ioff1 - L.ioff0);
+  const double cx = f->dtype == HS_C64 ? 4.0 : 1.0;
+  hs_stats_t& s = f->stats;
+  s.nnodes = nn; s.nlevels = maxlev; s.n = f->n; s.max_ni = max_ni; s.max_nb = max_nb;
+  s.factor_flops = flops * cx;
+  s.solve_bytes = sbytes * f->esz;
+  s.extadd_bytes = ebytes * f->esz;
+  s.front_bytes = (double)poff * f->esz;
+  s.singular_front = s.singular_col = -1;
+  s.maxrank = 0;
+  // upload
+  cudaStream_t st = f->ctx->stream;
+  CUDA_OK(cudaMalloc(&f->pool, std::max<size_t>((size_t)poff, 1) * f->esz));
+  dev_upload(&f->d_fronts, f->fronts.data(), f->fronts.size(), st);
+  dev_upload(&f->d_gidx, gidx.data(), gidx.size(), st);
+  dev_upload(&f->d_cmap, cmap.data(), cmap.size(), st);
+  CUDA_OK(cudaMalloc((void**)&f->d_ipiv, std::max<size_t>(ioff, 1) * sizeof(int)));
+  CUDA_OK(cudaMalloc((void**)&f->d_rperm, std::max<size_t>(ioff, 1) * sizeof(int)));
+  CUDA_OK(cudaMalloc((void**)&f->d_own, std::max<size_t>(f->n, 1) * sizeof(int)));
+  CUDA_OK(cudaMalloc((void**)&f->d_pos, std::max<size_t>(f->n, 1) * sizeof(int)));
+  CUDA_OK(cudaMalloc((void**)&f->d_info, 4 * sizeof(int)));
+  CUDA_OK(cudaMemsetAsync(f->d_own, 0xff, std::max<size_t>(f->n, 1) * sizeof(int), st));
+  CUDA_OK(cudaMemsetAsync(f->d_ipiv, 0, std::max<size_t>(ioff, 1) * sizeof(int), st));
+  CUDA_OK(cudaMemsetAsync(f->d_rperm, 0, std::max<size_t>(ioff, 1) * sizeof(int), st));
+  CUDA_OK(cudaStreamSynchronize(st));  // host vectors go out of scope
+}
+
+__global__ void k_shift_index(long long* a, long long n, long long base) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] -= base;
+}
+
+extern "C" int32_t hs_factor(hs_ctx* ctx, hs_dtype dtype, int64_t n, const int64_t* colptr, const int64_t* rowval,
+                             const void* nzval, const hs_tree* tree, const hs_opts* opts, int32_t on_device,
+                             hs_fac** out) {
+  HS_TRY_BEGIN
+  if (!ctx || !colptr || !rowval || !nzval || !tree || !out) return hs_fail(HS_EARG, "hs_factor: null argument");
+  if (dtype != HS_F64 && dtype != HS_C64) return hs_fail(HS_EARG, "hs_factor: dtype must be HS_F64 or HS_C64");
+  if (n <= 0) return hs_fail(HS_EARG, "hs_factor: n must be positive");
+  CUDA_OK(cudaSetDevice(ctx->device));
+  auto t_begin = std::chrono::steady_clock::now();
+  std::unique_ptr<hs_fac> f(new hs_fac());
+  f->ctx = ctx;
+  f->dtype = dtype;
+  f->esz = dtype == HS_C64 ? 16 : 8;
+  f->n = n;
+  if (opts) f->opts = *opts;
+  else { f->opts = hs_opts{5, 1, 1e-6, 1e-6, 0.5, 32, -1, 10, 0, 1}; }
+  check_opts(f->opts);
+  CUDA_OK(cudaEventCreate(&f->ev0));
+  CUDA_OK(cudaEventCreate(&f->ev1));
+  build_plan(f.get(), tree);
+  // swlevel < 0 is relative to the tree depth (factorization.jl:8)
+  f->swlevel_resolved = f->opts.swlevel < 0 ? std::max<int64_t>(f->depth + f->opts.swlevel, 0) : f->opts.swlevel;
+  if (f->swlevel_resolved > 0) {
+    // compression_flag = (level ≤ swlevel) && (|bnd| ≥ swsize) (factorization.jl:15)
+    for (int64_t k = 0; k < f->nnodes; ++k)
+      if (f->level[k] <= f->swlevel_resolved && f->node_nb[k] >= f->opts.swsize)
+        return hs_fail(HS_ENOTIMPL, "hs_factor: HSS-compressed fronts (swlevel > 0) are not built yet; pass swlevel = 0");
+  }
+  auto t_plan = std::chrono::steady_clock::now();
+  f->stats.ms_analyze = std::chrono::duration<double, std::milli>(t_plan - t_begin).count();
+  // matrix
+  cudaStream_t st = ctx->stream;
+  const int64_t base = tree->index_base;
+  CUDA_OK(cudaMalloc((void**)&f->d_colptr, (size_t)(n + 1) * sizeof(long long)));
+  const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  CUDA_OK(cudaMemcpyAsync(f->d_colptr, colptr, (size_t)(n + 1) * sizeof(long long), kind, st));
+  int64_t last = 0;
+  if (on_device) {
+    CUDA_OK(cudaMemcpyAsync(&last, colptr + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+  } else last = colptr[n];
+  f->nnz = last - (on_device ? 0 : base);
+  if (f->nnz < 0) return hs_fail(HS_EARG, "hs_factor: negative nnz");
+  CUDA_OK(cudaMalloc((void**)&f->d_rowval, std::max<size_t>(f->nnz, 1) * sizeof(long long)));
+  CUDA_OK(cudaMalloc(&f->d_nzval, std::max<size_t>(f->nnz, 1) * f->esz));
+  CUDA_OK(cudaMemcpyAsync(f->d_rowval, rowval, (size_t)f->nnz * sizeof(long long), kind, st));
+  CUDA_OK(cudaMemcpyAsync(f->d_nzval, nzval, (size_t)f->nnz * f->esz, kind, st));
+  if (!on_device && base != 0) {
+    k_shift_index<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(f->d_colptr, n + 1, base);
+    if (f->nnz) k_shift_index<<<(unsigned)((f->nnz + 255) / 256), 256, 0, st>>>(f->d_rowval, f->nnz, base);
+  }
+  CUDA_OK(cudaStreamSynchronize(st));
+  auto t_h2d = std::chrono::steady_clock::now();
+  f->stats.ms_h2d = std::chrono::duration<double, std::milli>(t_h2d - t_plan).count();
+  if (dtype == HS_F64) numeric<double>(f.get()); else numeric<cplx>(f.get());
+  *out = f.release();
+  if ((*out)->stats.singular_front >= 0 || (*out)->stats.singular_col >= 0)
+    return hs_fail(HS_ESINGULAR, "hs_factor: exactly singular pivot block in node " + std::to_string((*out)->stats.singular_front) +
+                                     ", column " + std::to_string((*out)->stats.singular_col));
+  return HS_OK;
+  HS_TRY_END
+}
+
+extern "C" int32_t hs_refactor(hs_fac* f, const void* nzval, int32_t on_device) {
+  HS_TRY_BEGIN
+  if (!f || !nzval) return hs_fail(HS_EARG, "hs_refactor: null argument");
+  CUDA_OK(cudaSetDevice(f->ctx->device));
+  if (nzval != f->d_nzval)
+    CUDA_OK(cudaMemcpyAsync(f->d_nzval, nzval, (size_t)f->nnz * f->esz, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                            f->ctx->stream));
+  if (f->dtype == HS_F64) numeric<double>(f); else numeric<cplx>(f);
+  if (f->stats.singular_col >= 0) return hs_fail(HS_ESINGULAR, "hs_refactor: exactly singular pivot block");
+  return HS_OK;
+  HS_TRY_END
+}
+
+extern "C" int32_t hs_factor_free(hs_fac* f) {
+  if (f) { cudaSetDevice(f->ctx->device); delete f; }
+  return HS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// hs_solve
+// ------------------------------------------------------------------------------------------------
+template <typename T> static void solve_impl(hs_fac* f, int64_t nrhs, const void* B, int64_t ldb, void* X, int64_t ldx, int on_device) {
+  cudaStream_t st = f->ctx->stream;
+  if (nrhs > f->rhs_cap) {
+    cudaFree(f->d_x); cudaFree(f->d_work);
+    f->d_x = f->d_work = nullptr;
+    CUDA_OK(cudaMalloc(&f->d_x, (size_t)f->n * nrhs * sizeof(T)));
+    CUDA_OK(cudaMalloc(&f->d_work, std::max<size_t>((size_t)f->max_level_idx * nrhs, 1) * sizeof(T)));
+    f->rhs_cap = nrhs;
+  }
+  T* x = (T*)f->d_x;
+  const cudaMemcpyKind kin = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  const cudaMemcpyKind kout = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  CUDA_OK(cudaMemcpy2DAsync(x, (size_t)f->n * sizeof(T), B, (size_t)ldb * sizeof(T), (size_t)f->n * sizeof(T), nrhs, kin, st));
+  CUDA_OK(cudaEventRecord(f->ev0, st));
+  hs_stats_t& s = f->stats;
+  s.launches_solve = 0;
+  const long long ws = f->max_level_idx;
+  for (size_t li = 0; li < f->levels.size(); ++li) {  // post-order: deepest level first
+    const Level& L = f->levels[li];
+    dim3 grid(L.f1 - L.f0, (unsigned)nrhs);
+    k_solve_fwd<T><<<grid, 256, 0, st>>>(f->d_fronts, (const T*)f->pool, f->d_gidx, f->d_rperm, x, f->n, (T*)f->d_work, ws, L.ioff0, L.f0);
+    ++s.launches_solve;
+  }
+  for (size_t li = f->levels.size(); li-- > 0;) {  // pre-order: root first
+    const Level& L = f->levels[li];
+    dim3 grid(L.f1 - L.f0, (unsigned)nrhs);
+    k_solve_bwd<T><<<grid, 256, 0, st>>>(f->d_fronts, (const T*)f->pool, f->d_gidx, x, f->n, (T*)f->d_work, ws, L.ioff0, L.f0);
+    ++s.launches_solve;
+  }
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaEventRecord(f->ev1, st));
+  CUDA_OK(cudaMemcpy2DAsync(X, (size_t)ldx * sizeof(T), x, (size_t)f->n * sizeof(T), (size_t)f->n * sizeof(T), nrhs, kout, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  float ms = 0;
+  CUDA_OK(cudaEventElapsedTime(&ms, f->ev0, f->ev1));
+  s.ms_solve_total = ms;
+}
+
+extern "C" int32_t hs_solve(hs_fac* f, int64_t nrhs, const void* B, int64_t ldb, void* X, int64_t ldx, int32_t on_device) {
+  HS_TRY_BEGIN
+  if (!f || !B || !X) return hs_fail(HS_EARG, "hs_solve: null argument");
+  if (nrhs <= 0) return HS_OK;
+  if (ldb < f->n || ldx < f->n) return hs_fail(HS_EDIM, "hs_solve: leading dimension smaller than n");
+  CUDA_OK(cudaSetDevice(f->ctx->device));
+  if (f->dtype == HS_F64) solve_impl<double>(f, nrhs, B, ldb, X, ldx, on_device);
+  else solve_impl<cplx>(f, nrhs, B, ldb, X, ldx, on_device);
+  return HS_OK;
+  HS_TRY_END
+}
+
+// ------------------------------------------------------------------------------------------------
+// introspection: FactorNode fields as the reference defines them (host-side reconstruction from the front)
+// ------------------------------------------------------------------------------------------------
+template <typename T> static void node_get_impl(hs_fac* f, int64_t node, hs_which which, void* out, int64_t* dims) {
+  const Front& fr = f->fronts[f->node2front[node]];
+  const int n = fr.n, ni = fr.ni, nb = n - ni;
+  int64_t r = 0, c = 0;
+  switch (which) {
+    case HS_GET_D: r = ni; c = ni; break;
+    case HS_GET_S: r = nb; c = nb; break;
+    case HS_GET_L: r = nb; c = ni; break;
+    case HS_GET_R: r = ni; c = nb; break;
+    case HS_GET_FRONT: r = n; c = n; break;
+    case HS_GET_PIV: r = ni; c = 1; break;
+    default: throw hs_error(HS_EARG, "hs_node_get: unknown field");
+  }
+  if (dims) { dims[0] = r; dims[1] = c; }
+  if (!out) return;
+  cudaStream_t st = f->ctx->stream;
+  std::vector<T> Fh((size_t)n * n);
+  std::vector<int> piv(ni);
+  if (n) CUDA_OK(cudaMemcpy2DAsync(Fh.data(), (size_t)n * sizeof(T), (T*)f->pool + fr.off, (size_t)fr.ld * sizeof(T), (size_t)n * sizeof(T), n,
+                                   cudaMemcpyDeviceToHost, st));
+  if (ni) CUDA_OK(cudaMemcpyAsync(piv.data(), f->d_ipiv + fr.ioff, (size_t)ni * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  auto Fm = [&](int i, int j) -> T& { return Fh[(size_t)j * n + i]; };
+  T* o = (T*)out;
+  if (which == HS_GET_FRONT) { std::memcpy(out, Fh.data(), Fh.size() * sizeof(T)); return; }
+  if (which == HS_GET_PIV) { int64_t* po = (int64_t*)out; for (int i = 0; i < ni; ++i) po[i] = piv[i]; return; }
+  if (which == HS_GET_S) {
+    // S[perm,perm], perm = [int_loc; bnd_loc] (factorization.jl:39-41,73-74); rows the parent drops are omitted
+    std::vector<int> perm;
+    for (int64_t q = f->iloc_ptr[node]; q < f->iloc_ptr[node + 1]; ++q) perm.push_back((int)f->iloc_idx[q]);
+    for (int64_t q = f->bloc_ptr[node]; q < f->bloc_ptr[node + 1]; ++q) perm.push_back((int)f->bloc_idx[q]);
+    const int np = (int)perm.size();
+    if (dims) { dims[0] = np; dims[1] = np; }
+    for (int j = 0; j < np; ++j)
+      for (int i = 0; i < np; ++i) o[(size_t)j * np + i] = Fm(ni + perm[i], ni + perm[j]);
+    return;
+  }
+  if (which == HS_GET_D) {
+    // A_ii = Pᵀ·L11·U11
+    std::vector<T> M((size_t)ni * ni, hs_zero<T>());
+    for (int j = 0; j < ni; ++j)
+      for (int k = 0; k <= j; ++k) {
+        const T u = Fm(k, j);
+        M[(size_t)j * ni + k] = hs_add(M[(size_t)j * ni + k], u);  // unit diagonal of L
+        for (int i = k + 1; i < ni; ++i) M[(size_t)j * ni + i] = hs_fma(M[(size_t)j * ni + i], Fm(i, k), u);
+      }
+    for (int k = ni - 1; k >= 0; --k)
+      if (piv[k] != k)
+        for (int j = 0; j < ni; ++j) std::swap(M[(size_t)j * ni + k], M[(size_t)j * ni + piv[k]]);
+    std::memcpy(out, M.data(), M.size() * sizeof(T));
+    return;
+  }
+  if (which == HS_GET_R) {
+    // R = A_ii⁻¹·A_ib = U11⁻¹·U12
+    for (int j = 0; j < nb; ++j) {
+      T* x = o + (size_t)j * ni;
+      for (int i = 0; i < ni; ++i) x[i] = Fm(i, ni + j);
+      for (int k = ni - 1; k >= 0; --k) {
+        x[k] = hs_mul(x[k], hs_recip(Fm(k, k)));
+        for (int i = 0; i < k; ++i) x[i] = hs_fnma(x[i], Fm(i, k), x[k]);
+      }
+    }
+    return;
+  }
+  if (which == HS_GET_L) {
+    // L = A_bi·A_ii⁻¹ = L21·L11⁻¹·P : solve X·L11 = L21 (unit lower), then undo the interchanges on the columns
+    std::vector<T> X((size_t)nb * ni);
+    for (int k = 0; k < ni; ++k)
+      for (int i = 0; i < nb; ++i) X[(size_t)k * nb + i] = Fm(ni + i, k);
+    for (int k = ni - 1; k >= 0; --k)
+      for (int j = 0; j < k; ++j) {
+        const T l = Fm(k, j);
+        for (int i = 0; i < nb; ++i) X[(size_t)j * nb + i] = hs_fnma(X[(size_t)j * nb + i], X[(size_t)k * nb + i], l);
+      }
+    for (int k = ni - 1; k >= 0; --k)
+      if (piv[k] != k)
+        for (int i = 0; i < nb; ++i) std::swap(X[(size_t)k * nb + i], X[(size_t)piv[k] * nb + i]);
+    std::memcpy(out, X.data(), X.size() * sizeof(T));
+    return;
+  }
+}
+
+extern "C" int32_t hs_node_get(hs_fac* f, int64_t node, hs_which which, void* out, int64_t* dims) {
+  HS_TRY_BEGIN
+  if (!f) return hs_fail(HS_EARG, "hs_node_get: null argument");
+  if (node < 0 || node >= f->nnodes) return hs_fail(HS_EARG, "hs_node_get: node out of range");
+  CUDA_OK(cudaSetDevice(f->ctx->device));
+  if (f->dtype == HS_F64) node_get_impl<double>(f, node, which, out, dims);
+  else node_get_impl<cplx>(f, node, which, out, dims);
+  return HS_OK;
+  HS_TRY_END
+}
+
+extern "C" int32_t hs_maxrank(hs_fac* f, int64_t* rank) {
+  if (!f || !rank) return hs_fail(HS_EARG, "hs_maxrank: null argument");
+  *rank = f->stats.maxrank;  // 0 when nothing is compressed (factornode.jl:49-57)
+  return HS_OK;
+}
+
+extern "C" int32_t hs_stats(hs_fac* f, hs_stats_t* out) {
+  if (!f || !out) return hs_fail(HS_EARG, "hs_stats: null argument");
+  *out = f->stats;
+  return HS_OK;
+}
+
+extern "C" int32_t hs_resolved_swlevel(hs_fac* f, int64_t* sw) {
+  if (!f || !sw) return hs_fail(HS_EARG, "hs_resolved_swlevel: null argument");
+  *sw = f->swlevel_resolved;
+  return HS_OK;
+}

@@ -1,0 +1,89 @@
+// Scalar types and device-side front descriptor shared by all kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+// interleaved complex float64 (Julia ComplexF64 / numpy complex128 layout)
+struct __align__(16) cplx {
+  double x, y;
+};
+
+// One eliminated front (the device image of a reference FactorNode, factornode.jl:7-22).
+// The front is ONE column-major n×n matrix, rows/cols ordered [int (ni); bnd (nb)]:
+//
+//        [ LU(A_ii)      U12 = L11⁻¹·P·A_ib ]      ni
+//   F =  [ L21 = A_bi·U11⁻¹   S = A_bb − L21·U12 ]  nb
+//
+// so D, L = L21·L11⁻¹·P, R = U11⁻¹·U12 and S of the reference are all recoverable from it.
+struct Front {
+  long long off;   // element offset of F in the pool
+  long long ioff;  // offset of this front's slice in the per-row int arrays (gidx, ipiv, rperm, cmap); length n
+  int n, ni, ld;
+  int parent;      // front id of the parent, -1 for the root
+  int ni_l, nb_l;  // branch: #int / #bnd rows that come from the left child; leaf: ni_l = -1
+  int flags;       // bit0: pseudo front (root Schur block, factornode.jl:72) — no assembly
+  int pad;
+};
+
+template <typename T> struct hs_traits;
+template <> struct hs_traits<double> { static constexpr bool is_complex = false; };
+template <> struct hs_traits<cplx> { static constexpr bool is_complex = true; };
+
+__host__ __device__ __forceinline__ double hs_zero(double*) { return 0.0; }
+__host__ __device__ __forceinline__ cplx hs_zero(cplx*) { return cplx{0.0, 0.0}; }
+template <typename T> __host__ __device__ __forceinline__ T hs_zero() { return hs_zero((T*)nullptr); }
+template <typename T> __host__ __device__ __forceinline__ T hs_one();
+template <> __host__ __device__ __forceinline__ double hs_one<double>() { return 1.0; }
+template <> __host__ __device__ __forceinline__ cplx hs_one<cplx>() { return cplx{1.0, 0.0}; }
+
+// |re| + |im| for complex, as LAPACK izamax/zgetf2 pick pivots (cabs1); |x| for real
+__host__ __device__ __forceinline__ double hs_abs1(double a) { return fabs(a); }
+__host__ __device__ __forceinline__ double hs_abs1(cplx a) { return fabs(a.x) + fabs(a.y); }
+
+__host__ __device__ __forceinline__ double hs_mul(double a, double b) { return a * b; }
+__host__ __device__ __forceinline__ cplx hs_mul(cplx a, cplx b) { return cplx{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+__host__ __device__ __forceinline__ double hs_add(double a, double b) { return a + b; }
+__host__ __device__ __forceinline__ cplx hs_add(cplx a, cplx b) { return cplx{a.x + b.x, a.y + b.y}; }
+__host__ __device__ __forceinline__ double hs_sub(double a, double b) { return a - b; }
+__host__ __device__ __forceinline__ cplx hs_sub(cplx a, cplx b) { return cplx{a.x - b.x, a.y - b.y}; }
+// acc - a*b
+__host__ __device__ __forceinline__ double hs_fnma(double acc, double a, double b) { return fma(-a, b, acc); }
+__host__ __device__ __forceinline__ cplx hs_fnma(cplx acc, cplx a, cplx b) {
+  cplx r;
+  r.x = fma(-a.x, b.x, acc.x);
+  r.x = fma(a.y, b.y, r.x);
+  r.y = fma(-a.x, b.y, acc.y);
+  r.y = fma(-a.y, b.x, r.y);
+  return r;
+}
+// acc + a*b
+__host__ __device__ __forceinline__ double hs_fma(double acc, double a, double b) { return fma(a, b, acc); }
+__host__ __device__ __forceinline__ cplx hs_fma(cplx acc, cplx a, cplx b) {
+  cplx r;
+  r.x = fma(a.x, b.x, acc.x);
+  r.x = fma(-a.y, b.y, r.x);
+  r.y = fma(a.x, b.y, acc.y);
+  r.y = fma(a.y, b.x, r.y);
+  return r;
+}
+__host__ __device__ __forceinline__ double hs_recip(double a) { return 1.0 / a; }
+__host__ __device__ __forceinline__ cplx hs_recip(cplx a) {
+  // Smith's algorithm, as LAPACK dladiv-style division of 1 by a
+  if (fabs(a.x) >= fabs(a.y)) {
+    double r = a.y / a.x, d = a.x + a.y * r;
+    return cplx{1.0 / d, -r / d};
+  } else {
+    double r = a.x / a.y, d = a.y + a.x * r;
+    return cplx{r / d, -1.0 / d};
+  }
+}
+__host__ __device__ __forceinline__ bool hs_iszero(double a) { return a == 0.0; }
+__host__ __device__ __forceinline__ bool hs_iszero(cplx a) { return a.x == 0.0 && a.y == 0.0; }
+
+#ifdef __CUDACC__
+__device__ __forceinline__ double hs_shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ cplx hs_shfl(cplx v, int src) {
+  return cplx{__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src)};
+}
+#endif

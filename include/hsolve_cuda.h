@@ -1,0 +1,173 @@
+/*
+ * libhsolve_cuda — C ABI of the B200-native multifrontal nested-dissection factor + tree solve.
+ *
+ * This is the drop-in boundary for the hot path of bonevbs/HierarchicalSolvers.jl.  The reference has no
+ * FFI of its own (it is plain Julia dispatch), so each entry point below names the Julia method whose
+ * work it takes over; the Julia-side `ccall` binding a maintainer would add is in INTEGRATION.md and
+ * hierarchicalsolvers.jl_b200/julia/HierarchicalSolversCUDA.jl.
+ *
+ * Conventions
+ *   - every function returns an int32 status (HS_OK = 0); hs_last_error() gives the text of the last
+ *     failure on the calling thread.  Nothing throws across this boundary.
+ *   - all host inputs are copied during the call; the library owns every device allocation until the
+ *     matching *_free / hs_destroy.
+ *   - matrices are column-major; complex is interleaved (re, im) float64.
+ *   - index arrays are int64 and carry an explicit `index_base` (Julia passes 1, C/Python 0).
+ */
+#ifndef HSOLVE_CUDA_H
+#define HSOLVE_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HS_VERSION 100
+
+/* status codes — the Julia shim maps them to the exception the reference would raise */
+enum {
+  HS_OK = 0,
+  HS_EARG = 1,      /* ArgumentError      (HierarchicalSolvers.jl:74-78, nesteddissection.jl:111)        */
+  HS_EDIM = 2,      /* DimensionMismatch  (blockmatrix.jl:13-16,116-117, nesteddissection.jl:107)         */
+  HS_ETREE = 3,     /* ErrorException     (factorization.jl:25: node with a single child)                */
+  HS_ESINGULAR = 4, /* SingularException  (LAPACK getrf info > 0 behind every `\` in the reference)       */
+  HS_ECUDA = 5,
+  HS_ENOMEM = 6,
+  HS_ENOTIMPL = 7,
+  HS_ESIZE = 8      /* a front exceeds what the panel kernels cover                                      */
+};
+
+typedef enum { HS_F64 = 0, HS_C64 = 1 } hs_dtype;
+
+/* `SolverOptions` (HierarchicalSolvers.jl:30-40), same field names.  `swlevel` is passed as the user gave it;
+ * negative values are resolved against the tree depth inside hs_factor as factorization.jl:8 does. */
+typedef struct {
+  int64_t swlevel;
+  int64_t swsize;
+  double atol;
+  double rtol;
+  double c_tol;
+  int64_t leafsize;
+  int64_t kest;
+  int64_t stepsize;
+  int32_t verbose;
+  int32_t keep_schur; /* extension: 1 = keep every node's S resident (reference behaviour, FactorNode.S) */
+} hs_opts;
+
+/* Serialized elimination tree, the ragged form of the `.mat` schema that parse_elimtree consumes
+ * (nesteddissection.jl:105-148, util/read_problem.jl:14-20).  Node ids and DOF ids use `index_base`;
+ * `-1` means "none" for fathers/lsons/rsons regardless of the base (nesteddissection.jl:110,122). */
+typedef struct {
+  int64_t nnodes;
+  const int64_t* fathers;
+  const int64_t* lsons;
+  const int64_t* rsons;
+  const int64_t* inter_ptr; /* nnodes+1, 0-based offsets into inter_idx */
+  const int64_t* inter_idx;
+  const int64_t* bound_ptr;
+  const int64_t* bound_idx;
+  int32_t index_base;
+} hs_elimtree;
+
+/* What `symfact!` returns, flattened: the pair (nd, nd_loc) of nesteddissection.jl:29-69.
+ * Nodes are numbered 0..nnodes-1 in post-order (children before parents, root last); `left/right` are node
+ * numbers or -1.  `int/bnd` are global DOF ids, `iloc/bloc` are positions inside the node's own `bnd`
+ * (nd_loc.int / nd_loc.bnd), all using `index_base`. */
+typedef struct {
+  int64_t nnodes;
+  const int64_t* left;
+  const int64_t* right;
+  const int64_t* int_ptr;
+  const int64_t* int_idx;
+  const int64_t* bnd_ptr;
+  const int64_t* bnd_idx;
+  const int64_t* iloc_ptr;
+  const int64_t* iloc_idx;
+  const int64_t* bloc_ptr;
+  const int64_t* bloc_idx;
+  int32_t index_base;
+} hs_tree;
+
+typedef struct hs_ctx hs_ctx;
+typedef struct hs_symbolic hs_symbolic; /* host-side result of hs_symfact (owns the arrays an hs_tree views) */
+typedef struct hs_fac hs_fac;           /* device-resident FactorNode tree                                 */
+
+/* per-phase counters of the last factor / solve, CUDA-event timed on the context's stream */
+typedef struct {
+  int64_t nnodes, nlevels, n;
+  int64_t max_ni, max_nb;
+  double factor_flops;     /* Σ ⅔ni³ + 2ni²nb + 2ni·nb² (×4 complex)                                      */
+  double solve_bytes;      /* esz · Σ (ni² + 2 ni nb) per right-hand side                                 */
+  double extadd_bytes;     /* 2 · esz · Σ nb²                                                            */
+  double front_bytes;      /* device bytes held by the fronts                                            */
+  double ms_analyze, ms_h2d, ms_assemble, ms_panel, ms_trsm, ms_gemm, ms_factor_total;
+  double ms_solve_fwd, ms_solve_bwd, ms_solve_total;
+  int64_t launches_factor, launches_solve;
+  int64_t singular_front, singular_col; /* -1 when the factorization is non-singular                    */
+  int64_t maxrank;
+} hs_stats_t;
+
+typedef enum { HS_GET_D = 0, HS_GET_S = 1, HS_GET_L = 2, HS_GET_R = 3, HS_GET_FRONT = 4, HS_GET_PIV = 5 } hs_which;
+
+int32_t hs_version(void);
+const char* hs_last_error(void);
+
+/* context: one per GPU / host thread.  `stream` may be NULL (library creates its own). */
+int32_t hs_create(hs_ctx** out, int32_t device);
+int32_t hs_set_stream(hs_ctx* ctx, void* cuda_stream);
+int32_t hs_destroy(hs_ctx* ctx);
+/* 1 when the shared library was built with CUDA kernels and a device is usable; never falls back to CPU */
+int32_t hs_device_count(void);
+
+/* ---- symbolic phase, host only -------------------------------------------------------------------
+ * replaces parse_elimtree + symfact! + postorder + permuted!(nd, invperm(perm))
+ * (nesteddissection.jl:105-148, :29-69, :73-79, :82-88; driver order test/rungmres.jl:15-19).
+ * `apply_postorder` != 0 renumbers DOFs by the post-order permutation exactly as rungmres.jl:17-19 does;
+ * the caller must then factor permute(A, perm, perm).  perm is reported with `index_base`. */
+int32_t hs_symfact(const hs_elimtree* et, int32_t apply_postorder, hs_symbolic** out);
+int32_t hs_symbolic_tree(const hs_symbolic* s, hs_tree* tree_out);      /* views into `s` */
+int32_t hs_symbolic_perm(const hs_symbolic* s, const int64_t** perm, int64_t* n);
+int32_t hs_symbolic_depth(const hs_symbolic* s, int64_t* depth);
+int32_t hs_symbolic_free(hs_symbolic* s);
+
+/* ---- numeric factorization -----------------------------------------------------------------------
+ * replaces factor(A, nd, nd_loc, opts; kw...) → FactorNode   (factorization.jl:5-11 and everything below it:
+ * _factor :14-27, _factor_leaf :30-42, _factor_branch :62-75, _assemble_blocks :115-123,
+ * blockfactor/blockldiv/blockrdiv blockmatrix.jl:115-187).
+ * A is CSC (SparseMatrixCSC: colptr n+1, rowval nnz, nzval nnz) with `index_base` of the tree.
+ * `on_device` != 0: colptr/rowval/nzval are device pointers already resident in HBM (0-based int64). */
+int32_t hs_factor(hs_ctx* ctx, hs_dtype dtype, int64_t n, const int64_t* colptr, const int64_t* rowval,
+                  const void* nzval, const hs_tree* tree, const hs_opts* opts, int32_t on_device, hs_fac** out);
+/* same plan and sparsity, new values (the numeric part of `factor` alone) */
+int32_t hs_refactor(hs_fac* fac, const void* nzval, int32_t on_device);
+int32_t hs_factor_free(hs_fac* fac);
+
+/* replaces ldiv!(C, F, B) for vectors and matrices (factornode.jl:62-74: _lsolve! :77, _dsolve! :89,
+ * root Schur solve :72, _rsolve! :83).  B and X may alias.  on_device != 0: B/X are device pointers. */
+int32_t hs_solve(hs_fac* fac, int64_t nrhs, const void* B, int64_t ldb, void* X, int64_t ldx, int32_t on_device);
+
+/* FactorNode field access (factornode.jl:8-22), node numbering of hs_tree.  `dims[2]` receives rows, cols;
+ * call with out == NULL to query dims.  D/S/L/R are returned exactly as the reference defines them
+ * (D = the pivot block A_ii, L = A_bi·A_ii⁻¹, R = A_ii⁻¹·A_ib, S = Schur complement permuted by
+ * [int_loc; bnd_loc]); HS_GET_FRONT returns the raw partially factored front, HS_GET_PIV its pivots (int64). */
+int32_t hs_node_get(hs_fac* fac, int64_t node, hs_which which, void* out, int64_t* dims);
+int32_t hs_maxrank(hs_fac* fac, int64_t* rank);              /* factornode.jl:49-57 */
+int32_t hs_stats(hs_fac* fac, hs_stats_t* out);
+int32_t hs_resolved_swlevel(hs_fac* fac, int64_t* swlevel);  /* factorization.jl:8 */
+
+/* ---- GMRES with the factorization as right preconditioner (test/rungmres.jl:47-48) ---------------
+ * device-resident restarted GMRES (modified Gram-Schmidt, Givens), x0 = 0, stops when the running residual
+ * estimate ≤ reltol·‖b‖ or after maxiter Arnoldi steps.  `fac` may be NULL (no preconditioner).
+ * resnorm must hold maxiter doubles; niter receives the number of Arnoldi steps taken.
+ * colptr == NULL: iterate on the matrix held by `fac` (the one it factored).  on_device != 0: b and x are device
+ * pointers. */
+int32_t hs_gmres(hs_ctx* ctx, hs_dtype dtype, int64_t n, const int64_t* colptr, const int64_t* rowval,
+                 const void* nzval, int32_t index_base, hs_fac* fac, const void* b, void* x, double reltol,
+                 int64_t restart, int64_t maxiter, double* resnorm, int64_t* niter, int32_t* converged,
+                 int32_t on_device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HSOLVE_CUDA_H */

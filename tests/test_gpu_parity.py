@@ -1,0 +1,195 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle on the same seeded inputs.
+Tolerance: 1e-10 relative (Frobenius / 2-norm) — the figure BASELINE.json's north_star states for FP64."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def rel(a, b):
+    d = np.linalg.norm(np.asarray(a) - np.asarray(b))
+    s = np.linalg.norm(np.asarray(b))
+    return d / s if s > 0 else d
+
+
+def both(hs, orc, shape, kind, nmax=100):
+    prob = hs.grid_problem(shape, kind, nmax=nmax)
+    Ap, nd, nd_loc, perm = hs.prepare(prob.A, prob.elim_tree)
+    F = hs.factor(Ap, nd, nd_loc, swlevel=0)
+    Ao, ndo, ndo_loc, _ = orc.prepare(prob.A, prob.elim_tree)
+    Fo = orc.factor(Ao, ndo, ndo_loc)
+    return prob, Ap, F, Fo
+
+
+CASES = [("poisson", (33, 33), 40), ("helmholtz", (33, 33), 40), ("poisson", (65, 65), 100),
+         ("helmholtz", (65, 65), 100), ("poisson", (9, 8, 7), 60), ("helmholtz", (10, 9, 8), 60),
+         ("poisson", (37, 3), 20), ("poisson", (4, 4), 100)]
+
+
+@pytest.mark.parametrize("kind,shape,nmax", CASES)
+def test_every_node_matches_oracle(hs, orc, kind, shape, nmax):
+    """D, L, R, S of every FactorNode (factornode.jl:8-11) against the oracle's."""
+    prob, Ap, F, Fo = both(hs, orc, shape, kind, nmax)
+    onodes = orc.nodes_postorder(Fo)
+    assert len(onodes) == F._hd.nd.nnodes
+    worst = 0.0
+    for k, on in enumerate(onodes):
+        gn = F.node(k)
+        assert np.array_equal(gn.int, on.int) and np.array_equal(gn.bnd, on.bnd)
+        assert np.array_equal(gn.int_loc, on.int_loc) and np.array_equal(gn.bnd_loc, on.bnd_loc)
+        for name, ref in (("D", on.D_dense()), ("L", on.L_dense()), ("R", on.R_dense()), ("S", on.S)):
+            got = getattr(gn, name)
+            assert got.shape == ref.shape, (k, name, got.shape, ref.shape)
+            if ref.size:
+                e = rel(got, ref)
+                worst = max(worst, e)
+                assert e < TOL, (k, name, e)
+    assert hs.maxrank(F) == orc.maxrank(Fo) == 0
+    assert hs.isleaf(F.node(0)) and hs.isbranch(F) or F._hd.nd.nnodes == 1
+
+
+@pytest.mark.parametrize("kind,shape,nmax", CASES)
+def test_ldiv_matches_oracle(hs, orc, kind, shape, nmax):
+    prob, Ap, F, Fo = both(hs, orc, shape, kind, nmax)
+    x = hs.ldiv(F, prob.b)
+    xo = orc.ldiv(Fo, prob.b)
+    assert rel(x, xo) < TOL
+    assert rel(Ap @ x, prob.b) < TOL
+    # 3-argument form writes into C; 2-argument form leaves B untouched (factornode.jl:62-67)
+    b0 = prob.b.copy()
+    C = np.empty_like(x)
+    out = hs.ldiv(C, F, prob.b)
+    assert out is C and np.array_equal(prob.b, b0) and np.array_equal(C, x)
+    # matrices (factornode.jl:68-74)
+    B = np.random.default_rng(7).standard_normal((Ap.shape[0], 3)).astype(x.dtype)
+    X = hs.ldiv(F, B)
+    assert rel(X, orc.ldiv(Fo, B)) < TOL
+
+
+@pytest.mark.parametrize("kind,shape", [("poisson", (65, 65)), ("helmholtz", (65, 65))])
+def test_gmres_iterations_match_oracle(hs, orc, kind, shape):
+    """rungmres.jl:47: same iteration count and residual history as the oracle's GMRES with the oracle's factors."""
+    prob, Ap, F, Fo = both(hs, orc, shape, kind)
+    xo, reso, convo = orc.gmres(Ap, prob.b, Pr=lambda v: orc.ldiv(Fo, v), reltol=1e-9, restart=30, maxiter=30)
+    for dev in (True, False):
+        x, hist = hs.gmres(Ap, prob.b, Pr=F, reltol=1e-9, restart=30, maxiter=30, log=True, device_resident=dev)
+        assert hist.isconverged == convo and hist.iters == len(reso)
+        assert rel(Ap @ x, prob.b) < 1e-9
+        assert rel(x, xo) < 1e-8
+    # no preconditioner: same (non-)convergence history as the oracle to 1e-6 relative per entry
+    x0, h0 = hs.gmres(Ap, prob.b, Pr=None, reltol=1e-9, restart=30, maxiter=30, log=True)
+    _, r0, c0 = orc.gmres(Ap, prob.b, Pr=None, reltol=1e-9, restart=30, maxiter=30)
+    assert h0.iters == len(r0) and h0.isconverged == c0
+    assert np.allclose(h0.resnorm, r0, rtol=1e-6)
+
+
+@pytest.mark.parametrize("kind,shape", [("poisson", (257, 257)), ("helmholtz", (257, 257)), ("poisson", (513, 513)),
+                                        ("helmholtz", (300, 200)), ("poisson", (40, 40, 40))])
+def test_large_residual_property(hs, kind, shape):
+    """Sizes past what the oracle finishes in seconds: the factorization is an exact direct solver
+    (‖A·x − b‖/‖b‖ ≤ 1e-10) and preconditioned GMRES needs ≤ 2 steps; exercises the multi-CTA cluster panels."""
+    prob = hs.grid_problem(shape, kind)
+    Ap, nd, nd_loc, _ = hs.prepare(prob.A, prob.elim_tree)
+    F = hs.factor(Ap, nd, nd_loc, swlevel=0)
+    x = hs.ldiv(F, prob.b)
+    assert rel(Ap @ x, prob.b) < TOL
+    _, hist = hs.gmres(Ap, prob.b, Pr=F, log=True)
+    assert hist.isconverged and hist.iters <= 2
+    # linearity of the solve
+    y = hs.ldiv(F, 2.0 * prob.b)
+    assert rel(y, 2.0 * x) < 1e-12
+    st = F.stats()
+    assert st["factor_flops"] > 0 and st["launches_factor"] > 0 and st["ms_factor_total"] > 0
+
+
+def test_refactor_same_pattern(hs):
+    prob = hs.grid_problem((65, 65), "poisson")
+    Ap, nd, nd_loc, _ = hs.prepare(prob.A, prob.elim_tree)
+    F = hs.factor(Ap, nd, nd_loc, swlevel=0)
+    A2 = Ap.copy()
+    A2.data = A2.data * 3.0
+    F.refactor(A2)
+    x = hs.ldiv(F, prob.b)
+    assert rel(A2 @ x, prob.b) < TOL
+
+
+def _subtree_problem(hs, shape, kind):
+    """The left subtree of a grid problem as a problem of its own: its root keeps a non-empty boundary, which
+    exercises the root Schur solve `C[F.bnd,:] = F.S \\ C[F.bnd,:]` (factornode.jl:72)."""
+    from hsolve_b200.problems import ElimTree, Problem
+    full = hs.grid_problem(shape, kind, nmax=40)
+    et = full.elim_tree
+    root = int(np.nonzero(et.fathers == -1)[0][0])
+    sub_root = int(et.lsons[root]) - 1
+    keep, stack = [], [sub_root]
+    while stack:
+        i = stack.pop()
+        keep.append(i)
+        if et.lsons[i] != -1:
+            stack += [int(et.lsons[i]) - 1, int(et.rsons[i]) - 1]
+    keep = sorted(keep)
+    newid = {old: k + 1 for k, old in enumerate(keep)}
+    dofs = np.unique(np.concatenate([np.concatenate([et.inter(i), et.bound(i)]) for i in keep if et.lsons[i] == -1]))
+    dmap = np.zeros(full.A.shape[0] + 1, dtype=np.int64)
+    dmap[dofs] = np.arange(1, len(dofs) + 1)
+    mp = lambda v: -1 if v == -1 else newid[int(v) - 1]
+    fathers = np.array([-1 if i == sub_root else mp(et.fathers[i]) for i in keep], dtype=np.int64)
+    lsons = np.array([mp(et.lsons[i]) for i in keep], dtype=np.int64)
+    rsons = np.array([mp(et.rsons[i]) for i in keep], dtype=np.int64)
+    iptr = np.concatenate([[0], np.cumsum([len(et.inter(i)) for i in keep])]).astype(np.int64)
+    bptr = np.concatenate([[0], np.cumsum([len(et.bound(i)) for i in keep])]).astype(np.int64)
+    iidx = dmap[np.concatenate([et.inter(i) for i in keep])]
+    bidx = dmap[np.concatenate([et.bound(i) for i in keep])]
+    A = full.A.tocsr()[dofs - 1][:, dofs - 1].tocsc()
+    b = full.b[dofs - 1]
+    return Problem(A, b, ElimTree(fathers, lsons, rsons, iptr, iidx, bptr, bidx))
+
+
+@pytest.mark.parametrize("kind", ["poisson", "helmholtz"])
+def test_nonempty_root_boundary(hs, orc, kind):
+    prob = _subtree_problem(hs, (33, 33), kind)
+    Ap, nd, nd_loc, _ = hs.prepare(prob.A, prob.elim_tree)
+    assert len(nd.node().bnd) > 0
+    F = hs.factor(Ap, nd, nd_loc, swlevel=0)
+    Ao, ndo, ndo_loc, _ = orc.prepare(prob.A, prob.elim_tree)
+    Fo = orc.factor(Ao, ndo, ndo_loc)
+    x, xo = hs.ldiv(F, prob.b), orc.ldiv(Fo, prob.b)
+    assert rel(x, xo) < TOL and rel(Ap @ x, prob.b) < TOL
+    assert rel(F.S, Fo.S) < TOL
+
+
+def test_errors_match_reference_exceptions(hs):
+    prob = hs.grid_problem((17, 17), "poisson", nmax=40)
+    Ap, nd, nd_loc, _ = hs.prepare(prob.A, prob.elim_tree)
+    with pytest.raises(hs.ArgumentError):
+        hs.factor(Ap, nd, nd_loc, swlevel=0, swsize=0)          # chkopts! HierarchicalSolvers.jl:74
+    Z = Ap.copy()
+    Z.data[:] = 0.0
+    with pytest.raises(hs.SingularException):                     # `D \ …` on a singular pivot block
+        hs.factor(Z, nd, nd_loc, swlevel=0)
+    F = hs.factor(Ap, nd, nd_loc, swlevel=0)
+    with pytest.raises(hs.DimensionMismatch):
+        hs.ldiv(F, np.zeros(Ap.shape[0] + 1))
+    with pytest.raises(NotImplementedError):
+        hs.factor(Ap, nd, nd_loc, swlevel=3, swsize=1)           # compressed path not built yet
+
+
+def test_pivoting_is_exercised(hs, orc):
+    """A matrix whose pivot blocks need row interchanges: scale rows of an indefinite Helmholtz operator so that the
+    diagonal is tiny; the result must still match the oracle (LAPACK partial pivoting) to 1e-10."""
+    prob = hs.grid_problem((33, 33), "helmholtz", nmax=40)
+    A = prob.A.tolil()
+    rng = np.random.default_rng(3)
+    idx = rng.choice(A.shape[0], size=200, replace=False)
+    for i in idx:
+        A[i, i] = 1e-9 * (1 + 1j)
+    prob.A = A.tocsc()
+    Ap, nd, nd_loc, _ = hs.prepare(prob.A, prob.elim_tree)
+    F = hs.factor(Ap, nd, nd_loc, swlevel=0)
+    Ao, ndo, ndo_loc, _ = orc.prepare(prob.A, prob.elim_tree)
+    Fo = orc.factor(Ao, ndo, ndo_loc)
+    piv_moved = sum(int(np.any(F.node(k).piv != np.arange(len(F.node(k).piv)))) for k in range(nd.nnodes))
+    assert piv_moved > 0
+    x, xo = hs.ldiv(F, prob.b), orc.ldiv(Fo, prob.b)
+    assert rel(Ap @ x, prob.b) < 1e-9 and rel(x, xo) < 1e-8
