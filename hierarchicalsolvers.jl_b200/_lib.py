@@ -42,7 +42,8 @@ class hs_stats_t(C.Structure):
                 ("ms_gemm", C.c_double), ("ms_factor_total", C.c_double), ("ms_solve_fwd", C.c_double),
                 ("ms_solve_bwd", C.c_double), ("ms_solve_total", C.c_double), ("launches_factor", C.c_int64),
                 ("launches_solve", C.c_int64), ("singular_front", C.c_int64), ("singular_col", C.c_int64),
-                ("maxrank", C.c_int64)]
+                ("maxrank", C.c_int64), ("gemm_flops", C.c_double), ("gemm_launches", C.c_int64),
+                ("panel_launches", C.c_int64)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -56,6 +57,8 @@ PROTOTYPES = [
     ("hs_set_stream", C.c_int32, [C.c_void_p, C.c_void_p]),
     ("hs_destroy", C.c_int32, [C.c_void_p]),
     ("hs_device_count", C.c_int32, []),
+    ("hs_set_profile", C.c_int32, [C.c_void_p, C.c_int32]),
+    ("hs_launch_count", C.c_int32, [C.c_void_p, i64p]),
     ("hs_symfact", C.c_int32, [C.POINTER(hs_elimtree), C.c_int32, C.POINTER(C.c_void_p)]),
     ("hs_symbolic_tree", C.c_int32, [C.c_void_p, C.POINTER(hs_tree)]),
     ("hs_symbolic_perm", C.c_int32, [C.c_void_p, C.POINTER(i64p), i64p]),

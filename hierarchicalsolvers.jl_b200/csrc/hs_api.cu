@@ -74,6 +74,18 @@ extern "C" int32_t hs_set_stream(hs_ctx* ctx, void* s) {
   return HS_OK;
 }
 
+extern "C" int32_t hs_set_profile(hs_ctx* ctx, int32_t on) {
+  if (!ctx) return hs_fail(HS_EARG, "hs_set_profile: null context");
+  ctx->profile = on != 0;
+  return HS_OK;
+}
+
+extern "C" int32_t hs_launch_count(hs_ctx* ctx, int64_t* count) {
+  if (!ctx || !count) return hs_fail(HS_EARG, "hs_launch_count: null argument");
+  *count = ctx->launches;
+  return HS_OK;
+}
+
 extern "C" int32_t hs_destroy(hs_ctx* ctx) {
   if (!ctx) return HS_OK;
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -148,8 +160,20 @@ template <typename T> static void factor_level(hs_fac* f, const Level& L) {
       dim3 grid(nact, tiles, tiles);
       k_gemm<T><<<grid, 128, smem_gemm, st>>>(f->d_fronts, (T*)f->pool, L.f0, j0, W);
       CUDA_OK(cudaGetLastError());
+      ++f->stats.gemm_launches;
     }
+    ++f->stats.panel_launches;
     f->stats.launches_factor += 3;
+  }
+  {  // flops the GEMM launches of this level issue: Σ_steps 2·(n−j0−wc)²·wc per front
+    const double cx = f->dtype == HS_C64 ? 4.0 : 1.0;
+    for (int i = L.f0; i < L.f1; ++i) {
+      const Front& fr = f->fronts[i];
+      for (int j0 = 0; j0 < fr.ni; j0 += W) {
+        const double wc = std::min(W, fr.ni - j0), mt = fr.n - j0 - wc;
+        f->stats.gemm_flops += cx * 2.0 * mt * mt * wc;
+      }
+    }
   }
   if (L.max_ni > 0) {
     const size_t sm = (size_t)L.max_ni * sizeof(int);
@@ -166,6 +190,8 @@ template <typename T> static void numeric(hs_fac* f) {
   hs_stats_t& s = f->stats;
   s.ms_assemble = s.ms_panel = s.ms_trsm = s.ms_gemm = 0;
   s.launches_factor = 0;
+  s.gemm_launches = s.panel_launches = 0;
+  s.gemm_flops = 0;
   CUDA_OK(cudaEventRecord(f->ev0, st));
   CUDA_OK(cudaMemsetAsync(f->d_info, 0, 4 * sizeof(int), st));
   for (size_t li = 0; li < f->levels.size(); ++li) {
@@ -193,6 +219,7 @@ template <typename T> static void numeric(hs_fac* f) {
     factor_level<T>(f, L);
   }
   CUDA_OK(cudaEventRecord(f->ev1, st));
+  f->ctx->launches += s.launches_factor;
   int info[4];
   CUDA_OK(cudaMemcpyAsync(info, f->d_info, sizeof(info), cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaStreamSynchronize(st));
@@ -551,6 +578,7 @@ template <typename T> static void solve_impl(hs_fac* f, int64_t nrhs, const void
   }
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaEventRecord(f->ev1, st));
+  f->ctx->launches += s.launches_solve;
   CUDA_OK(cudaMemcpy2DAsync(X, (size_t)ldx * sizeof(T), x, (size_t)f->n * sizeof(T), (size_t)f->n * sizeof(T), nrhs, kout, st));
   CUDA_OK(cudaStreamSynchronize(st));
   float ms = 0;
@@ -606,8 +634,26 @@ template <typename T> static void node_get_impl(hs_fac* f, int64_t node, hs_whic
     for (int64_t q = f->bloc_ptr[node]; q < f->bloc_ptr[node + 1]; ++q) perm.push_back((int)f->bloc_idx[q]);
     const int np = (int)perm.size();
     if (dims) { dims[0] = np; dims[1] = np; }
+    std::vector<T> Sd;
+    if (f->pseudo_front >= 0 && f->node2front[node] == f->root_front && nb > 0) {
+      // the root's Schur block was LU-factored in place for the boundary solve (factornode.jl:72): S = Pᵀ·L·U
+      const Front& pf = f->fronts[f->pseudo_front];
+      std::vector<int> pv(nb);
+      CUDA_OK(cudaMemcpy(pv.data(), f->d_ipiv + pf.ioff, (size_t)nb * sizeof(int), cudaMemcpyDeviceToHost));
+      Sd.assign((size_t)nb * nb, hs_zero<T>());
+      for (int j = 0; j < nb; ++j)
+        for (int k = 0; k <= j; ++k) {
+          const T u = Fm(ni + k, ni + j);
+          Sd[(size_t)j * nb + k] = hs_add(Sd[(size_t)j * nb + k], u);
+          for (int i = k + 1; i < nb; ++i) Sd[(size_t)j * nb + i] = hs_fma(Sd[(size_t)j * nb + i], Fm(ni + i, ni + k), u);
+        }
+      for (int k = nb - 1; k >= 0; --k)
+        if (pv[k] != k)
+          for (int j = 0; j < nb; ++j) std::swap(Sd[(size_t)j * nb + k], Sd[(size_t)j * nb + pv[k]]);
+    }
+    auto Sm = [&](int i, int j) -> T { return Sd.empty() ? Fm(ni + i, ni + j) : Sd[(size_t)j * nb + i]; };
     for (int j = 0; j < np; ++j)
-      for (int i = 0; i < np; ++i) o[(size_t)j * np + i] = Fm(ni + perm[i], ni + perm[j]);
+      for (int i = 0; i < np; ++i) o[(size_t)j * np + i] = Sm(perm[i], perm[j]);
     return;
   }
   if (which == HS_GET_D) {

@@ -26,6 +26,7 @@ struct hs_ctx {
   bool own_stream = false;
   int max_cluster = 8;
   bool profile = false;
+  long long launches = 0;
 };
 
 // ------------------------------------------------------------------------------------------------

@@ -156,6 +156,7 @@ void gmres_impl(hs_ctx* ctx, hs_fac* f, long long n, const long long* rptr, cons
   alloc((void**)&dres, sizeof(cplx));
   const unsigned gb = (unsigned)((n + 255) / 256);
   auto dot = [&](const T* a, const T* bb) -> zc {
+    ctx->launches += 2;
     k_dot_partial<T><<<RED_BLOCKS, RED_THREADS, 0, st>>>(n, a, bb, part);
     k_dot_final<<<1, RED_THREADS, 0, st>>>(RED_BLOCKS, part, dres);
     cplx h;
@@ -164,6 +165,7 @@ void gmres_impl(hs_ctx* ctx, hs_fac* f, long long n, const long long* rptr, cons
     return zc(h.x, h.y);
   };
   auto axpy = [&](zc alpha, const T* xx, T* yy, int assign) {
+    ++ctx->launches;
     k_axpy<T><<<gb, 256, 0, st>>>(n, cplx{alpha.real(), alpha.imag()}, xx, yy, assign);
   };
   auto precond = [&](const T* in, T* out) {
@@ -174,7 +176,7 @@ void gmres_impl(hs_ctx* ctx, hs_fac* f, long long n, const long long* rptr, cons
       CUDA_OK(cudaMemcpyAsync(out, in, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, st));
     }
   };
-  auto matvec = [&](const T* in, T* out) { k_spmv_csr<T><<<gb, 256, 0, st>>>(n, rptr, ccol, cval, in, out); };
+  auto matvec = [&](const T* in, T* out) { ++ctx->launches; k_spmv_csr<T><<<gb, 256, 0, st>>>(n, rptr, ccol, cval, in, out); };
 
   CUDA_OK(cudaMemcpyAsync(bdev, b_host, (size_t)n * sizeof(T), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
   CUDA_OK(cudaMemsetAsync(x, 0, (size_t)n * sizeof(T), st));

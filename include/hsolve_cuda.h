@@ -106,6 +106,8 @@ typedef struct {
   int64_t launches_factor, launches_solve;
   int64_t singular_front, singular_col; /* -1 when the factorization is non-singular                    */
   int64_t maxrank;
+  double gemm_flops;       /* flops issued by the Schur/trailing-update GEMM launches (2·m²·k per step, ×4 complex) */
+  int64_t gemm_launches, panel_launches;
 } hs_stats_t;
 
 typedef enum { HS_GET_D = 0, HS_GET_S = 1, HS_GET_L = 2, HS_GET_R = 3, HS_GET_FRONT = 4, HS_GET_PIV = 5 } hs_which;
@@ -117,6 +119,10 @@ const char* hs_last_error(void);
 int32_t hs_create(hs_ctx** out, int32_t device);
 int32_t hs_set_stream(hs_ctx* ctx, void* cuda_stream);
 int32_t hs_destroy(hs_ctx* ctx);
+/* per-phase CUDA-event timing (serialises the stream; off by default, HS_PROFILE=1 turns it on at hs_create) */
+int32_t hs_set_profile(hs_ctx* ctx, int32_t on);
+/* number of kernels this context has launched so far */
+int32_t hs_launch_count(hs_ctx* ctx, int64_t* count);
 /* 1 when the shared library was built with CUDA kernels and a device is usable; never falls back to CPU */
 int32_t hs_device_count(void);
 

@@ -1,0 +1,25 @@
+"""One factorization + one preconditioner application, for ncu launch lists / captures.
+    python tools/profile_run.py [grid] [kind]"""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import _pkg  # noqa: E402
+
+hs = _pkg.load()
+grid = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+kind = sys.argv[2] if len(sys.argv) > 2 else "poisson"
+prob = hs.grid_problem((grid, grid), kind)
+Ap, nd, nd_loc, perm = hs.prepare(prob.A, prob.elim_tree)
+t0 = time.perf_counter()
+F = hs.factor(Ap, nd, nd_loc, swlevel=0)
+t1 = time.perf_counter()
+x = hs.ldiv(F, prob.b)
+t2 = time.perf_counter()
+st = F.stats()
+print(f"grid {grid} {kind}: factor {st['ms_factor_total']:.2f} ms (call {1e3 * (t1 - t0):.0f} ms), solve {st['ms_solve_total']:.2f} ms "
+      f"(call {1e3 * (t2 - t1):.0f} ms), resid {np.linalg.norm(Ap @ x - prob.b) / np.linalg.norm(prob.b):.2e}, "
+      f"{st['factor_flops'] / st['ms_factor_total'] / 1e9:.2f} TFLOP/s")
