@@ -55,6 +55,7 @@ extern "C" int32_t hs_create(hs_ctx** out, int32_t device) {
   // opt in to 16-CTA clusters for the tall panels, and to >48 KB dynamic shared memory for the DMMA tiles
   hs_panel_setup_f64();
   hs_panel_setup_c64();
+  hs_solve_setup();
   c->max_cluster = getenv("HS_MAX_CLUSTER") ? atoi(getenv("HS_MAX_CLUSTER")) : 16;
   CUDA_OK(cudaFuncSetAttribute(k_gemm<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (GemmCfg<double>::KC * GemmCfg<double>::LDA + 64 * GemmCfg<double>::LDB) * (int)sizeof(double)));
@@ -181,6 +182,9 @@ template <typename T> static void factor_level(hs_fac* f, const Level& L) {
     k_rperm<<<L.f1 - L.f0, 256, sm, st>>>(f->d_fronts, f->d_ipiv, f->d_rperm, L.f0);
     CUDA_OK(cudaGetLastError());
     f->stats.launches_factor += 1;
+    // solve preparation: invert the diagonal blocks of L11/U11 in place (see hs_solve.cu)
+    PhaseTimer t(f, &f->stats.ms_solve_prep);
+    hs_solve_prep(f, L);
   }
 }
 
@@ -188,7 +192,7 @@ template <typename T> static void numeric(hs_fac* f) {
   cudaStream_t st = f->ctx->stream;
   T* pool = (T*)f->pool;
   hs_stats_t& s = f->stats;
-  s.ms_assemble = s.ms_panel = s.ms_trsm = s.ms_gemm = 0;
+  s.ms_assemble = s.ms_panel = s.ms_trsm = s.ms_gemm = s.ms_solve_prep = 0;
   s.launches_factor = 0;
   s.gemm_launches = s.panel_launches = 0;
   s.gemm_flops = 0;
@@ -563,19 +567,7 @@ template <typename T> static void solve_impl(hs_fac* f, int64_t nrhs, const void
   CUDA_OK(cudaEventRecord(f->ev0, st));
   hs_stats_t& s = f->stats;
   s.launches_solve = 0;
-  const long long ws = f->max_level_idx;
-  for (size_t li = 0; li < f->levels.size(); ++li) {  // post-order: deepest level first
-    const Level& L = f->levels[li];
-    dim3 grid(L.f1 - L.f0, (unsigned)nrhs);
-    k_solve_fwd<T><<<grid, 256, 0, st>>>(f->d_fronts, (const T*)f->pool, f->d_gidx, f->d_rperm, x, f->n, (T*)f->d_work, ws, L.ioff0, L.f0);
-    ++s.launches_solve;
-  }
-  for (size_t li = f->levels.size(); li-- > 0;) {  // pre-order: root first
-    const Level& L = f->levels[li];
-    dim3 grid(L.f1 - L.f0, (unsigned)nrhs);
-    k_solve_bwd<T><<<grid, 256, 0, st>>>(f->d_fronts, (const T*)f->pool, f->d_gidx, x, f->n, (T*)f->d_work, ws, L.ioff0, L.f0);
-    ++s.launches_solve;
-  }
+  hs_solve_run(f, nrhs, x);
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaEventRecord(f->ev1, st));
   f->ctx->launches += s.launches_solve;
@@ -625,6 +617,36 @@ template <typename T> static void node_get_impl(hs_fac* f, int64_t node, hs_whic
   CUDA_OK(cudaStreamSynchronize(st));
   auto Fm = [&](int i, int j) -> T& { return Fh[(size_t)j * n + i]; };
   T* o = (T*)out;
+  auto undo_prep = [&](int off, int m) {
+    // the solve preparation replaced the DB×DB diagonal blocks of L11/U11 by their inverses: invert them back
+    const int DB = hs_solve_block(f->dtype);
+    for (int b0 = 0; b0 < m; b0 += DB) {
+      const int db = std::min(DB, m - b0);
+      std::vector<T> X((size_t)db * db), Y((size_t)db * db, hs_zero<T>());
+      for (int j = 0; j < db; ++j) for (int i = 0; i < db; ++i) X[(size_t)j * db + i] = Fm(off + b0 + i, off + b0 + j);
+      // L = (Linv)⁻¹, unit lower: forward substitution column by column
+      for (int j = 0; j < db; ++j)
+        for (int i = j + 1; i < db; ++i) {
+          T sacc = X[(size_t)j * db + i];
+          for (int k = j + 1; k < i; ++k) sacc = hs_fma(sacc, X[(size_t)k * db + i], Y[(size_t)j * db + k]);
+          Y[(size_t)j * db + i] = hs_sub(hs_zero<T>(), sacc);
+        }
+      // U = (Uinv)⁻¹, upper: back substitution column by column
+      for (int j = 0; j < db; ++j) {
+        Y[(size_t)j * db + j] = hs_recip(X[(size_t)j * db + j]);
+        for (int i = j - 1; i >= 0; --i) {
+          T sacc = hs_zero<T>();
+          for (int k = i + 1; k <= j; ++k) sacc = hs_fma(sacc, X[(size_t)k * db + i], Y[(size_t)j * db + k]);
+          Y[(size_t)j * db + i] = hs_sub(hs_zero<T>(), hs_mul(sacc, hs_recip(X[(size_t)i * db + i])));
+        }
+      }
+      for (int j = 0; j < db; ++j) for (int i = 0; i < db; ++i) Fm(off + b0 + i, off + b0 + j) = Y[(size_t)j * db + i];
+    }
+  };
+  if (which != HS_GET_PIV) {
+    undo_prep(0, ni);
+    if (f->pseudo_front >= 0 && f->node2front[node] == f->root_front) undo_prep(ni, nb);
+  }
   if (which == HS_GET_FRONT) { std::memcpy(out, Fh.data(), Fh.size() * sizeof(T)); return; }
   if (which == HS_GET_PIV) { int64_t* po = (int64_t*)out; for (int i = 0; i < ni; ++i) po[i] = piv[i]; return; }
   if (which == HS_GET_S) {

@@ -94,3 +94,9 @@ inline int hs_panel_width(const hs_fac* f, int max_n) {
 inline void hs_panel_launch(hs_fac* f, int W, int f0, int nact, int j0, int m) {
   if (f->dtype == HS_F64) hs_panel_launch_f64(f, W, f0, nact, j0, m); else hs_panel_launch_c64(f, W, f0, nact, j0, m);
 }
+
+// hs_solve.cu
+void hs_solve_setup();
+int hs_solve_block(hs_dtype dt);
+void hs_solve_prep(hs_fac* f, const Level& L);
+void hs_solve_run(hs_fac* f, int64_t nrhs, void* x);

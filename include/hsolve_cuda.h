@@ -108,6 +108,7 @@ typedef struct {
   int64_t maxrank;
   double gemm_flops;       /* flops issued by the Schur/trailing-update GEMM launches (2·m²·k per step, ×4 complex) */
   int64_t gemm_launches, panel_launches;
+  double ms_solve_prep;    /* in-place inversion of the diagonal blocks of L11/U11 (part of the factor time) */
 } hs_stats_t;
 
 typedef enum { HS_GET_D = 0, HS_GET_S = 1, HS_GET_L = 2, HS_GET_R = 3, HS_GET_FRONT = 4, HS_GET_PIV = 5 } hs_which;
