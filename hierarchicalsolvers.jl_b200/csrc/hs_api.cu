@@ -57,10 +57,9 @@ extern "C" int32_t hs_create(hs_ctx** out, int32_t device) {
   hs_panel_setup_c64();
   hs_solve_setup();
   c->max_cluster = getenv("HS_MAX_CLUSTER") ? atoi(getenv("HS_MAX_CLUSTER")) : 16;
-  CUDA_OK(cudaFuncSetAttribute(k_gemm<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (GemmCfg<double>::KC * GemmCfg<double>::LDA + 64 * GemmCfg<double>::LDB) * (int)sizeof(double)));
-  CUDA_OK(cudaFuncSetAttribute(k_gemm<cplx>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (GemmCfg<cplx>::KC * GemmCfg<cplx>::LDA + 64 * GemmCfg<cplx>::LDB) * (int)sizeof(cplx)));
+  if (getenv("HS_OUTER_BLOCK")) c->outer_block = std::max(1, atoi(getenv("HS_OUTER_BLOCK")));
+  CUDA_OK(cudaFuncSetAttribute(k_gemm<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes<double>()));
+  CUDA_OK(cudaFuncSetAttribute(k_gemm<cplx>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes<cplx>()));
   CUDA_OK(cudaFuncSetAttribute(k_rperm, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   *out = c;
   return HS_OK;
@@ -121,50 +120,86 @@ template <typename T> struct PanelW;  // widest register tile per scalar type
 template <> struct PanelW<double> { static constexpr int W0 = 64; };
 template <> struct PanelW<cplx> { static constexpr int W0 = 32; };
 
-template <typename T, int W> static void launch_trsm_w(hs_fac* f, int f0, int nact, int j0, int max_n) {
-  dim3 grid(nact, (max_n + 127) / 128);
-  k_swap_trsm<T, W><<<grid, 128, 0, f->ctx->stream>>>(f->d_fronts, (T*)f->pool, f->d_ipiv, f0, j0);
+template <typename T, int W> static void launch_trsm_w(hs_fac* f, int f0, int nact, int J0, int j0, int NB, int cmode, int max_cols) {
+  dim3 grid(nact, (max_cols + 127) / 128);
+  k_swap_trsm<T, W><<<grid, 128, 0, f->ctx->stream>>>(f->d_fronts, (T*)f->pool, f->d_ipiv, f0, J0, j0, NB, cmode);
   CUDA_OK(cudaGetLastError());
 }
 
-template <typename T> static void trsm_dispatch(hs_fac* f, int W, int f0, int nact, int j0, int max_n) {
+template <typename T> static void trsm_dispatch(hs_fac* f, int W, int f0, int nact, int J0, int j0, int NB, int cmode, int max_cols) {
   constexpr int W0 = PanelW<T>::W0;
-  if (W == W0) launch_trsm_w<T, W0>(f, f0, nact, j0, max_n);
-  else if (W == W0 / 2) launch_trsm_w<T, W0 / 2>(f, f0, nact, j0, max_n);
-  else if (W == W0 / 4) launch_trsm_w<T, W0 / 4>(f, f0, nact, j0, max_n);
-  else launch_trsm_w<T, W0 / 8>(f, f0, nact, j0, max_n);
+  if (max_cols <= 0) return;
+  if (W == W0) launch_trsm_w<T, W0>(f, f0, nact, J0, j0, NB, cmode, max_cols);
+  else if (W == W0 / 2) launch_trsm_w<T, W0 / 2>(f, f0, nact, J0, j0, NB, cmode, max_cols);
+  else if (W == W0 / 4) launch_trsm_w<T, W0 / 4>(f, f0, nact, J0, j0, NB, cmode, max_cols);
+  else launch_trsm_w<T, W0 / 8>(f, f0, nact, J0, j0, NB, cmode, max_cols);
+  ++f->stats.launches_factor;
 }
 
-// partial LU of all fronts of one level (pivot block + Schur update), batched over the level
+// partial LU of all fronts of one level (pivot block + Schur update), batched over the level.
+// Two-level blocking: outer blocks of NB pivot columns, inner register-resident panels of width W.
 template <typename T> static void factor_level(hs_fac* f, const Level& L) {
   cudaStream_t st = f->ctx->stream;
   const int W = hs_panel_width(f, L.max_n);
   if (W < 0) throw hs_error(HS_ESIZE, "front with " + std::to_string(L.max_n) + " rows exceeds the panel kernels");
-  constexpr int smem_gemm = (GemmCfg<T>::KC * GemmCfg<T>::LDA + 64 * GemmCfg<T>::LDB) * (int)sizeof(T);
-  for (int j0 = 0; j0 < L.max_ni; j0 += W) {
-    // fronts are sorted by ni descending: the active ones (ni > j0) are a prefix
-    const int nact = (int)(std::partition_point(L.ni_sorted.begin(), L.ni_sorted.end(), [&](int v) { return v > j0; }) -
-                           L.ni_sorted.begin());
-    if (nact == 0) break;
-    const int m = L.max_n - j0;
-    {
-      PhaseTimer t(f, &f->stats.ms_panel);
-      hs_panel_launch(f, W, L.f0, nact, j0, m);
+  const int NB = std::max(W, f->ctx->outer_block / W * W);
+  constexpr int smem_gemm = gemm_smem_bytes<T>();
+  using Cfg = GemmCfg<T>;
+  auto nactive = [&](int j) {
+    // fronts are sorted by ni descending: the active ones (ni > j) are a prefix
+    return (int)(std::partition_point(L.ni_sorted.begin(), L.ni_sorted.end(), [&](int v) { return v > j; }) - L.ni_sorted.begin());
+  };
+  auto gemm = [&](int nact, int J0, int j0, int mode, int mrows, int mcols) {
+    if (nact <= 0 || mrows <= 0 || mcols <= 0) return;
+    PhaseTimer t(f, &f->stats.ms_gemm);
+    dim3 grid(nact, (mrows + Cfg::TM - 1) / Cfg::TM + 1, (mcols + Cfg::TN - 1) / Cfg::TN);
+    k_gemm<T><<<grid, 256, smem_gemm, st>>>(f->d_fronts, (T*)f->pool, L.f0, J0, j0, NB, W, mode);
+    CUDA_OK(cudaGetLastError());
+    ++f->stats.gemm_launches;
+    ++f->stats.launches_factor;
+  };
+  for (int J0 = 0; J0 < L.max_ni; J0 += NB) {
+    const int JE = std::min(J0 + NB, L.max_ni);
+    // phase A: factor the block's columns; interchanges, solves and updates stay inside the block
+    for (int j0 = J0; j0 < JE; j0 += W) {
+      const int nact = nactive(j0);
+      if (nact == 0) break;
+      const int m = L.max_n - j0;
+      {
+        PhaseTimer t(f, &f->stats.ms_panel);
+        hs_panel_launch(f, W, L.f0, nact, j0, m);
+        ++f->stats.panel_launches;
+        ++f->stats.launches_factor;
+      }
+      {
+        PhaseTimer t(f, &f->stats.ms_trsm);
+        trsm_dispatch<T>(f, W, L.f0, nact, J0, j0, NB, 0, JE - J0);
+      }
+      gemm(nact, J0, j0, 0, m, JE - j0);
     }
-    if (m > 1) {
-      PhaseTimer t(f, &f->stats.ms_trsm);
-      trsm_dispatch<T>(f, W, L.f0, nact, j0, L.max_n);
+    // phase B: the columns outside the block: all interchanges first, then solve / update sub-block by sub-block
+    const int nactB = nactive(J0);
+    const int mB = L.max_n - J0 - 1;  // at least one pivot column is gone
+    if (nactB > 0 && L.max_n > 1) {
+      {
+        PhaseTimer t(f, &f->stats.ms_trsm);
+        dim3 grid(nactB, (L.max_n + 127) / 128);
+        k_laswp<T><<<grid, 128, 0, st>>>(f->d_fronts, (T*)f->pool, f->d_ipiv, L.f0, J0, NB);
+        CUDA_OK(cudaGetLastError());
+        ++f->stats.launches_factor;
+      }
+      for (int j0 = J0; j0 < JE; j0 += W) {
+        const int nact = nactive(j0);
+        if (nact == 0) break;
+        {
+          PhaseTimer t(f, &f->stats.ms_trsm);
+          trsm_dispatch<T>(f, W, L.f0, nact, J0, j0, NB, 1, mB);
+        }
+        gemm(nact, J0, j0, 2, JE - j0, mB);
+      }
+      // phase C: the big update with K = BE − J0
+      gemm(nactB, J0, J0, 1, mB, mB);
     }
-    if (m > 1) {
-      PhaseTimer t(f, &f->stats.ms_gemm);
-      const int tiles = (m + 63) / 64;
-      dim3 grid(nact, tiles, tiles);
-      k_gemm<T><<<grid, 128, smem_gemm, st>>>(f->d_fronts, (T*)f->pool, L.f0, j0, W);
-      CUDA_OK(cudaGetLastError());
-      ++f->stats.gemm_launches;
-    }
-    ++f->stats.panel_launches;
-    f->stats.launches_factor += 3;
   }
   {  // flops the GEMM launches of this level issue: Σ_steps 2·(n−j0−wc)²·wc per front
     const double cx = f->dtype == HS_C64 ? 4.0 : 1.0;
@@ -172,7 +207,7 @@ template <typename T> static void factor_level(hs_fac* f, const Level& L) {
       const Front& fr = f->fronts[i];
       for (int j0 = 0; j0 < fr.ni; j0 += W) {
         const double wc = std::min(W, fr.ni - j0), mt = fr.n - j0 - wc;
-        f->stats.gemm_flops += cx * 2.0 * mt * mt * wc;
+        f->stats.gemm_flops += cx * 2.0 * mt * mt * wc;  // same total however the update is blocked
       }
     }
   }

@@ -27,6 +27,7 @@ struct hs_ctx {
   int max_cluster = 8;
   bool profile = false;
   long long launches = 0;
+  int outer_block = 256;  // NB of the two-level blocked LU (HS_OUTER_BLOCK)
 };
 
 // ------------------------------------------------------------------------------------------------

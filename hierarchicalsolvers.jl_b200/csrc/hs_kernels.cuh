@@ -110,18 +110,25 @@ __global__ void k_rperm(const Front* __restrict__ fronts, const int* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
-// row interchanges outside the panel + U row panel:  U12 = L11⁻¹ · (P·A)(j0:j0+wc, j0+wc:n)
-// one thread per front column
+// row interchanges + U row panel:  U(j0:j0+wc, c) = L11⁻¹·(P·A)(j0:j0+wc, c);  one thread per front column.
+// Two-level blocked LU (outer block [J0, BE), BE = min(J0+NB, ni)):
+//   cmode 0 (while the block is being factored): the interchanges of panel j0 go to the block's own columns
+//            [J0, j0) ∪ [j0+wc, BE); the columns right of the panel inside the block also get the triangular solve.
+//   cmode 1 (after the block): columns [BE, n) get the triangular solve of sub-block j0 — their interchanges were
+//            applied for the whole block at once by k_laswp (they must all precede the first solve).
 // ------------------------------------------------------------------------------------------------
 template <typename T, int W>
 __global__ void __launch_bounds__(128) k_swap_trsm(const Front* __restrict__ fronts, T* __restrict__ pool,
-                                                    const int* __restrict__ ipiv, int f0, int j0) {
+                                                    const int* __restrict__ ipiv, int f0, int J0, int j0, int NB,
+                                                    int cmode) {
   const int fi = f0 + blockIdx.x;
   const Front fr = fronts[fi];
   if (fr.ni <= j0) return;
   const int wc = min(W, fr.ni - j0);
-  const int nother = fr.n - wc;
-  if ((int)(blockIdx.y * blockDim.x) >= nother) return;
+  const int BE = min(J0 + NB, fr.ni);
+  const int nleft = cmode == 0 ? j0 - J0 : 0;
+  const int ncols = cmode == 0 ? nleft + (BE - j0 - wc) : fr.n - BE;
+  if ((int)(blockIdx.y * blockDim.x) >= ncols) return;
   T* F = pool + fr.off;
   __shared__ T sL[W * W];
   __shared__ int spiv[W];
@@ -132,14 +139,23 @@ __global__ void __launch_bounds__(128) k_swap_trsm(const Front* __restrict__ fro
   if (threadIdx.x < W) spiv[threadIdx.x] = threadIdx.x < wc ? ipiv[fr.ioff + j0 + threadIdx.x] : 0;
   __syncthreads();
   const int cc = blockIdx.y * blockDim.x + threadIdx.x;
-  if (cc >= nother) return;
-  const int c = cc < j0 ? cc : cc + wc;
-  T* col = F + (long long)c * fr.ld;
-  for (int j = 0; j < wc; ++j) {
-    const int p = spiv[j];
-    if (p != j0 + j) { const T t = col[j0 + j]; col[j0 + j] = col[p]; col[p] = t; }
+  if (cc >= ncols) return;
+  int c;
+  bool solve = true;
+  if (cmode == 0) {
+    solve = cc >= nleft;
+    c = solve ? j0 + wc + (cc - nleft) : J0 + cc;
+  } else {
+    c = BE + cc;
   }
-  if (c < j0) return;
+  T* col = F + (long long)c * fr.ld;
+  if (cmode == 0) {
+    for (int j = 0; j < wc; ++j) {
+      const int p = spiv[j];
+      if (p != j0 + j) { const T t = col[j0 + j]; col[j0 + j] = col[p]; col[p] = t; }
+    }
+  }
+  if (!solve) return;
   T x[W];
 #pragma unroll
   for (int i = 0; i < W; ++i) x[i] = i < wc ? col[j0 + i] : hs_zero<T>();
@@ -156,86 +172,192 @@ __global__ void __launch_bounds__(128) k_swap_trsm(const Front* __restrict__ fro
     if (i < wc) col[j0 + i] = x[i];
 }
 
+// interchanges of a whole outer block [J0, BE) applied to the columns outside it, [0, J0) ∪ [BE, n)
+template <typename T>
+__global__ void __launch_bounds__(128) k_laswp(const Front* __restrict__ fronts, T* __restrict__ pool,
+                                                const int* __restrict__ ipiv, int f0, int J0, int NB) {
+  const Front fr = fronts[f0 + blockIdx.x];
+  if (fr.ni <= J0) return;
+  const int BE = min(J0 + NB, fr.ni);
+  const int ncols = J0 + fr.n - BE;
+  const int cc = blockIdx.y * blockDim.x + threadIdx.x;
+  if (cc >= ncols) return;
+  const int c = cc < J0 ? cc : BE + (cc - J0);
+  T* col = pool + fr.off + (long long)c * fr.ld;
+  const int* pv = ipiv + fr.ioff;
+  for (int j = J0; j < BE; ++j) {
+    const int p = pv[j];
+    if (p != j) { const T t = col[j]; col[j] = col[p]; col[p] = t; }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
-// Schur / trailing update on the FP64 tensor cores:  C(j0+wc:n, j0+wc:n) -= F(j0+wc:n, j0:j0+wc)·F(j0:j0+wc, j0+wc:n)
-// DMMA m8n8k4; complex = 4 real DMMAs on interleaved operands.  64×64 tile per CTA, 4 warps of 32×32.
+// Schur / trailing update on the FP64 tensor cores:  C -= A·B  with A = L panel, B = U row panel of the same front.
+// DMMA m8n8k4 (the native FP64 MMA shape on sm_100a: `DMMA.8x8x4`); complex = 4 real DMMAs on interleaved operands.
+// 128×128 (f64) / 128×64 (c64) CTA tile, 8 warps, K in chunks staged by a 4-deep cp.async pipeline.
+//
+// Two-level blocking: inside an outer block [J0, BE) of pivot columns (BE = min(J0+NB, ni)) the inner panels of
+// width W update only the L-shaped region they must (mode 0); the big trailing block [BE,n)² is updated once per
+// outer block with K = BE−J0 (mode 1), which is where almost all flops go.
+//   mode 0: K = [j0, j0+wc),  C = rows [j0+wc, n)  × cols [j0+wc, BE)   (inside the block, while it is factored)
+//   mode 2: K = [j0, j0+wc),  C = rows [j0+wc, BE) × cols [BE, n)      (top strip of the outside columns, after it)
+//   mode 1: K = [J0, BE),     C = [BE, n)²                             (the big update, K up to NB)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(c0), "+d"(c1)
                : "d"(a), "d"(b));
 }
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(gmem), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem, int src_bytes) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sa), "l"(gmem), "r"(src_bytes) : "memory");
+}
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <typename T> struct GemmCfg;
-template <> struct GemmCfg<double> { static constexpr int KC = 64, LDA = 68, LDB = 68; };
-template <> struct GemmCfg<cplx> { static constexpr int KC = 32, LDA = 66, LDB = 36; };
+template <> struct GemmCfg<double> {
+  static constexpr int TM = 128, TN = 128, WM = 64, WN = 32, KC = 16, ST = 4, LDA = 132, LDB = 20;
+};
+template <> struct GemmCfg<cplx> {
+  static constexpr int TM = 128, TN = 64, WM = 32, WN = 32, KC = 8, ST = 4, LDA = 130, LDB = 12;
+};
+template <typename T> constexpr int gemm_smem_bytes() {
+  return GemmCfg<T>::ST * (GemmCfg<T>::KC * GemmCfg<T>::LDA + GemmCfg<T>::TN * GemmCfg<T>::LDB) * (int)sizeof(T);
+}
 
 template <typename T>
-__global__ void __launch_bounds__(128) k_gemm(const Front* __restrict__ fronts, T* __restrict__ pool, int f0, int j0,
-                                               int W) {
-  constexpr int KC = GemmCfg<T>::KC, LDA = GemmCfg<T>::LDA, LDB = GemmCfg<T>::LDB;
+__global__ void __launch_bounds__(256, 1) k_gemm(const Front* __restrict__ fronts, T* __restrict__ pool, int f0, int J0,
+                                                  int j0, int NB, int W, int mode) {
+  using Cfg = GemmCfg<T>;
+  constexpr int TM = Cfg::TM, TN = Cfg::TN, WM = Cfg::WM, WN = Cfg::WN, KC = Cfg::KC, ST = Cfg::ST, LDA = Cfg::LDA,
+                LDB = Cfg::LDB;
   constexpr bool CX = hs_traits<T>::is_complex;
-  const int fi = f0 + blockIdx.x;
-  const Front fr = fronts[fi];
-  if (fr.ni <= j0) return;
-  const int wc = min(W, fr.ni - j0);
-  const int t0 = j0 + wc;          // first trailing row/col
-  const int mt = fr.n - t0;        // trailing size
-  const int m0 = blockIdx.y * 64, n0 = blockIdx.z * 64;
-  if (m0 >= mt || n0 >= mt) return;
+  constexpr int EPV = 16 / (int)sizeof(T);  // elements per 16-byte vector: 2 (f64) or 1 (c64)
+  constexpr int MI = WM / 8, NI = WN / 8;
+  const Front fr = fronts[f0 + blockIdx.x];
+  const int n = fr.n, ni = fr.ni;
+  int kbase, kcount, lo, rhi, clo, chi;  // C = rows [lo, rhi) × cols [clo, chi)
+  const int BE = min(J0 + NB, ni);
+  if (mode == 1) {
+    if (ni <= J0) return;
+    kbase = J0; kcount = BE - J0; lo = BE; rhi = n; clo = BE; chi = n;
+  } else {
+    if (ni <= j0) return;
+    const int wc = min(W, ni - j0);
+    kbase = j0; kcount = wc; lo = j0 + wc;
+    if (mode == 0) { rhi = n; clo = lo; chi = BE; } else { rhi = BE; clo = BE; chi = n; }
+  }
+  if (lo >= rhi || clo >= chi) return;
+  // rows are loaded in aligned 16-byte pairs; a front whose base is not 16-byte aligned (only the root-boundary
+  // pseudo front can be) takes the 8-byte copy path
+  const bool al = (fr.off & (EPV - 1)) == 0;
+  const int rbase = al ? (lo & ~(EPV - 1)) : lo;
+  const int m0 = rbase + blockIdx.y * TM, n0 = clo + blockIdx.z * TN;
+  if (m0 >= rhi || n0 >= chi) return;
   T* F = pool + fr.off;
   const long long ld = fr.ld;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* As = reinterpret_cast<T*>(smem_raw);  // [KC][LDA]  (k-major, m contiguous)
-  T* Bs = As + KC * LDA;                   // [64][LDB]  (n-major, k contiguous)
+  T* smem = reinterpret_cast<T*>(smem_raw);
+  constexpr int STAGE = KC * LDA + TN * LDB;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = (warp & 1) * 32, wn = (warp >> 1) * 32;
+  const int wm = (warp % (TM / WM)) * WM, wn = (warp / (TM / WM)) * WN;
   const int g = lane >> 2, q = lane & 3;
 
-  double acc[CX ? 2 : 1][4][4][2];
+  // warm L2 with the C tile: the epilogue's read-modify-write then does not wait on HBM
+  {
+    const int lines_per_col = (TM * (int)sizeof(T)) / 128;
+    for (int e = tid; e < TN * lines_per_col; e += 256) {
+      const int c = n0 + e / lines_per_col, r = m0 + (e % lines_per_col) * (128 / (int)sizeof(T));
+      if (c < chi && r < rhi) asm volatile("prefetch.global.L2 [%0];" ::"l"(F + (long long)c * ld + r));
+    }
+  }
+
+  auto load_stage = [&](int stage, int chunk) {
+    T* As = smem + stage * STAGE;
+    T* Bs = As + KC * LDA;
+    const int krem = kcount - chunk * KC;
+    const int kg = kbase + chunk * KC;
+    if (EPV > 1 && !al) {
+      for (int c = tid; c < KC * TM; c += 256) {
+        const int k = c / TM, m = c % TM;
+        const bool ok = k < krem && m0 + m < rhi;
+        cp_async8(As + k * LDA + m, ok ? F + (long long)(kg + k) * ld + (m0 + m) : F, ok ? 8 : 0);
+      }
+      for (int c = tid; c < TN * KC; c += 256) {
+        const int nn = c / KC, k = c % KC;
+        const bool ok = n0 + nn < chi && k < krem;
+        cp_async8(Bs + nn * LDB + k, ok ? F + (long long)(n0 + nn) * ld + (kg + k) : F, ok ? 8 : 0);
+      }
+      return;
+    }
+    constexpr int AV = TM / EPV;  // 16-byte vectors per k-row of the A tile
+#pragma unroll
+    for (int i = 0; i < (KC * AV) / 256; ++i) {
+      const int c = tid + i * 256;
+      const int k = c / AV, m = (c % AV) * EPV;
+      const int left = rhi - (m0 + m);
+      int bytes = 0;
+      if (k < krem && left > 0) bytes = left >= EPV ? 16 : (int)sizeof(T);
+      const T* src = bytes ? F + (long long)(kg + k) * ld + (m0 + m) : F;
+      cp_async16(As + k * LDA + m, src, bytes);
+    }
+    constexpr int BV = KC / EPV;  // 16-byte vectors per column of the B tile
+#pragma unroll
+    for (int i = 0; i < (TN * BV) / 256; ++i) {
+      const int c = tid + i * 256;
+      const int nn = c / BV, k = (c % BV) * EPV;
+      int bytes = 0;
+      if (n0 + nn < chi && k < krem) bytes = (krem - k) >= EPV ? 16 : (int)sizeof(T);
+      const T* src = bytes ? F + (long long)(n0 + nn) * ld + (kg + k) : F;
+      cp_async16(Bs + nn * LDB + k, src, bytes);
+    }
+  };
+
+  double acc[CX ? 2 : 1][MI][NI][2];
 #pragma unroll
   for (int z = 0; z < (CX ? 2 : 1); ++z)
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < MI; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[z][i][j][0] = acc[z][i][j][1] = 0.0;
+      for (int j = 0; j < NI; ++j) acc[z][i][j][0] = acc[z][i][j][1] = 0.0;
 
-  for (int kc = 0; kc < wc; kc += KC) {
-    const int kn = min(KC, wc - kc);
-    // A tile: rows t0+m0.. (64), cols j0+kc.. (KC)
-    for (int e = tid; e < 64 * KC; e += 128) {
-      const int mm = e & 63, kk = e >> 6;
-      T v = hs_zero<T>();
-      if (m0 + mm < mt && kk < kn) v = F[(long long)(j0 + kc + kk) * ld + (t0 + m0 + mm)];
-      As[kk * LDA + mm] = v;
-    }
-    // B tile: rows j0+kc.. (KC), cols t0+n0.. (64)
-    for (int e = tid; e < 64 * KC; e += 128) {
-      const int kk = e % KC, nn = e / KC;
-      T v = hs_zero<T>();
-      if (n0 + nn < mt && kk < kn) v = F[(long long)(t0 + n0 + nn) * ld + (j0 + kc + kk)];
-      Bs[nn * LDB + kk] = v;
-    }
+  const int nchunks = (kcount + KC - 1) / KC;
+#pragma unroll
+  for (int s = 0; s < ST - 1; ++s) {
+    if (s < nchunks) load_stage(s, s);
+    cp_async_commit();
+  }
+  for (int c = 0; c < nchunks; ++c) {
+    cp_async_wait<ST - 2>();
     __syncthreads();
-    const int ksteps = (kn + 3) >> 2;
-    for (int ks = 0; ks < ksteps; ++ks) {
+    if (c + ST - 1 < nchunks) load_stage((c + ST - 1) % ST, c + ST - 1);
+    cp_async_commit();
+    const T* As = smem + (c % ST) * STAGE;
+    const T* Bs = As + KC * LDA;
+#pragma unroll
+    for (int ks = 0; ks < KC / 4; ++ks) {
       const int k = ks * 4 + q;
-      T af[4], bf[4];
+      T af[MI], bf[NI];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) af[i] = As[k * LDA + wm + i * 8 + g];
+      for (int i = 0; i < MI; ++i) af[i] = As[k * LDA + wm + i * 8 + g];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) bf[j] = Bs[(wn + j * 8 + g) * LDB + k];
+      for (int j = 0; j < NI; ++j) bf[j] = Bs[(wn + j * 8 + g) * LDB + k];
       if constexpr (!CX) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < MI; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) dmma884(acc[0][i][j][0], acc[0][i][j][1], af[i], bf[j]);
+          for (int j = 0; j < NI; ++j) dmma884(acc[0][i][j][0], acc[0][i][j][1], af[i], bf[j]);
       } else {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < MI; ++i) {
           const double nai = -af[i].y;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < NI; ++j) {
             dmma884(acc[0][i][j][0], acc[0][i][j][1], af[i].x, bf[j].x);
             dmma884(acc[0][i][j][0], acc[0][i][j][1], nai, bf[j].y);
             dmma884(acc[1][i][j][0], acc[1][i][j][1], af[i].x, bf[j].y);
@@ -244,20 +366,20 @@ __global__ void __launch_bounds__(128) k_gemm(const Front* __restrict__ fronts, 
         }
       }
     }
-    __syncthreads();
   }
+  cp_async_wait<0>();
   // epilogue: C -= acc
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < MI; ++i) {
     const int r = m0 + wm + i * 8 + g;
-    if (r >= mt) continue;
+    if (r < lo || r >= rhi) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < NI; ++j) {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int c = n0 + wn + j * 8 + q * 2 + h;
-        if (c >= mt) continue;
-        T* pc = F + (long long)(t0 + c) * ld + (t0 + r);
+        if (c >= chi) continue;
+        T* pc = F + (long long)c * ld + r;
         if constexpr (!CX) {
           *pc -= acc[0][i][j][h];
         } else {

@@ -193,3 +193,39 @@ def test_pivoting_is_exercised(hs, orc):
     assert piv_moved > 0
     x, xo = hs.ldiv(F, prob.b), orc.ldiv(Fo, prob.b)
     assert rel(Ap @ x, prob.b) < 1e-9 and rel(x, xo) < 1e-8
+
+
+def _single_front_problem(hs, ni, nb, cx, seed=0):
+    """One dense front: a tree whose only node is a leaf with ni interior and nb boundary DOFs and a dense A.
+    Isolates the partial-LU kernels (panel / TRSM / DMMA update) at sizes the grid problems reach only at 1024²+."""
+    import scipy.sparse as sp
+    from hsolve_b200.problems import ElimTree, Problem
+    rng = np.random.default_rng(seed)
+    n = ni + nb
+    A = rng.standard_normal((n, n))
+    if cx:
+        A = A + 1j * rng.standard_normal((n, n))
+    A = A + np.diag(np.full(n, 0.5 * np.sqrt(n)))   # keeps the pivot block well conditioned but not pivot-free
+    b = rng.standard_normal(n).astype(A.dtype)
+    et = ElimTree(np.array([-1]), np.array([-1]), np.array([-1]), np.array([0, ni]), np.arange(1, ni + 1),
+                  np.array([0, nb]), np.arange(ni + 1, n + 1))
+    return Problem(sp.csc_matrix(A), b, et), A
+
+
+@pytest.mark.parametrize("ni,nb,cx", [(100, 60, False), (300, 200, False), (700, 400, False), (1100, 300, False),
+                                      (100, 60, True), (300, 200, True), (700, 400, True), (1100, 300, True),
+                                      (513, 0, True), (65, 1000, False), (33, 700, True)])
+def test_single_dense_front(hs, ni, nb, cx):
+    prob, A = _single_front_problem(hs, ni, nb, cx)
+    Ap, nd, nd_loc, perm = hs.prepare(prob.A, prob.elim_tree)
+    assert np.array_equal(perm, np.arange(1, ni + nb + 1))
+    F = hs.factor(Ap, nd, nd_loc, swlevel=0)
+    Aii, Aib, Abi, Abb = A[:ni, :ni], A[:ni, ni:], A[ni:, :ni], A[ni:, ni:]
+    R = np.linalg.solve(Aii, Aib) if nb else np.zeros((ni, 0), A.dtype)
+    L = np.linalg.solve(Aii.T, Abi.T).T if nb else np.zeros((0, ni), A.dtype)
+    S = Abb - Abi @ R
+    assert rel(F.D, Aii) < TOL
+    if nb:
+        assert rel(F.R, R) < TOL and rel(F.L, L) < TOL and rel(F.S, S) < TOL
+    x = hs.ldiv(F, prob.b)
+    assert rel(A @ x, prob.b) < TOL

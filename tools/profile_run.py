@@ -23,3 +23,6 @@ st = F.stats()
 print(f"grid {grid} {kind}: factor {st['ms_factor_total']:.2f} ms (call {1e3 * (t1 - t0):.0f} ms), solve {st['ms_solve_total']:.2f} ms "
       f"(call {1e3 * (t2 - t1):.0f} ms), resid {np.linalg.norm(Ap @ x - prob.b) / np.linalg.norm(prob.b):.2e}, "
       f"{st['factor_flops'] / st['ms_factor_total'] / 1e9:.2f} TFLOP/s")
+if os.environ.get("HS_PROFILE"):
+    print("  phases(ms):", {k: round(v, 2) for k, v in st.items() if k.startswith("ms_")}, "gemm TF/s",
+          round(st["gemm_flops"] / max(st["ms_gemm"], 1e-9) / 1e9, 2), "launches", st["launches_factor"], st["launches_solve"])
