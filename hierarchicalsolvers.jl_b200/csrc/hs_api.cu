@@ -140,6 +140,16 @@ template <typename T> static void trsm_dispatch(hs_fac* f, int W, int f0, int na
 // Two-level blocking: outer blocks of NB pivot columns, inner register-resident panels of width W.
 template <typename T> static void factor_level(hs_fac* f, const Level& L) {
   cudaStream_t st = f->ctx->stream;
+  if (L.max_n <= hs_small_max_n(f->dtype) && L.max_ni > 0) {
+    // small fronts: one fused register-resident kernel does pivot block, both panels and the Schur update
+    {
+      PhaseTimer t(f, &f->stats.ms_small);
+      hs_small_factor(f, L);
+    }
+    PhaseTimer t(f, &f->stats.ms_solve_prep);
+    hs_solve_prep(f, L);
+    return;
+  }
   const int W = hs_panel_width(f, L.max_n);
   if (W < 0) throw hs_error(HS_ESIZE, "front with " + std::to_string(L.max_n) + " rows exceeds the panel kernels");
   const int NB = std::max(W, f->ctx->outer_block / W * W);
@@ -227,7 +237,7 @@ template <typename T> static void numeric(hs_fac* f) {
   cudaStream_t st = f->ctx->stream;
   T* pool = (T*)f->pool;
   hs_stats_t& s = f->stats;
-  s.ms_assemble = s.ms_panel = s.ms_trsm = s.ms_gemm = s.ms_solve_prep = 0;
+  s.ms_assemble = s.ms_panel = s.ms_trsm = s.ms_gemm = s.ms_solve_prep = s.ms_small = 0;
   s.launches_factor = 0;
   s.gemm_launches = s.panel_launches = 0;
   s.gemm_flops = 0;

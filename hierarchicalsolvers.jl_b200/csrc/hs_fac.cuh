@@ -101,3 +101,7 @@ void hs_solve_setup();
 int hs_solve_block(hs_dtype dt);
 void hs_solve_prep(hs_fac* f, const Level& L);
 void hs_solve_run(hs_fac* f, int64_t nrhs, void* x);
+
+// hs_small.cu
+int hs_small_max_n(hs_dtype dt);
+void hs_small_factor(hs_fac* f, const Level& L);
