@@ -14,74 +14,76 @@
 // launch per block step with one CTA per 32-row tile.
 #include <cuda_runtime.h>
 
+#include <cooperative_groups.h>
+
 #include <algorithm>
 
 #include "hs_fac.cuh"
 
 namespace {
 
-template <typename T> struct SolveCfg;
-template <> struct SolveCfg<double> { static constexpr int DB = 128; };
-template <> struct SolveCfg<cplx> { static constexpr int DB = 96; };
+namespace cg = cooperative_groups;
+
+constexpr int DB = 64;  // diagonal blocks of L11/U11 that are inverted in place (both scalar types)
+template <typename T> struct SolveCfg { static constexpr int DB = ::DB; };
 
 constexpr int NW = 8;          // warps per CTA
 constexpr int NTH = NW * 32;
 
 // ------------------------------------------------------------------------------------------------
-// in-place inversion of the diagonal blocks of L11 (unit lower) and U11 (upper); one CTA per (front, block)
-// LAPACK trti2 order: L from the last column to the first, U from the first to the last; both in one sweep.
+// in-place inversion of the DB×DB diagonal blocks of L11 (unit lower) and U11 (upper); one CTA per (front, block).
+// Thread j < db builds column j of L_bb⁻¹ by forward substitution, thread 64 + j column j of U_bb⁻¹ by back
+// substitution; columns are independent, so there is no barrier inside the loops.  The factor is read from global
+// memory (every lane reads the same entry → one broadcast transaction), the inverse grows in shared memory.
 // ------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(128) k_trtri_diag(const Front* __restrict__ fronts, T* __restrict__ pool, int f0) {
-  constexpr int DB = SolveCfg<T>::DB;
+__global__ void __launch_bounds__(128) k_trtri_diag(const Front* __restrict__ fronts, T* __restrict__ pool, int f0, int lds) {
   const Front fr = fronts[f0 + blockIdx.x];
   const int b0 = blockIdx.y * DB;
   if (b0 >= fr.ni) return;
   const int db = min(DB, fr.ni - b0);
-  const int lds = db | 1;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* S = reinterpret_cast<T*>(smem_raw);  // db × lds, column-major
-  T* vl = S + (size_t)db * lds;           // column of L being replaced
-  T* vu = vl + db;                        // column of U being replaced
+  const int LDS = lds;
+  extern __shared__ __align__(16) unsigned char smem_x[];
+  T* S = reinterpret_cast<T*>(smem_x);  // the factor block (both triangles), column-major db × LDS
+  T* X = S + (size_t)lds * lds;         // its inverse
   T* G = pool + fr.off + (long long)b0 * fr.ld + b0;
+  const long long ld = fr.ld;
   const int tid = threadIdx.x;
   for (int e = tid; e < db * db; e += blockDim.x) {
     const int i = e % db, j = e / db;
-    S[j * lds + i] = G[(long long)j * fr.ld + i];
+    S[j * LDS + i] = G[(long long)j * ld + i];
   }
   __syncthreads();
-  for (int s = 0; s < db; ++s) {
-    const int jl = db - 1 - s;  // L column handled in this step (rows jl+1..db-1 use the inverted trailing block)
-    const int ju = s;           // U column handled in this step (rows 0..ju-1 use the inverted leading block)
-    for (int i = tid; i < db; i += blockDim.x) {
-      if (i > jl) vl[i] = S[jl * lds + i];
-      if (i < ju) vu[i] = S[ju * lds + i];
-    }
-    __syncthreads();
-    for (int i = tid; i < db; i += blockDim.x) {
-      if (i > jl) {  // y_i = v_i + Σ_{k=jl+1}^{i-1} X_ik v_k ;  X_i,jl = -y_i
-        T y = vl[i];
-        for (int k = jl + 1; k < i; ++k) y = hs_fma(y, S[k * lds + i], vl[k]);
-        S[jl * lds + i] = hs_sub(hs_zero<T>(), y);
+  // all lanes walk the same (i, k) pairs: S[k,i] is a broadcast read, X[.,j] is private to the lane
+  if (tid < 64) {
+    const int j = tid;  // column j of L⁻¹:  x_ij = −(L_ij + Σ_{j<k<i} L_ik·x_kj)
+    const bool act = j < db;
+    for (int i = 1; i < db; ++i) {
+      T sacc = (act && i > j) ? S[j * LDS + i] : hs_zero<T>();
+      for (int k = 1; k < i; ++k) {
+        const T g = S[k * LDS + i];
+        if (act && k > j) sacc = hs_fma(sacc, g, X[j * LDS + k]);
       }
+      if (act && i > j) X[j * LDS + i] = hs_sub(hs_zero<T>(), sacc);
     }
-    // U: needs 1/U_jj of this column: every thread recomputes it (cheap, avoids a broadcast)
-    const T xjj = hs_recip(S[ju * lds + ju]);
-    __syncthreads();  // S[ju*lds+ju] read by all before thread ju/… overwrites it
-    for (int i = tid; i < db; i += blockDim.x) {
-      if (i < ju) {  // y_i = Σ_{k=i}^{ju-1} X_ik v_k ;  X_i,ju = -x_jj·y_i
-        T y = hs_zero<T>();
-        for (int k = i; k < ju; ++k) y = hs_fma(y, S[k * lds + i], vu[k]);
-        S[ju * lds + i] = hs_sub(hs_zero<T>(), hs_mul(y, xjj));
-      } else if (i == ju) {
-        S[ju * lds + ju] = xjj;
+  } else {
+    const int j = tid - 64;  // column j of U⁻¹:  x_ij = −(Σ_{i<k≤j} U_ik·x_kj)/U_ii
+    const bool act = j < db;
+    if (act) X[j * LDS + j] = hs_recip(S[j * LDS + j]);
+    for (int i = db - 2; i >= 0; --i) {
+      T sacc = hs_zero<T>();
+      for (int k = i + 1; k < db; ++k) {
+        const T g = S[k * LDS + i];
+        if (act && k <= j && i < j) sacc = hs_fma(sacc, g, X[j * LDS + k]);
       }
+      const T dinv = hs_recip(S[i * LDS + i]);
+      if (act && i < j) X[j * LDS + i] = hs_sub(hs_zero<T>(), hs_mul(sacc, dinv));
     }
-    __syncthreads();
   }
+  __syncthreads();
   for (int e = tid; e < db * db; e += blockDim.x) {
     const int i = e % db, j = e / db;
-    G[(long long)j * fr.ld + i] = S[j * lds + i];
+    G[(long long)j * ld + i] = X[j * LDS + i];
   }
 }
 
@@ -193,187 +195,382 @@ __global__ void __launch_bounds__(NTH) k_sv_small_bwd(const Front* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------
-// large fronts (ni > DB): one launch per block step, CTA per 32-row tile; the CTA that owns the next diagonal block
-// (blockIdx.y == 0) also applies its inverse so that the next step can start from a final v_b.
-// The working vector of every front lives in `work` (one slice per front, offset ioff − ioff0).
+// large fronts (ni > DB): one thread-block CLUSTER per (front, rhs) runs the whole sweep; block steps are separated
+// by cluster barriers instead of kernel launches.  A warp owns 32-row tiles (lane = row) and streams its rows of the
+// current block column; global warp 0 additionally owns the next diagonal block and applies its inverse, so that the
+// next step starts from a final v_b.  The working vector lives in `work` (global, read/written with .cg accesses).
 // ------------------------------------------------------------------------------------------------
-// step = -1: gather v = [P x_int; x_bnd] into work and finalize block 0.  step = b ≥ 0: apply block column b.
+template <typename T> __device__ __forceinline__ T ldcg(const T* p);
+template <> __device__ __forceinline__ double ldcg<double>(const double* p) { return __ldcg(p); }
+template <> __device__ __forceinline__ cplx ldcg<cplx>(const cplx* p) {
+  const double2 v = __ldcg(reinterpret_cast<const double2*>(p));
+  return cplx{v.x, v.y};
+}
+template <typename T> __device__ __forceinline__ void stcg(T* p, T v);
+template <> __device__ __forceinline__ void stcg<double>(double* p, double v) { __stcg(p, v); }
+template <> __device__ __forceinline__ void stcg<cplx>(cplx* p, cplx v) { __stcg(reinterpret_cast<double2*>(p), make_double2(v.x, v.y)); }
+
+// Σ_k M[r, k]·v[k] for one row per lane, v (≤ 64 values) in shared memory
 template <typename T>
-__global__ void __launch_bounds__(NTH) k_sv_fwd_step(const Front* __restrict__ fronts, const T* __restrict__ pool,
-                                                      const int* __restrict__ gidx, const int* __restrict__ rperm,
-                                                      T* __restrict__ x, long long ldx, T* __restrict__ work,
-                                                      long long wstride, long long ioff0, int f0, int step) {
-  constexpr int DB = SolveCfg<T>::DB;
-  const Front fr = fronts[f0 + blockIdx.x];
+__device__ __forceinline__ T row_dot(const T* __restrict__ Mrow, long long ld, int kcnt, const T* __restrict__ v, bool ok) {
+  T acc = hs_zero<T>();
+  if (ok) {
+#pragma unroll 16
+    for (int k = 0; k < kcnt; ++k) acc = hs_fma(acc, Mrow[(long long)k * ld], v[k]);
+  }
+  return acc;
+}
+
+// two consecutive rows per lane through one 16-byte load (f64 only; Mrow must be 16-byte aligned): keeps
+// 16 × 16 B per thread in flight, which is what lets a handful of SMs pull a useful share of HBM bandwidth
+__device__ __forceinline__ void row_dot2(const double* __restrict__ Mrow, long long ld, int kcnt,
+                                         const double* __restrict__ v, double& a0, double& a1) {
+  double s0 = 0.0, s1 = 0.0;
+#pragma unroll 16
+  for (int k = 0; k < kcnt; ++k) {
+    const double2 m = *reinterpret_cast<const double2*>(Mrow + (long long)k * ld);
+    const double vk = v[k];
+    s0 = fma(m.x, vk, s0);
+    s1 = fma(m.y, vk, s1);
+  }
+  a0 = s0; a1 = s1;
+}
+
+// one tile of the streamed update  w[r] −= Σ_k M[r,k]·v[k]  (or the final scatter into x when `fin`);
+// a tile is 64 rows for aligned f64 fronts (2 rows per lane) and 32 rows otherwise
+template <typename T> struct TileRows { static constexpr int N = 32; };
+template <> struct TileRows<double> { static constexpr int N = 64; };
+
+template <typename T>
+__device__ __forceinline__ void tile_update(const T* __restrict__ Mb, long long ld, int kcnt, const T* __restrict__ v,
+                                            int rbase, int rend, bool al, T* __restrict__ w, T* __restrict__ xr,
+                                            const int* __restrict__ gi, bool fin, const T* __restrict__ src_x) {
+  const int lane = threadIdx.x & 31;
+  auto put = [&](int r, T acc) {
+    const T cur = src_x ? src_x[gi[r]] : ldcg(&w[r]);
+    const T val = hs_sub(cur, acc);
+    if (fin) xr[gi[r]] = val; else stcg(&w[r], val);
+  };
+  if constexpr (sizeof(T) == 8) {
+    const int r = rbase + 2 * lane;
+    if (al && (rbase & 1) == 0 && r + 1 < rend) {
+      double a0, a1;
+      row_dot2(reinterpret_cast<const double*>(Mb) + r, ld, kcnt, reinterpret_cast<const double*>(v), a0, a1);
+      put(r, a0); put(r + 1, a1);
+    } else {
+      // unaligned front or ragged tail: scalar fallback over the two rows this lane owns
+      for (int q = 0; q < 2; ++q) {
+        const int rr = r + q;
+        if (rr < rend) put(rr, row_dot<T>(Mb + rr, ld, kcnt, v, true));
+      }
+    }
+  } else {
+    const int r = rbase + lane;
+    if (r < rend) put(r, row_dot<T>(Mb + r, ld, kcnt, v, true));
+  }
+}
+
+// Work of the "diagonal CTA" in one step, executed by all NTH threads of that CTA:
+//   u[i]  = win[i] − Σ_{k<db} M[i, k]·vb[k]                 for the cnt ≤ 64 rows starting at Mrows / win
+//   y[i]  = (tri == 1 ? u[i] : 0) + Σ_k Tinv[i, k]·u[k]      for i < dn   (k < i lower-unit, k ≥ i upper)
+//   y[i]  = u[i]                                             for dn ≤ i < cnt (rows below a partial last block)
+// Returns y[tid] to threads tid < cnt (others get zero).
+template <typename T>
+__device__ __forceinline__ T diag_cta(const T* __restrict__ Mrows, long long ld, int db, const T* __restrict__ vb,
+                                      T win, int cnt, const T* __restrict__ Tinv, int dn, int tri, T* sT, T (*spart)[64],
+                                      T* su) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int LDT = 65;
+  // all global loads of this step are issued up front with static addressing (16 + 16 per thread in flight)
+  {
+    const int i = tid & 63, kq = tid >> 6;  // 4 columns per pass
+    T pre[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int k = kq + 4 * q;
+      pre[q] = (i < dn && k < dn) ? Tinv[(long long)k * ld + i] : hs_zero<T>();
+    }
+    T a0 = hs_zero<T>(), a1 = hs_zero<T>();
+    const bool ok0 = lane < cnt, ok1 = lane + 32 < cnt;
+    T m0[8], m1[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int k = warp + NW * q;
+      m0[q] = (ok0 && k < db) ? Mrows[(long long)k * ld + lane] : hs_zero<T>();
+      m1[q] = (ok1 && k < db) ? Mrows[(long long)k * ld + lane + 32] : hs_zero<T>();
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int k = warp + NW * q;
+      const T vk = k < db ? vb[k] : hs_zero<T>();
+      a0 = hs_fma(a0, m0[q], vk);
+      a1 = hs_fma(a1, m1[q], vk);
+    }
+    spart[warp][lane] = a0;
+    spart[warp][lane + 32] = a1;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) sT[(kq + 4 * q) * LDT + i] = pre[q];
+  }
+  __syncthreads();
+  if (tid < 64) {
+    T u = hs_zero<T>();
+    if (tid < cnt) {
+      T sum = hs_zero<T>();
+#pragma unroll
+      for (int w = 0; w < NW; ++w) sum = hs_add(sum, spart[w][tid]);
+      u = hs_sub(win, sum);
+    }
+    su[tid] = u;
+  }
+  __syncthreads();
+  {
+    T a0 = hs_zero<T>(), a1 = hs_zero<T>();
+    const int r0 = lane, r1 = lane + 32;
+    for (int k = warp; k < dn; k += NW) {
+      const T uk = su[k];
+      const bool use0 = r0 < dn && (tri == 1 ? k < r0 : k >= r0);
+      const bool use1 = r1 < dn && (tri == 1 ? k < r1 : k >= r1);
+      if (use0) a0 = hs_fma(a0, sT[k * LDT + r0], uk);
+      if (use1) a1 = hs_fma(a1, sT[k * LDT + r1], uk);
+    }
+    spart[warp][lane] = a0;
+    spart[warp][lane + 32] = a1;
+  }
+  __syncthreads();
+  T y = hs_zero<T>();
+  if (tid < cnt) {
+    if (tid < dn) {
+      T sum = tri == 1 ? su[tid] : hs_zero<T>();
+#pragma unroll
+      for (int w = 0; w < NW; ++w) sum = hs_add(sum, spart[w][tid]);
+      y = sum;
+    } else {
+      y = su[tid];
+    }
+  }
+  __syncthreads();
+  return y;
+}
+
+template <typename T, bool CL>
+__global__ void __launch_bounds__(NTH) k_sv_big_fwd(const Front* __restrict__ fronts, const T* __restrict__ pool,
+                                                     const int* __restrict__ gidx, const int* __restrict__ rperm,
+                                                     T* __restrict__ x, long long ldx, T* __restrict__ work,
+                                                     long long wstride, long long ioff0, int f0) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int C = CL ? (int)cluster.num_blocks() : 1;
+  const int crank = CL ? (int)cluster.block_rank() : 0;
+  const Front fr = fronts[f0 + (CL ? blockIdx.x / C : blockIdx.x)];
   const int n = fr.n, ni = fr.ni;
   const T* F = pool + fr.off;
   const long long ld = fr.ld;
-  T* xr = x + (long long)blockIdx.z * ldx;
-  T* w = work + (long long)blockIdx.z * wstride + (fr.ioff - ioff0);
+  const bool al = (fr.off & 1) == 0;  // 16-byte aligned columns (false only for the root-boundary pseudo front)
+  T* xr = x + (long long)blockIdx.y * ldx;
+  T* w = work + (long long)blockIdx.y * wstride + (fr.ioff - ioff0);
   const int* gi = gidx + fr.ioff;
   const int* rp = rperm + fr.ioff;
-  __shared__ T vb[DB], u[DB];
-  __shared__ T red[NW][32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (step < 0) {
-    // gather; tile 0 additionally finalizes block 0
-    const int rows_per_cta = 32 * NW * 4;
-    const int r_begin = blockIdx.y * rows_per_cta;
-    if (r_begin >= n) return;
-    for (int r = r_begin + tid; r < min(n, r_begin + rows_per_cta); r += NTH)
-      if (!(blockIdx.y == 0 && r < DB)) w[r] = xr[gi[r < ni ? rp[r] : r]];
-    if (blockIdx.y == 0) {
-      const int db = min(DB, ni);
-      for (int k = tid; k < db; k += NTH) u[k] = xr[gi[rp[k]]];
-      __syncthreads();
-      for (int r0 = 0; r0 < db; r0 += 32) {
-        const int r = r0 + lane;
-        const T s = tile_dot<T>(F, ld, r, r < db, 0, min(db, r0 + 32), u, 1, r, red);
-        if (warp == 0 && r < db) w[r] = hs_add(u[r], s);  // x itself is written in step 0 (other CTAs still gather from it)
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* sT = reinterpret_cast<T*>(smem_raw);        // 64·65
+  T(*spart)[64] = reinterpret_cast<T(*)[64]>(sT + 64 * 65);  // NW·64
+  T* su = sT + 64 * 65 + NW * 64;                // 64
+  T* svb = su + 64;                              // 64
+  auto sync = [&]() { if (CL) cluster.sync(); else __syncthreads(); };
+  // tile workers: the warps of CTAs 1..C-1 (all warps of the only CTA when C == 1)
+  const int nworkers = C > 1 ? NW * (C - 1) : NW;
+  const int me = C > 1 ? (crank - 1) * NW + warp : warp;
+  const bool worker = C == 1 || crank > 0;
+  // gather v = [P·x_int; x_bnd]
+  for (int r = crank * NTH + tid; r < n; r += NTH * C) stcg(&w[r], xr[gi[r < ni ? rp[r] : r]]);
+  sync();
+  const int B = (ni + DB - 1) / DB;
+  if (crank == 0) {  // v_0 = L00⁻¹·v_0
+    const int db0 = min(DB, ni);
+    const T win = tid < db0 ? ldcg(&w[tid]) : hs_zero<T>();
+    const T y = diag_cta<T>(F, ld, 0, svb, win, db0, F, db0, 1, sT, spart, su);
+    if (tid < db0) { stcg(&w[tid], y); xr[gi[tid]] = y; }
+  }
+  sync();
+  for (int b = 0; b < B; ++b) {
+    const int b0 = b * DB, b1 = min(b0 + DB, ni), db = b1 - b0;
+    const bool last = b1 >= ni;
+    if (tid < 64) svb[tid] = tid < db ? ldcg(&w[b0 + tid]) : hs_zero<T>();
+    __syncthreads();
+    const T* Fb = F + (long long)b0 * ld;
+    // rows after b1 in tiles of 32; the first 64 rows (the next diagonal block) belong to CTA 0 unless this is the
+    // last block column
+    if (!last) {
+      if (crank == 0) {
+        const int nb1 = min(b1 + DB, ni), dn = nb1 - b1;
+        const int cnt = min(64, n - b1);
+        const T win = tid < cnt ? ldcg(&w[b1 + tid]) : hs_zero<T>();
+        const T y = diag_cta<T>(Fb + b1, ld, db, svb, win, cnt, F + (long long)b1 * ld + b1, dn, 1, sT, spart, su);
+        if (tid < cnt) { stcg(&w[b1 + tid], y); if (tid < dn) xr[gi[b1 + tid]] = y; }
       }
     }
-    return;
-  }
-  const int b0 = step * DB;
-  if (b0 >= ni) return;
-  const int b1 = min(b0 + DB, ni), db = b1 - b0;
-  const bool last = b1 >= ni;
-  // rows handled: blockIdx.y == 0 → the next diagonal block [b1, b1+DB) ∩ [b1, ni) (if any); others → 32-row tiles after it
-  const int nb1 = last ? b1 : min(b1 + DB, ni);  // end of the next diagonal block
-  for (int k = tid; k < db; k += NTH) vb[k] = w[b0 + k];
-  __syncthreads();
-  if (blockIdx.y == 0) {
-    for (int k = tid; k < db; k += NTH) xr[gi[b0 + k]] = vb[k];  // block b is final: t = L11⁻¹·P·x[int]
-    if (last) return;
-    const int dn = nb1 - b1;
-    for (int r0 = 0; r0 < dn; r0 += 32) {
-      const int r = b1 + r0 + lane;
-      const T s = tile_dot<T>(F + (long long)b0 * ld, ld, r, r < nb1, 0, db, vb, 0, 0, red);
-      if (warp == 0 && r < nb1) u[r0 + lane] = hs_sub(w[r], s);
+    if (worker) {
+      constexpr int TR = TileRows<T>::N;
+      const int rstart = b1 + (last ? 0 : 64);
+      const int ntiles = (n - rstart + TR - 1) / TR;
+      for (int t = me; t < ntiles; t += nworkers)
+        tile_update<T>(Fb, ld, db, svb, rstart + t * TR, n, al, w, xr, gi, last, nullptr);
     }
-    __syncthreads();
-    for (int r0 = 0; r0 < dn; r0 += 32) {
-      const int r = r0 + lane;
-      const T s = tile_dot<T>(F + (long long)b1 * ld + b1, ld, r, r < dn, 0, min(dn, r0 + 32), u, 1, r, red);
-      if (warp == 0 && r < dn) w[b1 + r] = hs_add(u[r], s);
-    }
-    return;
-  }
-  const int r0 = nb1 + (blockIdx.y - 1) * 32;
-  if (r0 >= n) return;
-  const int r = r0 + lane;
-  const T s = tile_dot<T>(F + (long long)b0 * ld, ld, r, r < n, 0, db, vb, 0, 0, red);
-  if (warp == 0 && r < n) {
-    const T v = hs_sub(w[r], s);
-    if (last) xr[gi[r]] = v; else w[r] = v;   // after the last block column the boundary rows are final
+    if (b + 1 < B) sync();
   }
 }
 
-// step = -1: t = x_int − U12·x_bnd into work (all rows), the CTA owning the last diagonal block applies its inverse.
-// step = b ≥ 1 (descending): t[0:b0] -= F[0:b0, b]·t_b, the CTA owning block b-1 applies its inverse.
-template <typename T>
-__global__ void __launch_bounds__(NTH) k_sv_bwd_step(const Front* __restrict__ fronts, const T* __restrict__ pool,
-                                                      const int* __restrict__ gidx, T* __restrict__ x, long long ldx,
-                                                      T* __restrict__ work, long long wstride, long long ioff0, int f0,
-                                                      int step) {
-  constexpr int DB = SolveCfg<T>::DB;
-  const Front fr = fronts[f0 + blockIdx.x];
+template <typename T, bool CL>
+__global__ void __launch_bounds__(NTH) k_sv_big_bwd(const Front* __restrict__ fronts, const T* __restrict__ pool,
+                                                     const int* __restrict__ gidx, T* __restrict__ x, long long ldx,
+                                                     T* __restrict__ work, long long wstride, long long ioff0, int f0) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int C = CL ? (int)cluster.num_blocks() : 1;
+  const int crank = CL ? (int)cluster.block_rank() : 0;
+  const Front fr = fronts[f0 + (CL ? blockIdx.x / C : blockIdx.x)];
   const int n = fr.n, ni = fr.ni, nb = n - ni;
   const T* F = pool + fr.off;
   const long long ld = fr.ld;
-  T* xr = x + (long long)blockIdx.z * ldx;
-  T* w = work + (long long)blockIdx.z * wstride + (fr.ioff - ioff0);
+  const bool al = (fr.off & 1) == 0;
+  T* xr = x + (long long)blockIdx.y * ldx;
+  T* w = work + (long long)blockIdx.y * wstride + (fr.ioff - ioff0);
   const int* gi = gidx + fr.ioff;
-  __shared__ T vb[DB], u[DB];
-  __shared__ T red[NW][32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* sT = reinterpret_cast<T*>(smem_raw);
+  T(*spart)[64] = reinterpret_cast<T(*)[64]>(sT + 64 * 65);
+  T* su = sT + 64 * 65 + NW * 64;
+  T* svb = su + 64;
+  auto sync = [&]() { if (CL) cluster.sync(); else __syncthreads(); };
+  const int nworkers = C > 1 ? NW * (C - 1) : NW;
+  const int me = C > 1 ? (crank - 1) * NW + warp : warp;
+  const bool worker = C == 1 || crank > 0;
   const int B = (ni + DB - 1) / DB;
-  if (step < 0) {
-    // rows of the last diagonal block go to blockIdx.y == 0, the rest in 32-row tiles
-    const int l0 = (B - 1) * DB, dl = ni - l0;
-    const bool diag = blockIdx.y == 0;
-    const int rbase = diag ? l0 : (blockIdx.y - 1) * 32;
-    const int rend = diag ? ni : min(l0, rbase + 32);
-    if (rbase >= rend) return;
-    // U12·x_bnd in chunks of DB boundary entries
-    T acc[(DB + 31) / 32];
+  const int l0 = (B - 1) * DB, dl = ni - l0;
+  // phase 0: t = x_int − U12·x_bnd (boundary values in chunks of 64 through shared memory), then CTA 0 applies the
+  // inverse of the last diagonal block
+  {
+    const int ntop = l0 / 32;
+    T acc_d = hs_zero<T>();           // CTA 0: thread tid < dl accumulates row l0 + tid … via k-split partials
+    T accw[4];                        // worker: up to 4 tiles per warp kept in registers, more go through w
 #pragma unroll
-    for (int q = 0; q < (DB + 31) / 32; ++q) acc[q] = hs_zero<T>();
-    for (int c0 = 0; c0 < nb; c0 += DB) {
-      const int cw = min(DB, nb - c0);
+    for (int q = 0; q < 4; ++q) accw[q] = hs_zero<T>();
+    const int tiles_mine = worker ? (ntop - me + nworkers - 1) / nworkers : 0;
+    const bool inreg = tiles_mine <= 4;
+    if (worker && !inreg)
+      for (int t = me; t < ntop; t += nworkers) { const int r = t * 32 + lane; stcg(&w[r], xr[gi[r]]); }
+    for (int c0 = 0; c0 < nb; c0 += 64) {
+      const int cw = min(64, nb - c0);
       __syncthreads();
-      for (int k = tid; k < cw; k += NTH) vb[k] = xr[gi[ni + c0 + k]];
+      if (tid < 64) svb[tid] = tid < cw ? xr[gi[ni + c0 + tid]] : hs_zero<T>();
       __syncthreads();
+      const T* Fc = F + (long long)(ni + c0) * ld;
+      if (crank == 0) {  // rows of the last diagonal block: k-split over the warps, reduced at the end
+        T a0 = hs_zero<T>(), a1 = hs_zero<T>();
+        for (int k = warp; k < cw; k += NW) {
+          const T vk = svb[k];
+          if (lane < dl) a0 = hs_fma(a0, Fc[(long long)k * ld + l0 + lane], vk);
+          if (lane + 32 < dl) a1 = hs_fma(a1, Fc[(long long)k * ld + l0 + lane + 32], vk);
+        }
+        spart[warp][lane] = a0; spart[warp][lane + 32] = a1;
+        __syncthreads();
+        if (tid < 64) {
+#pragma unroll
+          for (int wv = 0; wv < NW; ++wv) acc_d = hs_add(acc_d, spart[wv][tid]);
+        }
+      }
+      if (worker) {
+        int q = 0;
+        for (int t = me; t < ntop; t += nworkers, ++q) {
+          const int r = t * 32 + lane;
+          const T a = row_dot<T>(Fc + r, ld, cw, svb, true);
+          if (inreg) { if (q < 4) accw[q] = hs_add(accw[q], a); }
+          else stcg(&w[r], hs_sub(ldcg(&w[r]), a));
+        }
+      }
+    }
+    if (worker && inreg) {
       int q = 0;
-      for (int r0 = rbase; r0 < rend; r0 += 32, ++q) {
-        const int r = r0 + lane;
-        const T s = tile_dot<T>(F + (long long)(ni + c0) * ld, ld, r, r < rend, 0, cw, vb, 0, 0, red);
-        if (warp == 0) acc[q] = hs_add(acc[q], s);
+      for (int t = me; t < ntop; t += nworkers, ++q) {
+        const int r = t * 32 + lane;
+        if (q < 4) stcg(&w[r], hs_sub(xr[gi[r]], accw[q]));
       }
     }
-    int q = 0;
-    for (int r0 = rbase; r0 < rend; r0 += 32, ++q) {
-      const int r = r0 + lane;
-      if (warp == 0 && r < rend) {
-        const T v = hs_sub(xr[gi[r]], acc[q]);
-        if (diag) u[r - l0] = v; else w[r] = v;
-      }
+    if (crank == 0) {
+      __syncthreads();
+      const T win = tid < dl ? hs_sub(xr[gi[l0 + tid]], acc_d) : hs_zero<T>();
+      const T y = diag_cta<T>(F, ld, 0, svb, win, dl, F + (long long)l0 * ld + l0, dl, 2, sT, spart, su);
+      if (tid < dl) { stcg(&w[l0 + tid], y); xr[gi[l0 + tid]] = y; }
     }
-    if (!diag) return;
-    __syncthreads();
-    for (int r0 = 0; r0 < dl; r0 += 32) {
-      const int r = r0 + lane;
-      const T s = tile_dot<T>(F + (long long)(l0 + r0) * ld + l0, ld, r, r < dl, 0, dl - r0, u + r0, 2, lane, red);
-      if (warp == 0 && r < dl) { w[l0 + r] = s; xr[gi[l0 + r]] = s; }
-    }
-    return;
   }
-  // apply block column `step` (≥ 1) to the rows above it
-  const int b0 = step * DB;
-  if (b0 >= ni || step < 1) return;
-  const int b1 = min(b0 + DB, ni), db = b1 - b0;
-  const int p0 = b0 - DB;  // previous diagonal block [p0, b0)
-  for (int k = tid; k < db; k += NTH) vb[k] = w[b0 + k];
-  __syncthreads();
-  if (blockIdx.y == 0) {
-    for (int r0 = 0; r0 < DB; r0 += 32) {
-      const int r = p0 + r0 + lane;
-      const T s = tile_dot<T>(F + (long long)b0 * ld, ld, r, true, 0, db, vb, 0, 0, red);
-      if (warp == 0) u[r0 + lane] = hs_sub(w[r], s);
-    }
+  for (int b = B - 1; b >= 1; --b) {
+    sync();
+    const int b0 = b * DB, b1 = min(b0 + DB, ni), db = b1 - b0;
+    const int p0 = b0 - DB;  // previous diagonal block [p0, b0), always full
+    if (tid < 64) svb[tid] = tid < db ? ldcg(&w[b0 + tid]) : hs_zero<T>();
     __syncthreads();
-    for (int r0 = 0; r0 < DB; r0 += 32) {
-      const int r = r0 + lane;
-      const T s = tile_dot<T>(F + (long long)(p0 + r0) * ld + p0, ld, r, true, 0, DB - r0, u + r0, 2, lane, red);
-      if (warp == 0) { w[p0 + r] = s; xr[gi[p0 + r]] = s; }
+    const T* Fb = F + (long long)b0 * ld;
+    if (crank == 0) {
+      const T win = tid < 64 ? ldcg(&w[p0 + tid]) : hs_zero<T>();
+      const T y = diag_cta<T>(Fb + p0, ld, db, svb, win, 64, F + (long long)p0 * ld + p0, 64, 2, sT, spart, su);
+      if (tid < 64) { stcg(&w[p0 + tid], y); xr[gi[p0 + tid]] = y; }
     }
-    return;
+    if (worker) {
+      constexpr int TR = TileRows<T>::N;
+      const int ntop = (p0 + TR - 1) / TR;
+      for (int t = me; t < ntop; t += nworkers)
+        tile_update<T>(Fb, ld, db, svb, t * TR, p0, al, w, xr, gi, false, nullptr);
+    }
   }
-  const int r0 = (blockIdx.y - 1) * 32;
-  if (r0 >= p0) return;
-  const int r = r0 + lane;
-  const T s = tile_dot<T>(F + (long long)b0 * ld, ld, r, r < p0, 0, db, vb, 0, 0, red);
-  if (warp == 0 && r < p0) w[r] = hs_sub(w[r], s);
 }
 
 template <typename T> void prep_impl(hs_fac* f, const Level& L) {
-  constexpr int DB = SolveCfg<T>::DB;
   if (L.max_ni == 0) return;
-  const int db = std::min(DB, L.max_ni);
-  const size_t sm = ((size_t)db * (db | 1) + 2 * db) * sizeof(T);
   dim3 grid(L.f1 - L.f0, (L.max_ni + DB - 1) / DB);
-  k_trtri_diag<T><<<grid, 128, sm, f->ctx->stream>>>(f->d_fronts, (T*)f->pool, L.f0);
+  const int dbm = std::min(DB, L.max_ni), lds = dbm | 1;
+  k_trtri_diag<T><<<grid, 128, (size_t)2 * lds * lds * sizeof(T), f->ctx->stream>>>(f->d_fronts, (T*)f->pool, L.f0, lds);
   CUDA_OK(cudaGetLastError());
   f->stats.launches_factor += 1;
 }
 
+template <typename T> constexpr size_t big_smem() { return (64 * 65 + NW * 64 + 128) * sizeof(T); }
+
+static int pow2_ceil_i(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+template <typename T, bool FWD> void launch_big(hs_fac* f, const Level& L, int nbig, int64_t nrhs, T* x) {
+  cudaStream_t st = f->ctx->stream;
+  const int C = std::min(f->ctx->max_cluster, std::max(1, pow2_ceil_i((L.max_n + 255) / 256)));
+  const Front* fr = f->d_fronts;
+  const T* pool = (const T*)f->pool;
+  const int* gidx = f->d_gidx;
+  const int* rperm = f->d_rperm;
+  T* work = (T*)f->d_work;
+  long long ldx = f->n, ws = f->max_level_idx, ioff0 = L.ioff0;
+  int f0 = L.f0;
+  if (C == 1) {
+    dim3 g(nbig, (unsigned)nrhs);
+    if (FWD) k_sv_big_fwd<T, false><<<g, NTH, big_smem<T>(), st>>>(fr, pool, gidx, rperm, x, ldx, work, ws, ioff0, f0);
+    else k_sv_big_bwd<T, false><<<g, NTH, big_smem<T>(), st>>>(fr, pool, gidx, x, ldx, work, ws, ioff0, f0);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(nbig * C), (unsigned)nrhs);
+    cfg.blockDim = dim3(NTH);
+    cfg.dynamicSmemBytes = big_smem<T>();
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    if (FWD) CUDA_OK(cudaLaunchKernelEx(&cfg, k_sv_big_fwd<T, true>, fr, pool, gidx, rperm, x, ldx, work, ws, ioff0, f0));
+    else CUDA_OK(cudaLaunchKernelEx(&cfg, k_sv_big_bwd<T, true>, fr, pool, gidx, x, ldx, work, ws, ioff0, f0));
+  }
+  CUDA_OK(cudaGetLastError());
+  ++f->stats.launches_solve;
+}
+
 template <typename T> void run_impl(hs_fac* f, int64_t nrhs, void* xv) {
-  constexpr int DB = SolveCfg<T>::DB;
   cudaStream_t st = f->ctx->stream;
   T* x = (T*)xv;
   const T* pool = (const T*)f->pool;
-  T* work = (T*)f->d_work;
-  const long long ws = f->max_level_idx;
   hs_stats_t& s = f->stats;
   auto nbig_of = [&](const Level& L) {
     return (int)(std::partition_point(L.ni_sorted.begin(), L.ni_sorted.end(), [&](int v) { return v > DB; }) - L.ni_sorted.begin());
@@ -381,21 +578,7 @@ template <typename T> void run_impl(hs_fac* f, int64_t nrhs, void* xv) {
   for (size_t li = 0; li < f->levels.size(); ++li) {  // post-order
     const Level& L = f->levels[li];
     const int nf = L.f1 - L.f0, nbig = nbig_of(L);
-    if (nbig > 0) {
-      const int B = (L.max_ni + DB - 1) / DB;
-      dim3 g0(nbig, (L.max_n + 32 * NW * 4 - 1) / (32 * NW * 4), (unsigned)nrhs);
-      k_sv_fwd_step<T><<<g0, NTH, 0, st>>>(f->d_fronts, pool, f->d_gidx, f->d_rperm, x, f->n, work, ws, L.ioff0, L.f0, -1);
-      ++s.launches_solve;
-      for (int b = 0; b < B; ++b) {
-        const int nact = (int)(std::partition_point(L.ni_sorted.begin(), L.ni_sorted.begin() + nbig, [&](int v) { return v > b * DB; }) -
-                               L.ni_sorted.begin());
-        if (nact == 0) break;
-        const int rows_after = std::max(0, L.max_n - b * DB);
-        dim3 g(nact, 1 + (rows_after + 31) / 32, (unsigned)nrhs);
-        k_sv_fwd_step<T><<<g, NTH, 0, st>>>(f->d_fronts, pool, f->d_gidx, f->d_rperm, x, f->n, work, ws, L.ioff0, L.f0, b);
-        ++s.launches_solve;
-      }
-    }
+    if (nbig > 0) launch_big<T, true>(f, L, nbig, nrhs, x);
     if (nf - nbig > 0) {
       dim3 g(nf - nbig, (unsigned)nrhs);
       k_sv_small_fwd<T><<<g, NTH, 0, st>>>(f->d_fronts, pool, f->d_gidx, f->d_rperm, x, f->n, L.f0 + nbig);
@@ -405,20 +588,7 @@ template <typename T> void run_impl(hs_fac* f, int64_t nrhs, void* xv) {
   for (size_t li = f->levels.size(); li-- > 0;) {  // pre-order
     const Level& L = f->levels[li];
     const int nf = L.f1 - L.f0, nbig = nbig_of(L);
-    if (nbig > 0) {
-      const int B = (L.max_ni + DB - 1) / DB;
-      dim3 g0(nbig, 1 + (L.max_ni + 31) / 32, (unsigned)nrhs);
-      k_sv_bwd_step<T><<<g0, NTH, 0, st>>>(f->d_fronts, pool, f->d_gidx, x, f->n, work, ws, L.ioff0, L.f0, -1);
-      ++s.launches_solve;
-      for (int b = B - 1; b >= 1; --b) {
-        const int nact = (int)(std::partition_point(L.ni_sorted.begin(), L.ni_sorted.begin() + nbig, [&](int v) { return v > b * DB; }) -
-                               L.ni_sorted.begin());
-        if (nact == 0) continue;
-        dim3 g(nact, 1 + ((b - 1) * DB + 31) / 32, (unsigned)nrhs);
-        k_sv_bwd_step<T><<<g, NTH, 0, st>>>(f->d_fronts, pool, f->d_gidx, x, f->n, work, ws, L.ioff0, L.f0, b);
-        ++s.launches_solve;
-      }
-    }
+    if (nbig > 0) launch_big<T, false>(f, L, nbig, nrhs, x);
     if (nf - nbig > 0) {
       dim3 g(nf - nbig, (unsigned)nrhs);
       const size_t sm = (size_t)std::max(L.max_nb, 1) * sizeof(T);
@@ -432,13 +602,21 @@ template <typename T> void run_impl(hs_fac* f, int64_t nrhs, void* xv) {
 }  // namespace
 
 void hs_solve_setup() {
-  CUDA_OK(cudaFuncSetAttribute(k_trtri_diag<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  CUDA_OK(cudaFuncSetAttribute(k_trtri_diag<cplx>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CUDA_OK(cudaFuncSetAttribute(k_trtri_diag<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (DB + 1) * (DB + 1) * (int)sizeof(double)));
+  CUDA_OK(cudaFuncSetAttribute(k_trtri_diag<cplx>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (DB + 1) * (DB + 1) * (int)sizeof(cplx)));
+  CUDA_OK(cudaFuncSetAttribute(k_sv_big_fwd<cplx, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_smem<cplx>()));
+  CUDA_OK(cudaFuncSetAttribute(k_sv_big_bwd<cplx, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_smem<cplx>()));
+  CUDA_OK(cudaFuncSetAttribute(k_sv_big_fwd<cplx, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_smem<cplx>()));
+  CUDA_OK(cudaFuncSetAttribute(k_sv_big_bwd<cplx, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_smem<cplx>()));
+  CUDA_OK(cudaFuncSetAttribute(k_sv_big_fwd<double, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  CUDA_OK(cudaFuncSetAttribute(k_sv_big_bwd<double, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  CUDA_OK(cudaFuncSetAttribute(k_sv_big_fwd<cplx, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  CUDA_OK(cudaFuncSetAttribute(k_sv_big_bwd<cplx, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   CUDA_OK(cudaFuncSetAttribute(k_sv_small_bwd<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CUDA_OK(cudaFuncSetAttribute(k_sv_small_bwd<cplx>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 }
 
-int hs_solve_block(hs_dtype dt) { return dt == HS_F64 ? SolveCfg<double>::DB : SolveCfg<cplx>::DB; }
+int hs_solve_block(hs_dtype) { return DB; }
 
 void hs_solve_prep(hs_fac* f, const Level& L) {
   if (f->dtype == HS_F64) prep_impl<double>(f, L); else prep_impl<cplx>(f, L);
