@@ -20,7 +20,7 @@ i64p = C.POINTER(C.c_int64)
 class hs_opts(C.Structure):
     _fields_ = [("swlevel", C.c_int64), ("swsize", C.c_int64), ("atol", C.c_double), ("rtol", C.c_double),
                 ("c_tol", C.c_double), ("leafsize", C.c_int64), ("kest", C.c_int64), ("stepsize", C.c_int64),
-                ("verbose", C.c_int32), ("keep_schur", C.c_int32)]
+                ("verbose", C.c_int32), ("subtree", C.c_int32)]
 
 
 class hs_elimtree(C.Structure):
@@ -67,6 +67,11 @@ PROTOTYPES = [
     ("hs_factor", C.c_int32, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(hs_tree),
                               C.POINTER(hs_opts), C.c_int32, C.POINTER(C.c_void_p)]),
     ("hs_refactor", C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32]),
+    ("hs_analyze", C.c_int32, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(hs_tree),
+                               C.POINTER(hs_opts), C.c_int32, C.POINTER(C.c_void_p)]),
+    ("hs_schur_export", C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),
+    ("hs_schur_import", C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),
+    ("hs_solve_sweep", C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32]),
     ("hs_factor_free", C.c_int32, [C.c_void_p]),
     ("hs_solve", C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32]),
     ("hs_node_get", C.c_int32, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, i64p]),

@@ -254,6 +254,12 @@ template <typename T> static void numeric(hs_fac* f) {
       k_scatter_A<T><<<grid, 256, 0, st>>>(f->d_fronts, pool, f->d_gidx, f->d_own, f->d_pos, f->d_colptr,
                                             f->d_rowval, (const T*)f->d_nzval, L.f0);
       s.launches_factor += 3;
+      for (int i = L.f0; i < L.f1; ++i) {  // external leaves: the front IS the imported Schur block
+        if (!f->ext_src[i]) continue;
+        const Front& fr = f->fronts[i];
+        CUDA_OK(cudaMemcpy2DAsync(pool + fr.off, (size_t)fr.ld * sizeof(T), f->ext_src[i], (size_t)f->ext_ld[i] * sizeof(T),
+                                  (size_t)fr.n * sizeof(T), fr.n, cudaMemcpyDeviceToDevice, st));
+      }
       if (li > 0 && !f->levels[li - 1].pseudo) {
         const Level& Lc = f->levels[li - 1];
         if (Lc.max_nb > 0) {
@@ -391,7 +397,7 @@ static void build_plan(hs_fac* f, const hs_tree* t) {
     if (f->level[a] != f->level[b]) return f->level[a] > f->level[b];
     return f->node_ni[a] > f->node_ni[b];
   });
-  const bool pseudo = f->node_nb[root] > 0;
+  const bool pseudo = f->node_nb[root] > 0 && !f->opts.subtree;
   const int nfr = (int)nn + (pseudo ? 1 : 0);
   f->fronts.assign(nfr, Front{});
   f->node2front.assign(nn, -1);
@@ -477,6 +483,8 @@ static void build_plan(hs_fac* f, const hs_tree* t) {
     flops += 2.0 / 3.0 * ni * ni * ni;
     sbytes += ni * ni;
   }
+  f->ext_src.assign(f->fronts.size(), nullptr);
+  f->ext_ld.assign(f->fronts.size(), 0);
   f->pool_elems = poff;
   f->idx_total = ioff;
   f->max_level_idx = 0;
@@ -512,9 +520,9 @@ __global__ void k_shift_index(long long* a, long long n, long long base) {
   if (i < n) a[i] -= base;
 }
 
-extern "C" int32_t hs_factor(hs_ctx* ctx, hs_dtype dtype, int64_t n, const int64_t* colptr, const int64_t* rowval,
-                             const void* nzval, const hs_tree* tree, const hs_opts* opts, int32_t on_device,
-                             hs_fac** out) {
+static int32_t factor_impl(hs_ctx* ctx, hs_dtype dtype, int64_t n, const int64_t* colptr, const int64_t* rowval,
+                           const void* nzval, const hs_tree* tree, const hs_opts* opts, int32_t on_device,
+                           hs_fac** out, bool do_numeric) {
   HS_TRY_BEGIN
   if (!ctx || !colptr || !rowval || !nzval || !tree || !out) return hs_fail(HS_EARG, "hs_factor: null argument");
   if (dtype != HS_F64 && dtype != HS_C64) return hs_fail(HS_EARG, "hs_factor: dtype must be HS_F64 or HS_C64");
@@ -527,7 +535,7 @@ extern "C" int32_t hs_factor(hs_ctx* ctx, hs_dtype dtype, int64_t n, const int64
   f->esz = dtype == HS_C64 ? 16 : 8;
   f->n = n;
   if (opts) f->opts = *opts;
-  else { f->opts = hs_opts{5, 1, 1e-6, 1e-6, 0.5, 32, -1, 10, 0, 1}; }
+  else { f->opts = hs_opts{5, 1, 1e-6, 1e-6, 0.5, 32, -1, 10, 0, 0}; }
   check_opts(f->opts);
   CUDA_OK(cudaEventCreate(&f->ev0));
   CUDA_OK(cudaEventCreate(&f->ev1));
@@ -566,7 +574,7 @@ extern "C" int32_t hs_factor(hs_ctx* ctx, hs_dtype dtype, int64_t n, const int64
   CUDA_OK(cudaStreamSynchronize(st));
   auto t_h2d = std::chrono::steady_clock::now();
   f->stats.ms_h2d = std::chrono::duration<double, std::milli>(t_h2d - t_plan).count();
-  if (dtype == HS_F64) numeric<double>(f.get()); else numeric<cplx>(f.get());
+  if (do_numeric) { if (dtype == HS_F64) numeric<double>(f.get()); else numeric<cplx>(f.get()); }
   *out = f.release();
   if ((*out)->stats.singular_front >= 0 || (*out)->stats.singular_col >= 0)
     return hs_fail(HS_ESINGULAR, "hs_factor: exactly singular pivot block in node " + std::to_string((*out)->stats.singular_front) +
@@ -575,11 +583,83 @@ extern "C" int32_t hs_factor(hs_ctx* ctx, hs_dtype dtype, int64_t n, const int64
   HS_TRY_END
 }
 
+extern "C" int32_t hs_factor(hs_ctx* ctx, hs_dtype dtype, int64_t n, const int64_t* colptr, const int64_t* rowval,
+                             const void* nzval, const hs_tree* tree, const hs_opts* opts, int32_t on_device,
+                             hs_fac** out) {
+  return factor_impl(ctx, dtype, n, colptr, rowval, nzval, tree, opts, on_device, out, true);
+}
+
+extern "C" int32_t hs_analyze(hs_ctx* ctx, hs_dtype dtype, int64_t n, const int64_t* colptr, const int64_t* rowval,
+                              const void* nzval, const hs_tree* tree, const hs_opts* opts, int32_t on_device,
+                              hs_fac** out) {
+  return factor_impl(ctx, dtype, n, colptr, rowval, nzval, tree, opts, on_device, out, false);
+}
+
+extern "C" int32_t hs_schur_export(hs_fac* f, int64_t node, void* dst, int64_t ld) {
+  HS_TRY_BEGIN
+  if (!f || !dst) return hs_fail(HS_EARG, "hs_schur_export: null argument");
+  if (node < 0 || node >= f->nnodes) return hs_fail(HS_EARG, "hs_schur_export: node out of range");
+  const Front& fr = f->fronts[f->node2front[node]];
+  const int nb = fr.n - fr.ni;
+  if (ld < nb) return hs_fail(HS_EDIM, "hs_schur_export: leading dimension smaller than the boundary");
+  if (f->pseudo_front >= 0 && f->node2front[node] == f->root_front)
+    return hs_fail(HS_EARG, "hs_schur_export: the root boundary block was factored for the solve; factor with opts.subtree = 1");
+  CUDA_OK(cudaSetDevice(f->ctx->device));
+  if (nb) {
+    const char* src = (const char*)f->pool + ((size_t)fr.off + (size_t)fr.ni * fr.ld + fr.ni) * f->esz;
+    CUDA_OK(cudaMemcpy2DAsync(dst, (size_t)ld * f->esz, src, (size_t)fr.ld * f->esz, (size_t)nb * f->esz, nb,
+                              cudaMemcpyDeviceToDevice, f->ctx->stream));
+    CUDA_OK(cudaStreamSynchronize(f->ctx->stream));
+  }
+  return HS_OK;
+  HS_TRY_END
+}
+
+extern "C" int32_t hs_schur_import(hs_fac* f, int64_t node, const void* src, int64_t ld) {
+  HS_TRY_BEGIN
+  if (!f || !src) return hs_fail(HS_EARG, "hs_schur_import: null argument");
+  if (node < 0 || node >= f->nnodes) return hs_fail(HS_EARG, "hs_schur_import: node out of range");
+  const int fi = f->node2front[node];
+  Front& fr = f->fronts[fi];
+  if (f->left[node] >= 0 || fr.ni != 0) return hs_fail(HS_EARG, "hs_schur_import: node must be a leaf with an empty int set");
+  if (ld < fr.n) return hs_fail(HS_EDIM, "hs_schur_import: leading dimension smaller than the boundary");
+  CUDA_OK(cudaSetDevice(f->ctx->device));
+  f->ext_src[fi] = src;
+  f->ext_ld[fi] = ld;
+  if (!(fr.flags & 4)) {  // tell the assembly kernels not to gather A into this front
+    fr.flags |= 4;
+    CUDA_OK(cudaMemcpy(f->d_fronts + fi, &fr, sizeof(Front), cudaMemcpyHostToDevice));
+  }
+  return HS_OK;
+  HS_TRY_END
+}
+
+extern "C" int32_t hs_solve_sweep(hs_fac* f, int64_t nrhs, void* x, int64_t ldx, int32_t which) {
+  HS_TRY_BEGIN
+  if (!f || !x) return hs_fail(HS_EARG, "hs_solve_sweep: null argument");
+  if (nrhs <= 0 || !(which & 3)) return HS_OK;
+  if (ldx != f->n) return hs_fail(HS_EDIM, "hs_solve_sweep: ldx must equal n");
+  CUDA_OK(cudaSetDevice(f->ctx->device));
+  if (nrhs > f->rhs_cap) {
+    cudaFree(f->d_x); cudaFree(f->d_work);
+    f->d_x = f->d_work = nullptr;
+    CUDA_OK(cudaMalloc(&f->d_x, (size_t)f->n * nrhs * f->esz));
+    CUDA_OK(cudaMalloc(&f->d_work, std::max<size_t>((size_t)f->max_level_idx * nrhs, 1) * f->esz));
+    f->rhs_cap = nrhs;
+  }
+  f->stats.launches_solve = 0;
+  hs_solve_run(f, nrhs, x, which);
+  f->ctx->launches += f->stats.launches_solve;
+  CUDA_OK(cudaStreamSynchronize(f->ctx->stream));
+  return HS_OK;
+  HS_TRY_END
+}
+
 extern "C" int32_t hs_refactor(hs_fac* f, const void* nzval, int32_t on_device) {
   HS_TRY_BEGIN
-  if (!f || !nzval) return hs_fail(HS_EARG, "hs_refactor: null argument");
+  if (!f) return hs_fail(HS_EARG, "hs_refactor: null argument");
   CUDA_OK(cudaSetDevice(f->ctx->device));
-  if (nzval != f->d_nzval)
+  if (nzval && nzval != f->d_nzval)
     CUDA_OK(cudaMemcpyAsync(f->d_nzval, nzval, (size_t)f->nnz * f->esz, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
                             f->ctx->stream));
   if (f->dtype == HS_F64) numeric<double>(f); else numeric<cplx>(f);
@@ -612,7 +692,7 @@ template <typename T> static void solve_impl(hs_fac* f, int64_t nrhs, const void
   CUDA_OK(cudaEventRecord(f->ev0, st));
   hs_stats_t& s = f->stats;
   s.launches_solve = 0;
-  hs_solve_run(f, nrhs, x);
+  hs_solve_run(f, nrhs, x, 3);
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaEventRecord(f->ev1, st));
   f->ctx->launches += s.launches_solve;

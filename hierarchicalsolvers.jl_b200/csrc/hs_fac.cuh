@@ -56,6 +56,9 @@ struct hs_fac {
   std::vector<Front> fronts;
   std::vector<Level> levels;  // deepest first, root last (+ pseudo front for a non-empty root boundary)
   int root_front = -1, pseudo_front = -1;
+  // external leaves (subtree-per-GPU): front id → device buffer its Schur block is imported from
+  std::vector<const void*> ext_src;
+  std::vector<long long> ext_ld;
   long long pool_elems = 0, idx_total = 0, max_level_idx = 0;
   // device
   void* pool = nullptr;
@@ -100,7 +103,7 @@ inline void hs_panel_launch(hs_fac* f, int W, int f0, int nact, int j0, int m) {
 void hs_solve_setup();
 int hs_solve_block(hs_dtype dt);
 void hs_solve_prep(hs_fac* f, const Level& L);
-void hs_solve_run(hs_fac* f, int64_t nrhs, void* x);
+void hs_solve_run(hs_fac* f, int64_t nrhs, void* x, int which);  // which: 1 forward, 2 backward, 3 both
 
 // hs_small.cu
 int hs_small_max_n(hs_dtype dt);

@@ -44,7 +44,7 @@ __global__ void k_scatter_A(const Front* __restrict__ fronts, T* __restrict__ po
   const int fi = f0 + blockIdx.x;
   const Front fr = fronts[fi];
   const int k = blockIdx.y * blockDim.x + threadIdx.x;
-  if (k >= fr.n) return;
+  if (k >= fr.n || (fr.flags & 4)) return;  // bit2: external leaf, its front is an imported Schur block
   const int g = gidx[fr.ioff + k];
   T* col = pool + fr.off + (long long)k * fr.ld;
   const bool leaf = fr.ni_l < 0;

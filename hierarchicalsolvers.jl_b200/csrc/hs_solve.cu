@@ -567,7 +567,7 @@ template <typename T, bool FWD> void launch_big(hs_fac* f, const Level& L, int n
   ++f->stats.launches_solve;
 }
 
-template <typename T> void run_impl(hs_fac* f, int64_t nrhs, void* xv) {
+template <typename T> void run_impl(hs_fac* f, int64_t nrhs, void* xv, int which) {
   cudaStream_t st = f->ctx->stream;
   T* x = (T*)xv;
   const T* pool = (const T*)f->pool;
@@ -575,7 +575,7 @@ template <typename T> void run_impl(hs_fac* f, int64_t nrhs, void* xv) {
   auto nbig_of = [&](const Level& L) {
     return (int)(std::partition_point(L.ni_sorted.begin(), L.ni_sorted.end(), [&](int v) { return v > DB; }) - L.ni_sorted.begin());
   };
-  for (size_t li = 0; li < f->levels.size(); ++li) {  // post-order
+  for (size_t li = 0; (which & 1) && li < f->levels.size(); ++li) {  // post-order
     const Level& L = f->levels[li];
     const int nf = L.f1 - L.f0, nbig = nbig_of(L);
     if (nbig > 0) launch_big<T, true>(f, L, nbig, nrhs, x);
@@ -585,7 +585,7 @@ template <typename T> void run_impl(hs_fac* f, int64_t nrhs, void* xv) {
       ++s.launches_solve;
     }
   }
-  for (size_t li = f->levels.size(); li-- > 0;) {  // pre-order
+  for (size_t li = f->levels.size(); (which & 2) && li-- > 0;) {  // pre-order
     const Level& L = f->levels[li];
     const int nf = L.f1 - L.f0, nbig = nbig_of(L);
     if (nbig > 0) launch_big<T, false>(f, L, nbig, nrhs, x);
@@ -622,6 +622,6 @@ void hs_solve_prep(hs_fac* f, const Level& L) {
   if (f->dtype == HS_F64) prep_impl<double>(f, L); else prep_impl<cplx>(f, L);
 }
 
-void hs_solve_run(hs_fac* f, int64_t nrhs, void* x) {
-  if (f->dtype == HS_F64) run_impl<double>(f, nrhs, x); else run_impl<cplx>(f, nrhs, x);
+void hs_solve_run(hs_fac* f, int64_t nrhs, void* x, int which) {
+  if (f->dtype == HS_F64) run_impl<double>(f, nrhs, x, which); else run_impl<cplx>(f, nrhs, x, which);
 }

@@ -38,7 +38,7 @@ def chkopts(opts: SolverOptions) -> None:
     if not opts.leafsize >= 1: bad("leafsize")
 
 
-def to_c(opts: SolverOptions, keep_schur: bool = True) -> _lib.hs_opts:
+def to_c(opts: SolverOptions, subtree: bool = False) -> _lib.hs_opts:
     return _lib.hs_opts(int(opts.swlevel), int(opts.swsize), float(opts.atol), float(opts.rtol), float(opts.c_tol),
                         int(opts.leafsize), int(opts.kest), int(opts.stepsize), int(bool(opts.verbose)),
-                        int(bool(keep_schur)))
+                        int(bool(subtree)))

@@ -1,0 +1,294 @@
+"""Subtree-per-GPU factorization and solve.
+
+The reference is single-process (no Threads / Distributed / MPI anywhere in src/), so this layer has no counterpart
+there; it partitions the same elimination tree `_factor` recurses over (factorization.jl:14-27) at a cut:
+
+  * every rank owns one disjoint bottom subtree and factors it on its own GPU (``hs_factor`` with ``opts.subtree``);
+  * the Schur complement of each subtree root — the only data the parent front needs (factorization.jl:118-121) —
+    is all-gathered (NCCL over NVLink); because sibling boundaries are disjoint (nesteddissection.jl:64-65) this is a
+    concatenation, never a reduction;
+  * the few fronts above the cut are factored redundantly on every rank from the gathered blocks, so the solve needs
+    no broadcast of the top part;
+  * ``ldiv``: local forward sweep → all-gather of the subtree-root boundary segments → top solve (replicated) → local
+    backward sweep → all-gather of the subtree interiors.  Two small collectives and one n-sized one per application.
+
+The numerical work goes through an *engine*; the product engine is the CUDA library (``CudaEngine``).  Tests on CPU
+plug in an engine built on the oracle to exercise this host logic with the ``gloo`` backend.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import _lib
+from .nesteddissection import NDLoc, NestedDissection
+from .options import SolverOptions, chkopts, to_c
+
+__all__ = ["partition_tree", "TreePartition", "DistributedFactor", "CudaEngine"]
+
+
+# ------------------------------------------------------------------------------------------------
+# host logic: cut the tree
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class TreePartition:
+    cut: List[int]                 # post-order ids of the P subtree roots, one per rank, ascending
+    sub_nd: List[NestedDissection]
+    sub_loc: List[NDLoc]
+    top_nd: NestedDissection
+    top_loc: NDLoc
+    top_leaf: List[int]            # node id inside the top tree of every cut node
+    int_idx: List[np.ndarray]      # per rank: 1-based DOFs eliminated inside its subtree
+    bnd_idx: List[np.ndarray]      # per rank: 1-based boundary DOFs of its subtree root
+    work: np.ndarray               # estimated flops per node
+
+
+def _front_flops(nd: NestedDissection) -> np.ndarray:
+    ni = np.diff(nd.int_ptr).astype(np.float64)
+    nb = np.diff(nd.bnd_ptr).astype(np.float64)
+    return (2.0 / 3.0) * ni ** 3 + 2.0 * ni ** 2 * nb + 2.0 * ni * nb ** 2
+
+
+def _slice_tree(nd: NestedDissection, loc: NDLoc, nodes: np.ndarray, as_leaf: set):
+    """Sub-forest given by ``nodes`` (ascending post-order ids, parents after children).  Nodes in ``as_leaf`` lose
+    their children and their ``int`` set (they become external leaves of the upper tree)."""
+    newid = -np.ones(nd.nnodes, dtype=np.int64)
+    newid[nodes] = np.arange(len(nodes))
+    out = NestedDissection(nd.elim)
+    out.nnodes = len(nodes)
+    out.analyzed = True
+    out.depth = nd.depth
+
+    def remap(child):
+        c = child[nodes].copy()
+        m = c >= 0
+        c[m] = newid[c[m]]
+        for k, g in enumerate(nodes):
+            if int(g) in as_leaf:
+                c[k] = -1
+        return c
+
+    out.left, out.right = remap(nd.left), remap(nd.right)
+
+    def ragged(ptr, idx, drop=()):
+        lens = (ptr[1:] - ptr[:-1])[nodes].copy()
+        parts = []
+        for k, g in enumerate(nodes):
+            if int(g) in drop:
+                lens[k] = 0
+            else:
+                parts.append(idx[ptr[g]:ptr[g + 1]])
+        p = np.zeros(len(nodes) + 1, dtype=np.int64)
+        np.cumsum(lens, out=p[1:])
+        return p, (np.concatenate(parts) if parts else np.zeros(0, np.int64)).astype(np.int64)
+
+    out.int_ptr, out.int_idx = ragged(nd.int_ptr, nd.int_idx, drop=as_leaf)
+    out.bnd_ptr, out.bnd_idx = ragged(nd.bnd_ptr, nd.bnd_idx)
+    out.root = len(nodes) - 1
+    ilp, ili = ragged(loc.iloc_ptr, loc.iloc_idx)
+    blp, bli = ragged(loc.bloc_ptr, loc.bloc_idx)
+    return out, NDLoc(out, ilp, ili, blp, bli), newid
+
+
+def partition_tree(nd: NestedDissection, nd_loc: NDLoc, nparts: int) -> TreePartition:
+    """Choose ``nparts`` disjoint subtrees: start from the root and repeatedly split the heaviest open subtree into
+    its two children (for a balanced tree and a power-of-two count this is the level ``log2(P)+1`` of SURVEY §8e)."""
+    nd._need_analyzed()
+    nn = nd.nnodes
+    w = _front_flops(nd)
+    sub = w.copy()            # work of the whole subtree below each node (post-order: children come first)
+    size = np.ones(nn, dtype=np.int64)
+    for k in range(nn):
+        for c in (nd.left[k], nd.right[k]):
+            if c >= 0:
+                sub[k] += sub[c]
+                size[k] += size[c]
+    open_ = [nn - 1]
+    while len(open_) < nparts:
+        cand = [k for k in open_ if nd.left[k] >= 0]
+        if not cand:
+            raise ValueError(f"elimination tree has fewer than {nparts} disjoint subtrees")
+        k = max(cand, key=lambda q: sub[q])
+        open_.remove(k)
+        open_ += [int(nd.left[k]), int(nd.right[k])]
+    cut = sorted(open_)
+    in_sub = np.zeros(nn, dtype=bool)
+    sub_nd, sub_loc, int_idx, bnd_idx = [], [], [], []
+    for g in cut:
+        nodes = np.arange(g - size[g] + 1, g + 1)      # a subtree is a contiguous post-order range
+        in_sub[nodes] = True
+        s_nd, s_loc, _ = _slice_tree(nd, nd_loc, nodes, set())
+        sub_nd.append(s_nd)
+        sub_loc.append(s_loc)
+        int_idx.append(s_nd.int_idx.copy())
+        bnd_idx.append(nd.bnd_idx[nd.bnd_ptr[g]:nd.bnd_ptr[g + 1]].copy())
+    top_nodes = np.array(sorted(set(np.nonzero(~in_sub)[0].tolist()) | set(cut)), dtype=np.int64)
+    top_nd, top_loc, newid = _slice_tree(nd, nd_loc, top_nodes, set(cut))
+    return TreePartition(cut, sub_nd, sub_loc, top_nd, top_loc, [int(newid[g]) for g in cut], int_idx, bnd_idx, w)
+
+
+# ------------------------------------------------------------------------------------------------
+# product engine: libhsolve_cuda
+# ------------------------------------------------------------------------------------------------
+def _tree_struct(nd: NestedDissection, loc: NDLoc):
+    arrs = dict(int_ptr=nd.int_ptr, int_idx=nd.int_idx, bnd_ptr=nd.bnd_ptr, bnd_idx=nd.bnd_idx, iloc_ptr=loc.iloc_ptr,
+                iloc_idx=loc.iloc_idx, bloc_ptr=loc.bloc_ptr, bloc_idx=loc.bloc_idx)
+    arrs = {k: _lib.as_i64(v) for k, v in arrs.items()}
+    arrs["left"] = np.where(nd.left >= 0, nd.left + 1, -1).astype(np.int64)
+    arrs["right"] = np.where(nd.right >= 0, nd.right + 1, -1).astype(np.int64)
+    t = _lib.hs_tree(nd.nnodes, *[_lib.ptr(arrs[k]) for k in ("left", "right", "int_ptr", "int_idx", "bnd_ptr", "bnd_idx",
+                                                              "iloc_ptr", "iloc_idx", "bloc_ptr", "bloc_idx")], 1)
+    return t, arrs
+
+
+class CudaEngine:
+    """Numerics of one rank on its GPU through the C ABI.  Vectors and Schur blocks are torch CUDA tensors so that
+    torch.distributed (NCCL) can move them without staging."""
+
+    def __init__(self, device: int = 0):
+        import torch
+        self.torch = torch
+        self.device = device
+        self.ctx = _lib.default_context(device)
+        self.handles = []
+
+    def __del__(self):
+        for h in getattr(self, "handles", []):
+            try:
+                _lib.lib.hs_factor_free(h)
+            except Exception:
+                pass
+
+    def _csc(self, A):
+        A = sp.csc_matrix(A)
+        A.sort_indices()
+        cx = np.iscomplexobj(A.data)
+        self.cx = cx
+        self.np_dtype = np.complex128 if cx else np.float64
+        self.t_dtype = self.torch.complex128 if cx else self.torch.float64
+        return (A.shape[0], _lib.as_i64(A.indptr) + 1, _lib.as_i64(A.indices) + 1,
+                np.ascontiguousarray(A.data, dtype=self.np_dtype))
+
+    def _factor(self, A, nd, loc, opts, subtree, numeric):
+        n, colptr, rowval, nz = self._csc(A)
+        tree, keep = _tree_struct(nd, loc)
+        copts = to_c(opts, subtree=subtree)
+        h = C.c_void_p()
+        fn = _lib.lib.hs_factor if numeric else _lib.lib.hs_analyze
+        rc = fn(self.ctx, _lib.HS_C64 if self.cx else _lib.HS_F64, n, colptr.ctypes.data_as(C.c_void_p),
+                rowval.ctypes.data_as(C.c_void_p), nz.ctypes.data_as(C.c_void_p), C.byref(tree), C.byref(copts), 0, C.byref(h))
+        if rc != _lib.HS_OK:
+            if h:
+                _lib.lib.hs_factor_free(h)
+            _lib.check(rc)
+        self.handles.append(h)
+        return h
+
+    def factor_subtree(self, A, nd, loc, opts):
+        return self._factor(A, nd, loc, opts, True, True)
+
+    def export_schur(self, h, node, nb, pad):
+        """Schur complement of ``node`` as a (pad, pad) column-major block (zero padded) on the device."""
+        buf = self.torch.zeros((pad, pad), dtype=self.t_dtype, device=f"cuda:{self.device}")
+        if nb:
+            _lib.check(_lib.lib.hs_schur_export(h, node, C.c_void_p(buf.data_ptr()), pad))
+        return buf
+
+    def analyze_top(self, A, nd, loc, opts):
+        return self._factor(A, nd, loc, opts, False, False)
+
+    def import_schur(self, h, node, buf, pad):
+        _lib.check(_lib.lib.hs_schur_import(h, node, C.c_void_p(buf.data_ptr()), pad))
+
+    def numeric(self, h):
+        _lib.check(_lib.lib.hs_refactor(h, None, 0))
+
+    def to_device(self, b):
+        return self.torch.from_numpy(np.ascontiguousarray(b, dtype=self.np_dtype)).to(f"cuda:{self.device}")
+
+    def to_host(self, x):
+        return x.cpu().numpy()
+
+    def sweep(self, h, x, which):
+        _lib.check(_lib.lib.hs_solve_sweep(h, 1, C.c_void_p(x.data_ptr()), x.shape[0], which))
+
+    def index(self, idx):
+        return self.torch.from_numpy(np.asarray(idx, dtype=np.int64) - 1).to(f"cuda:{self.device}")
+
+    def zeros(self, n):
+        return self.torch.zeros(n, dtype=self.t_dtype, device=f"cuda:{self.device}")
+
+    def stats(self, h):
+        s = _lib.hs_stats_t()
+        _lib.check(_lib.lib.hs_stats(h, C.byref(s)))
+        return s.asdict()
+
+
+# ------------------------------------------------------------------------------------------------
+# the distributed factorization object
+# ------------------------------------------------------------------------------------------------
+class DistributedFactor:
+    """Collective: every rank of ``group`` constructs it with the same ``A``/tree and calls ``ldiv`` together."""
+
+    def __init__(self, A, nd: NestedDissection, nd_loc: NDLoc, opts: Optional[SolverOptions] = None, engine=None,
+                 group=None, **kw):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        opts = (opts or SolverOptions()).copy(**kw)
+        chkopts(opts)
+        self.eng = engine if engine is not None else CudaEngine()
+        self.part = part = partition_tree(nd, nd_loc, self.world)
+        self.n = A.shape[0]
+        g = self.rank
+        # 1. my subtree
+        self.h_sub = self.eng.factor_subtree(A, part.sub_nd[g], part.sub_loc[g], opts)
+        # 2. exchange the subtree-root Schur complements (concatenation — boundaries are disjoint)
+        nbs = [len(b) for b in part.bnd_idx]
+        self.pad = pad = max(max(nbs), 1)
+        mine = self.eng.export_schur(self.h_sub, part.sub_nd[g].root, nbs[g], pad)
+        self.schur = [self.eng.torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(self.schur, mine, group=group)
+        self.schur_bytes = int(sum(nb * nb for nb in nbs) * mine.element_size())
+        # 3. the fronts above the cut, redundantly on every rank
+        self.h_top = self.eng.analyze_top(A, part.top_nd, part.top_loc, opts)
+        for r in range(self.world):
+            if nbs[r]:
+                self.eng.import_schur(self.h_top, part.top_leaf[r], self.schur[r], pad)
+        self.eng.numeric(self.h_top)
+        self._bidx = [self.eng.index(b) for b in part.bnd_idx]
+        self._iidx = [self.eng.index(i) for i in part.int_idx]
+        self._ipad = max(max(len(i) for i in part.int_idx), 1)
+
+    def _allgather_segments(self, x, idx_list, pad):
+        torch = self.eng.torch
+        mine = self.eng.zeros(pad)
+        k = idx_list[self.rank].shape[0]
+        if k:
+            mine[:k] = x[idx_list[self.rank]]
+        parts = [torch.empty_like(mine) for _ in range(self.world)]
+        self.dist.all_gather(parts, mine, group=self.group)
+        for r in range(self.world):
+            k = idx_list[r].shape[0]
+            if r != self.rank and k:
+                x[idx_list[r]] = parts[r][:k]
+
+    def ldiv_device(self, x):
+        """In place on a replicated device vector (every rank passes the same values)."""
+        self.eng.sweep(self.h_sub, x, 1)                       # forward inside my subtree, updates x[bnd of my root]
+        self._allgather_segments(x, self._bidx, self.pad)      # everyone learns every subtree-root boundary segment
+        self.eng.sweep(self.h_top, x, 3)                       # fronts above the cut (replicated)
+        self.eng.sweep(self.h_sub, x, 2)                       # backward inside my subtree
+        self._allgather_segments(x, self._iidx, self._ipad)    # everyone gets every subtree's interior solution
+        return x
+
+    def ldiv(self, b: np.ndarray) -> np.ndarray:
+        x = self.eng.to_device(b)
+        self.ldiv_device(x)
+        return self.eng.to_host(x)

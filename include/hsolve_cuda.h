@@ -52,7 +52,8 @@ typedef struct {
   int64_t kest;
   int64_t stepsize;
   int32_t verbose;
-  int32_t keep_schur; /* extension: 1 = keep every node's S resident (reference behaviour, FactorNode.S) */
+  int32_t subtree;    /* extension for subtree-per-GPU runs: 1 = the tree is a subtree of a larger one — its root keeps a
+                         non-empty boundary whose Schur block is exported (hs_schur_export) instead of being solved */
 } hs_opts;
 
 /* Serialized elimination tree, the ragged form of the `.mat` schema that parse_elimtree consumes
@@ -147,8 +148,23 @@ int32_t hs_symbolic_free(hs_symbolic* s);
  * `on_device` != 0: colptr/rowval/nzval are device pointers already resident in HBM (0-based int64). */
 int32_t hs_factor(hs_ctx* ctx, hs_dtype dtype, int64_t n, const int64_t* colptr, const int64_t* rowval,
                   const void* nzval, const hs_tree* tree, const hs_opts* opts, int32_t on_device, hs_fac** out);
-/* same plan and sparsity, new values (the numeric part of `factor` alone) */
+/* same plan and sparsity, new values (the numeric part of `factor` alone); nzval == NULL re-uses the stored values */
 int32_t hs_refactor(hs_fac* fac, const void* nzval, int32_t on_device);
+/* hs_factor without the numeric phase (plan + upload only); follow with hs_schur_import / hs_refactor */
+int32_t hs_analyze(hs_ctx* ctx, hs_dtype dtype, int64_t n, const int64_t* colptr, const int64_t* rowval,
+                   const void* nzval, const hs_tree* tree, const hs_opts* opts, int32_t on_device, hs_fac** out);
+
+/* ---- subtree-per-GPU plumbing -------------------------------------------------------
+ * Disjoint bottom subtrees are factored one per GPU with opts.subtree = 1; each exports the Schur complement of its
+ * root (nb×nb, rows/cols in the node's `bnd` order, column-major with leading dimension ld) into a device buffer that
+ * the host moves over NCCL.  The upper part of the tree is a tree whose leaves are those roots with an EMPTY `int`:
+ * hs_schur_import registers the device buffer such a leaf's front is copied from (instead of gathering A) by the
+ * next hs_refactor.  Child boundaries are disjoint, so the exchange is a concatenation, never a reduction. */
+int32_t hs_schur_export(hs_fac* fac, int64_t node, void* dst_dev, int64_t ld);
+int32_t hs_schur_import(hs_fac* fac, int64_t node, const void* src_dev, int64_t ld);
+/* one half of ldiv! in place on a device-resident n×nrhs block: which = 1 forward (post-order), 2 backward
+ * (pre-order), 3 both.  With opts.subtree the root's boundary rows are updated (forward) / consumed (backward). */
+int32_t hs_solve_sweep(hs_fac* fac, int64_t nrhs, void* x_dev, int64_t ldx, int32_t which);
 int32_t hs_factor_free(hs_fac* fac);
 
 /* replaces ldiv!(C, F, B) for vectors and matrices (factornode.jl:62-74: _lsolve! :77, _dsolve! :89,
