@@ -142,6 +142,103 @@ def fp64_peak(complex_):
     return (37.0 if complex_ else 35.5), "fallback: earlier cuBLAS measurement on this pool"
 
 
+def gemm_roofline(stp, peak, peak_src):
+    gemm_tf = stp["gemm_flops"] / (stp["ms_gemm"] * 1e-3) / 1e12 if stp["ms_gemm"] > 0 else 0.0
+    return {"kernel": "k_gemm (FP64 DMMA m8n8k4 Schur/trailing update)", "bound": "tensor", "achieved": gemm_tf,
+            "peak": peak, "unit": "TFLOP/s", "frac": gemm_tf / peak, "traffic": None, "peak_source": peak_src,
+            "launches": stp["gemm_launches"], "flops_per_launch": stp["gemm_flops"] / max(stp["gemm_launches"], 1),
+            "ms_per_launch": stp["ms_gemm"] / max(stp["gemm_launches"], 1),
+            "phase_ms": {k: stp[k] for k in ("ms_assemble", "ms_small", "ms_panel", "ms_trsm", "ms_gemm", "ms_solve_prep")}}
+
+
+def h2d_bytes(Ap, nd, nd_loc, b):
+    tree_bytes = 8 * (2 * nd.nnodes + 4 * (nd.nnodes + 1) + len(nd.int_idx) + len(nd.bnd_idx) + len(nd_loc.iloc_idx) + len(nd_loc.bloc_idx))
+    a_bytes = Ap.indptr.size * 8 + Ap.indices.size * 8 + Ap.data.nbytes
+    return int(2 * a_bytes + tree_bytes + b.nbytes)
+
+
+def run_distributed(args, hs, torch, world, rank, local_rank, Ap, nd, nd_loc, b, flops, tdt):
+    """N > 1: one disjoint bottom subtree per GPU, Schur blocks of the subtree roots all-gathered over NCCL, the fronts
+    above the cut and the GMRES iteration replicated (hierarchicalsolvers.jl_b200/parallel.py).  Strong scaling."""
+    import torch.distributed as dist
+    from hsolve_b200.parallel import CudaEngine, DistributedFactor, gmres_replicated
+    lib = hs._lib.lib
+    eng = CudaEngine(local_rank)
+    t0 = time.perf_counter()
+    DF = DistributedFactor(Ap, nd, nd_loc, engine=eng, swlevel=0)
+    t_first = time.perf_counter() - t0
+    A_t = torch.sparse_csr_tensor(torch.from_numpy(Ap.tocsr().indptr.astype(np.int64)), torch.from_numpy(Ap.tocsr().indices.astype(np.int64)),
+                                  torch.from_numpy(np.ascontiguousarray(Ap.tocsr().data)).to(tdt), size=Ap.shape).to("cuda")
+    b_dev = eng.to_device(b)
+    out = {}
+
+    def step():
+        DF.refactor()
+        x, res, conv = gmres_replicated(A_t, b_dev, DF.ldiv_device, 1e-9, 30, 30)
+        out["x"], out["iters"] = x, len(res)
+
+    for _ in range(args.warmup):
+        step()
+    lc0 = C.c_int64(); lib.hs_launch_count(eng.ctx, C.byref(lc0))
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    fac_ms = []
+    for _ in range(args.steps):
+        tf0 = time.perf_counter()
+        DF.refactor()
+        torch.cuda.synchronize()
+        fac_ms.append((time.perf_counter() - tf0) * 1e3)
+        x, res, conv = gmres_replicated(A_t, b_dev, DF.ldiv_device, 1e-9, 30, 30)
+        out["x"], out["iters"] = x, len(res)
+    e1.record()
+    dist.barrier(); torch.cuda.synchronize()
+    clocks = sampler.stop()
+    lc1 = C.c_int64(); lib.hs_launch_count(eng.ctx, C.byref(lc1))
+    t = torch.tensor([e0.elapsed_time(e1) / args.steps, float(np.mean(fac_ms))], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    xh = out["x"].cpu().numpy()
+    resid = float(np.linalg.norm(Ap @ xh - b) / np.linalg.norm(b))
+    # roofline: the DMMA update of this rank's subtree and of the replicated top, event-timed
+    hs._lib.check(lib.hs_set_profile(eng.ctx, 1))
+    DF.refactor()
+    hs._lib.check(lib.hs_set_profile(eng.ctx, 0))
+    st_sub, st_top = eng.stats(DF.h_sub), eng.stats(DF.h_top)
+    stp = dict(st_top)
+    for k in ("gemm_flops", "ms_gemm", "gemm_launches", "ms_assemble", "ms_small", "ms_panel", "ms_trsm", "ms_solve_prep"):
+        stp[k] = st_sub[k] + st_top[k]
+    stp["solve_bytes"] = st_sub["solve_bytes"] + st_top["solve_bytes"]
+    stp["front_bytes"] = st_sub["front_bytes"] + st_top["front_bytes"]
+    peak, peak_src = fp64_peak(b.dtype == np.complex128)
+    e2e = None
+    if not args.no_e2e:
+        dist.barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        DF2 = DistributedFactor(Ap, nd, nd_loc, engine=eng, swlevel=0)
+        bh = eng.to_device(b)
+        x2, _, _ = gmres_replicated(A_t, bh, DF2.ldiv_device, 1e-9, 30, 30)
+        _ = x2.cpu()
+        torch.cuda.synchronize()
+        te = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": float(te.item()), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes(Ap, nd, nd_loc, b), "d2h_bytes_per_step": int(b.nbytes),
+               "note": "DistributedFactor(host CSC) + replicated GMRES, per rank; max over ranks"}
+    return {"ms_step": float(t[0].item()), "fac_ms": float(t[1].item()), "iters": out["iters"], "resid": resid,
+            "roofline": gemm_roofline(stp, peak, peak_src), "e2e": e2e, "clocks": clocks,
+            "launches": int(lc1.value - lc0.value) // max(args.steps, 1), "stats": stp, "t_first": t_first,
+            "parallelism": {"scheme": "subtree-per-GPU; Schur blocks of the subtree roots all-gathered (NCCL); top fronts and GMRES replicated",
+                            "cut_nodes": [int(c) for c in DF.part.cut], "schur_bytes_allgathered": DF.schur_bytes,
+                            "top_flops_share": float(1.0 - sum(float(np.sum(_ff(sn))) for sn in DF.part.sub_nd) / float(np.sum(DF.part.work)))}}
+
+
+def _ff(nd):
+    ni = np.diff(nd.int_ptr).astype(np.float64)
+    nb = np.diff(nd.bnd_ptr).astype(np.float64)
+    return (2.0 / 3.0) * ni ** 3 + 2.0 * ni ** 2 * nb + 2.0 * ni * nb ** 2
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -183,7 +280,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = hs._lib.default_context(local_rank)
-    stream = torch.cuda.Stream()
+    stream = torch.cuda.Stream() if world == 1 else torch.cuda.current_stream()
     hs._lib.check(hs._lib.lib.hs_set_stream(ctx, C.c_void_p(stream.cuda_stream)))
 
     # ---- problem (untimed) ----------------------------------------------------------------------
@@ -197,91 +294,81 @@ def main():
     b = np.ascontiguousarray(prob.b, dtype=dtype)
     flops = factor_flops(prob.elim_tree, cx)
 
-    # first factorization builds the plan and leaves A resident in HBM
-    t0 = time.perf_counter()
-    F = hs.factor(Ap, nd, nd_loc, swlevel=0, device=local_rank)
-    t_first = time.perf_counter() - t0
-    h = F._hd.h
-    tdt = torch.complex128 if cx else torch.float64
-    nz_dev = torch.from_numpy(np.ascontiguousarray(Ap.data, dtype=dtype)).to("cuda")
-    b_dev = torch.from_numpy(b).to("cuda")
-    x_dev = torch.zeros(n, dtype=tdt, device="cuda")
-    res = np.zeros(30, dtype=np.float64)
-    nit, conv = C.c_int64(), C.c_int32()
     lib = hs._lib.lib
-
-    def step_resident():
-        hs._lib.check(lib.hs_refactor(h, C.c_void_p(nz_dev.data_ptr()), 1))
-        hs._lib.check(lib.hs_gmres(ctx, hs._lib.HS_C64 if cx else hs._lib.HS_F64, n, None, None, None, 0, h,
-                                   C.c_void_p(b_dev.data_ptr()), C.c_void_p(x_dev.data_ptr()), 1e-9, 30, 30,
-                                   res.ctypes.data_as(C.POINTER(C.c_double)), C.byref(nit), C.byref(conv), 1))
-
-    def barrier():
-        if world > 1:
-            import torch.distributed as dist
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    with torch.cuda.stream(stream):
-        for _ in range(args.warmup):
-            step_resident()
-        lc0 = C.c_int64(); lib.hs_launch_count(ctx, C.byref(lc0))
-        sampler = ClockSampler(local_rank)
-        sampler.start()
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        fac_ms, sol_ms = [], []
-        for _ in range(args.steps):
-            step_resident()
-            st = F.stats()
-            fac_ms.append(st["ms_factor_total"])
-        e1.record(stream)
-        barrier()
-        clocks = sampler.stop()
-        lc1 = C.c_int64(); lib.hs_launch_count(ctx, C.byref(lc1))
-        ms_total = e0.elapsed_time(e1)
-    ms_step = ms_total / args.steps
-    if world > 1:
-        import torch.distributed as dist
-        t = torch.tensor([ms_step], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_step = float(t.item())
-    gm_iters = int(nit.value)
-    xh = x_dev.cpu().numpy()
-    resid = float(np.linalg.norm(Ap @ xh - b) / np.linalg.norm(b))
-    fac_ms_mean = float(np.mean(fac_ms))
-
-    # ---- roofline of the dominant kernel (DMMA Schur/trailing update), event-timed per launch ----
-    hs._lib.check(lib.hs_set_profile(ctx, 1))
-    with torch.cuda.stream(stream):
-        hs._lib.check(lib.hs_refactor(h, C.c_void_p(nz_dev.data_ptr()), 1))
-    hs._lib.check(lib.hs_set_profile(ctx, 0))
-    stp = F.stats()
+    tdt = torch.complex128 if cx else torch.float64
     peak, peak_src = fp64_peak(cx)
-    gemm_tf = stp["gemm_flops"] / (stp["ms_gemm"] * 1e-3) / 1e12 if stp["ms_gemm"] > 0 else 0.0
-    roofline = {"kernel": "k_gemm (FP64 DMMA m8n8k4 Schur/trailing update)", "bound": "tensor", "achieved": gemm_tf,
-                "peak": peak, "unit": "TFLOP/s", "frac": gemm_tf / peak, "traffic": None, "peak_source": peak_src,
-                "launches": stp["gemm_launches"], "flops_per_launch": stp["gemm_flops"] / max(stp["gemm_launches"], 1),
-                "ms_per_launch": stp["ms_gemm"] / max(stp["gemm_launches"], 1),
-                "phase_ms": {k: stp[k] for k in ("ms_assemble", "ms_panel", "ms_trsm", "ms_gemm")}}
+    if world > 1:
+        line_extra = run_distributed(args, hs, torch, world, rank, local_rank, Ap, nd, nd_loc, b, flops, tdt)
+        ms_step, fac_ms_mean, gm_iters, resid = (line_extra.pop(k) for k in ("ms_step", "fac_ms", "iters", "resid"))
+        roofline = line_extra.pop("roofline")
+        e2e = line_extra.pop("e2e")
+        clocks = line_extra.pop("clocks")
+        launches = line_extra.pop("launches")
+        stp = line_extra.pop("stats")
+        t_first = line_extra.pop("t_first")
+        config["parallelism"] = line_extra.pop("parallelism")
+    else:
+        # first factorization builds the plan and leaves A resident in HBM
+        t0 = time.perf_counter()
+        F = hs.factor(Ap, nd, nd_loc, swlevel=0, device=local_rank)
+        t_first = time.perf_counter() - t0
+        h = F._hd.h
+        nz_dev = torch.from_numpy(np.ascontiguousarray(Ap.data, dtype=dtype)).to("cuda")
+        b_dev = torch.from_numpy(b).to("cuda")
+        x_dev = torch.zeros(n, dtype=tdt, device="cuda")
+        res = np.zeros(30, dtype=np.float64)
+        nit, conv = C.c_int64(), C.c_int32()
 
-    # ---- end to end through the public API with host buffers ------------------------------------
-    e2e = None
-    if not args.no_e2e:
-        ts = []
-        for _ in range(max(1, min(args.steps, 2))):
+        def step_resident():
+            hs._lib.check(lib.hs_refactor(h, C.c_void_p(nz_dev.data_ptr()), 1))
+            hs._lib.check(lib.hs_gmres(ctx, hs._lib.HS_C64 if cx else hs._lib.HS_F64, n, None, None, None, 0, h,
+                                       C.c_void_p(b_dev.data_ptr()), C.c_void_p(x_dev.data_ptr()), 1e-9, 30, 30,
+                                       res.ctypes.data_as(C.POINTER(C.c_double)), C.byref(nit), C.byref(conv), 1))
+
+        with torch.cuda.stream(stream):
+            for _ in range(args.warmup):
+                step_resident()
+            lc0 = C.c_int64(); lib.hs_launch_count(ctx, C.byref(lc0))
+            sampler = ClockSampler(local_rank)
+            sampler.start()
             torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            F2 = hs.factor(Ap, nd, nd_loc, swlevel=0, device=local_rank)
-            x2, hist = hs.gmres(Ap, b, Pr=F2, reltol=1e-9, restart=30, maxiter=30, log=True)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            fac_ms = []
+            for _ in range(args.steps):
+                step_resident()
+                fac_ms.append(F.stats()["ms_factor_total"])
+            e1.record(stream)
             torch.cuda.synchronize()
-            ts.append(time.perf_counter() - t0)
-            del F2
-        tree_bytes = 8 * (2 * nd.nnodes + 4 * (nd.nnodes + 1) + len(nd.int_idx) + len(nd.bnd_idx) + len(nd_loc.iloc_idx) + len(nd_loc.bloc_idx))
-        a_bytes = Ap.indptr.size * 8 + Ap.indices.size * 8 + Ap.data.nbytes
-        e2e = {"value": float(np.mean(ts)), "unit": UNIT, "h2d_bytes_per_step": int(2 * a_bytes + tree_bytes + b.nbytes),
-               "d2h_bytes_per_step": int(b.nbytes + 8 * 31), "note": "hs.factor(host CSC) + hs.gmres(host b) incl. plan build"}
+            clocks = sampler.stop()
+            lc1 = C.c_int64(); lib.hs_launch_count(ctx, C.byref(lc1))
+            ms_step = e0.elapsed_time(e1) / args.steps
+        launches = int(lc1.value - lc0.value) // max(args.steps, 1)
+        gm_iters = int(nit.value)
+        xh = x_dev.cpu().numpy()
+        resid = float(np.linalg.norm(Ap @ xh - b) / np.linalg.norm(b))
+        fac_ms_mean = float(np.mean(fac_ms))
+        # ---- roofline of the dominant kernel (DMMA Schur/trailing update), event-timed per launch ----
+        hs._lib.check(lib.hs_set_profile(ctx, 1))
+        with torch.cuda.stream(stream):
+            hs._lib.check(lib.hs_refactor(h, C.c_void_p(nz_dev.data_ptr()), 1))
+        hs._lib.check(lib.hs_set_profile(ctx, 0))
+        stp = F.stats()
+        roofline = gemm_roofline(stp, peak, peak_src)
+        # ---- end to end through the public API with host buffers ------------------------------------
+        e2e = None
+        if not args.no_e2e:
+            ts = []
+            for _ in range(max(1, min(args.steps, 2))):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                F2 = hs.factor(Ap, nd, nd_loc, swlevel=0, device=local_rank)
+                x2, hist = hs.gmres(Ap, b, Pr=F2, reltol=1e-9, restart=30, maxiter=30, log=True)
+                torch.cuda.synchronize()
+                ts.append(time.perf_counter() - t0)
+                del F2
+            e2e = {"value": float(np.mean(ts)), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes(Ap, nd, nd_loc, b),
+                   "d2h_bytes_per_step": int(b.nbytes + 8 * 31), "note": "hs.factor(host CSC) + hs.gmres(host b) incl. plan build"}
 
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -304,7 +391,7 @@ def main():
             "factor_frac_of_fp64_peak": flops / (fac_ms_mean * 1e-3) / 1e12 / peak,
             "solve_bytes_per_rhs": stp["solve_bytes"], "front_bytes": stp["front_bytes"],
             "setup_s": {"generate+symfact": t_setup, "first_factor_incl_plan": t_first},
-            "e2e": e2e, "gpu_launches": int(lc1.value - lc0.value), "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "clocks": clocks}
     print(json.dumps(line))
 

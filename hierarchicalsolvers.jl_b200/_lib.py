@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libhsolve_cuda.so")
 
 HS_OK, HS_EARG, HS_EDIM, HS_ETREE, HS_ESINGULAR, HS_ECUDA, HS_ENOMEM, HS_ENOTIMPL, HS_ESIZE = range(9)
 HS_F64, HS_C64 = 0, 1
+HS_ON_DEVICE, HS_CSC_ZERO_BASED, HS_CSC_INT32 = 1, 2, 4
 HS_GET_D, HS_GET_S, HS_GET_L, HS_GET_R, HS_GET_FRONT, HS_GET_PIV = range(6)
 
 i64p = C.POINTER(C.c_int64)

@@ -89,6 +89,7 @@ extern "C" int32_t hs_launch_count(hs_ctx* ctx, int64_t* count) {
 extern "C" int32_t hs_destroy(hs_ctx* ctx) {
   if (!ctx) return HS_OK;
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  cudaFree(ctx->gm_buf);
   delete ctx;
   return HS_OK;
 }
@@ -515,15 +516,23 @@ static void build_plan(hs_fac* f, const hs_tree* t) {
   CUDA_OK(cudaStreamSynchronize(st));  // host vectors go out of scope
 }
 
+__global__ void k_widen_index(long long* dst, const int* src, long long n, long long base) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (long long)src[i] - base;
+}
+
 __global__ void k_shift_index(long long* a, long long n, long long base) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) a[i] -= base;
 }
 
 static int32_t factor_impl(hs_ctx* ctx, hs_dtype dtype, int64_t n, const int64_t* colptr, const int64_t* rowval,
-                           const void* nzval, const hs_tree* tree, const hs_opts* opts, int32_t on_device,
+                           const void* nzval, const hs_tree* tree, const hs_opts* opts, int32_t flags,
                            hs_fac** out, bool do_numeric) {
   HS_TRY_BEGIN
+  const bool on_device = flags & HS_ON_DEVICE;
+  const bool idx32 = flags & HS_CSC_INT32;
+  if (on_device && idx32) return hs_fail(HS_EARG, "hs_factor: device-resident CSC arrays must be int64");
   if (!ctx || !colptr || !rowval || !nzval || !tree || !out) return hs_fail(HS_EARG, "hs_factor: null argument");
   if (dtype != HS_F64 && dtype != HS_C64) return hs_fail(HS_EARG, "hs_factor: dtype must be HS_F64 or HS_C64");
   if (n <= 0) return hs_fail(HS_EARG, "hs_factor: n must be positive");
@@ -552,25 +561,37 @@ static int32_t factor_impl(hs_ctx* ctx, hs_dtype dtype, int64_t n, const int64_t
   f->stats.ms_analyze = std::chrono::duration<double, std::milli>(t_plan - t_begin).count();
   // matrix
   cudaStream_t st = ctx->stream;
-  const int64_t base = tree->index_base;
+  const int64_t base = (flags & HS_CSC_ZERO_BASED) ? 0 : tree->index_base;
   CUDA_OK(cudaMalloc((void**)&f->d_colptr, (size_t)(n + 1) * sizeof(long long)));
   const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-  CUDA_OK(cudaMemcpyAsync(f->d_colptr, colptr, (size_t)(n + 1) * sizeof(long long), kind, st));
   int64_t last = 0;
   if (on_device) {
     CUDA_OK(cudaMemcpyAsync(&last, colptr + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));
-  } else last = colptr[n];
+  } else last = idx32 ? (int64_t)((const int32_t*)colptr)[n] : colptr[n];
   f->nnz = last - (on_device ? 0 : base);
   if (f->nnz < 0) return hs_fail(HS_EARG, "hs_factor: negative nnz");
   CUDA_OK(cudaMalloc((void**)&f->d_rowval, std::max<size_t>(f->nnz, 1) * sizeof(long long)));
   CUDA_OK(cudaMalloc(&f->d_nzval, std::max<size_t>(f->nnz, 1) * f->esz));
-  CUDA_OK(cudaMemcpyAsync(f->d_rowval, rowval, (size_t)f->nnz * sizeof(long long), kind, st));
-  CUDA_OK(cudaMemcpyAsync(f->d_nzval, nzval, (size_t)f->nnz * f->esz, kind, st));
-  if (!on_device && base != 0) {
-    k_shift_index<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(f->d_colptr, n + 1, base);
-    if (f->nnz) k_shift_index<<<(unsigned)((f->nnz + 255) / 256), 256, 0, st>>>(f->d_rowval, f->nnz, base);
+  if (idx32) {
+    // int32 index arrays (SciPy): stage in a scratch buffer, widen to int64 on the device
+    int* t32 = nullptr;
+    CUDA_OK(cudaMalloc((void**)&t32, (size_t)(n + 1 + std::max<int64_t>(f->nnz, 1)) * sizeof(int)));
+    CUDA_OK(cudaMemcpyAsync(t32, colptr, (size_t)(n + 1) * sizeof(int), kind, st));
+    CUDA_OK(cudaMemcpyAsync(t32 + n + 1, rowval, (size_t)f->nnz * sizeof(int), kind, st));
+    k_widen_index<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(f->d_colptr, t32, n + 1, base);
+    if (f->nnz) k_widen_index<<<(unsigned)((f->nnz + 255) / 256), 256, 0, st>>>(f->d_rowval, t32 + n + 1, f->nnz, base);
+    CUDA_OK(cudaStreamSynchronize(st));
+    cudaFree(t32);
+  } else {
+    CUDA_OK(cudaMemcpyAsync(f->d_colptr, colptr, (size_t)(n + 1) * sizeof(long long), kind, st));
+    CUDA_OK(cudaMemcpyAsync(f->d_rowval, rowval, (size_t)f->nnz * sizeof(long long), kind, st));
+    if (!on_device && base != 0) {
+      k_shift_index<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(f->d_colptr, n + 1, base);
+      if (f->nnz) k_shift_index<<<(unsigned)((f->nnz + 255) / 256), 256, 0, st>>>(f->d_rowval, f->nnz, base);
+    }
   }
+  CUDA_OK(cudaMemcpyAsync(f->d_nzval, nzval, (size_t)f->nnz * f->esz, kind, st));
   CUDA_OK(cudaStreamSynchronize(st));
   auto t_h2d = std::chrono::steady_clock::now();
   f->stats.ms_h2d = std::chrono::duration<double, std::milli>(t_h2d - t_plan).count();

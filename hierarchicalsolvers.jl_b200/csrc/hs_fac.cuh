@@ -27,6 +27,8 @@ struct hs_ctx {
   int max_cluster = 8;
   bool profile = false;
   long long launches = 0;
+  void* gm_buf = nullptr;   // GMRES workspace (Krylov basis + work vectors), grow-only, reused across hs_gmres calls
+  size_t gm_bytes = 0;
   int outer_block = 256;  // NB of the two-level blocked LU (HS_OUTER_BLOCK)
 };
 

@@ -142,18 +142,26 @@ void gmres_impl(hs_ctx* ctx, hs_fac* f, long long n, const long long* rptr, cons
   cudaStream_t st = ctx->stream;
   T *V = nullptr, *w = nullptr, *z = nullptr, *x = nullptr, *bdev = nullptr;
   cplx *part = nullptr, *dres = nullptr;
-  struct Guard {
-    std::vector<void*> p;
-    ~Guard() { for (void* q : p) cudaFree(q); }
-  } guard;
-  auto alloc = [&](void** p, size_t bytes) { CUDA_OK(cudaMalloc(p, std::max<size_t>(bytes, 16))); guard.p.push_back(*p); };
-  alloc((void**)&V, (size_t)n * (restart + 1) * sizeof(T));
-  alloc((void**)&w, (size_t)n * sizeof(T));
-  alloc((void**)&z, (size_t)n * sizeof(T));
-  alloc((void**)&x, (size_t)n * sizeof(T));
-  alloc((void**)&bdev, (size_t)n * sizeof(T));
-  alloc((void**)&part, RED_BLOCKS * sizeof(cplx));
-  alloc((void**)&dres, sizeof(cplx));
+  // one grow-only workspace per context: cudaMalloc/cudaFree of the ~1 GB Krylov basis per call would dominate
+  auto up = [](size_t b) { return (b + 255) / 256 * 256; };
+  const size_t szv = up((size_t)n * sizeof(T));
+  const size_t need = szv * (restart + 1) + 4 * szv + up(RED_BLOCKS * sizeof(cplx)) + 256;
+  if (ctx->gm_bytes < need) {
+    cudaFree(ctx->gm_buf);
+    ctx->gm_buf = nullptr; ctx->gm_bytes = 0;
+    CUDA_OK(cudaMalloc(&ctx->gm_buf, need));
+    ctx->gm_bytes = need;
+  }
+  {
+    char* p = (char*)ctx->gm_buf;
+    V = (T*)p; p += szv * (restart + 1);
+    w = (T*)p; p += szv;
+    z = (T*)p; p += szv;
+    x = (T*)p; p += szv;
+    bdev = (T*)p; p += szv;
+    part = (cplx*)p; p += up(RED_BLOCKS * sizeof(cplx));
+    dres = (cplx*)p;
+  }
   const unsigned gb = (unsigned)((n + 255) / 256);
   auto dot = [&](const T* a, const T* bb) -> zc {
     ctx->launches += 2;

@@ -43,15 +43,19 @@ def gmres(A, b, Pr: Optional[FactorNode] = None, reltol: float = 1e-9, restart: 
     dtype = np.complex128 if cx else np.float64
     b = np.ascontiguousarray(b, dtype=dtype)
     if device_resident:
-        A.sort_indices()
-        colptr, rowval = _lib.as_i64(A.indptr), _lib.as_i64(A.indices)
-        nz = np.ascontiguousarray(A.data, dtype=dtype)
         x = np.zeros(n, dtype=dtype)
         res = np.zeros(max(maxiter, 1), dtype=np.float64)
         nit, conv = C.c_int64(), C.c_int32()
         ctx = Pr._hd.ctx if Pr is not None else _lib.default_context(device)
-        _lib.check(_lib.lib.hs_gmres(ctx, _lib.HS_C64 if cx else _lib.HS_F64, n, colptr.ctypes.data_as(C.c_void_p),
-                                     rowval.ctypes.data_as(C.c_void_p), nz.ctypes.data_as(C.c_void_p), 0,
+        ref = getattr(Pr._hd, "A_ref", None) if Pr is not None else None
+        same = ref is not None and ref() is A.data
+        if same:   # the matrix the factorization already holds in HBM
+            cp = rv = nzp = None
+        else:
+            colptr, rowval = _lib.as_i64(A.indptr), _lib.as_i64(A.indices)
+            nz = np.ascontiguousarray(A.data, dtype=dtype)
+            cp, rv, nzp = (a.ctypes.data_as(C.c_void_p) for a in (colptr, rowval, nz))
+        _lib.check(_lib.lib.hs_gmres(ctx, _lib.HS_C64 if cx else _lib.HS_F64, n, cp, rv, nzp, 0,
                                      Pr._hd.h if Pr is not None else None, b.ctypes.data_as(C.c_void_p),
                                      x.ctypes.data_as(C.c_void_p), reltol, restart, maxiter,
                                      res.ctypes.data_as(C.POINTER(C.c_double)), C.byref(nit), C.byref(conv), 0))

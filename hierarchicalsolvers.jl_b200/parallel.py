@@ -28,7 +28,7 @@ from . import _lib
 from .nesteddissection import NDLoc, NestedDissection
 from .options import SolverOptions, chkopts, to_c
 
-__all__ = ["partition_tree", "TreePartition", "DistributedFactor", "CudaEngine"]
+__all__ = ["partition_tree", "TreePartition", "DistributedFactor", "CudaEngine", "gmres_replicated"]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -154,6 +154,9 @@ class CudaEngine:
         self.torch = torch
         self.device = device
         self.ctx = _lib.default_context(device)
+        # library kernels and torch / NCCL operations must be ordered: run the library on torch's current stream
+        torch.cuda.set_device(device)
+        _lib.check(_lib.lib.hs_set_stream(self.ctx, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
         self.handles = []
 
     def __del__(self):
@@ -165,13 +168,11 @@ class CudaEngine:
 
     def _csc(self, A):
         A = sp.csc_matrix(A)
-        A.sort_indices()
         cx = np.iscomplexobj(A.data)
         self.cx = cx
         self.np_dtype = np.complex128 if cx else np.float64
         self.t_dtype = self.torch.complex128 if cx else self.torch.float64
-        return (A.shape[0], _lib.as_i64(A.indptr) + 1, _lib.as_i64(A.indices) + 1,
-                np.ascontiguousarray(A.data, dtype=self.np_dtype))
+        return (A.shape[0], _lib.as_i64(A.indptr), _lib.as_i64(A.indices), np.ascontiguousarray(A.data, dtype=self.np_dtype))
 
     def _factor(self, A, nd, loc, opts, subtree, numeric):
         n, colptr, rowval, nz = self._csc(A)
@@ -180,7 +181,8 @@ class CudaEngine:
         h = C.c_void_p()
         fn = _lib.lib.hs_factor if numeric else _lib.lib.hs_analyze
         rc = fn(self.ctx, _lib.HS_C64 if self.cx else _lib.HS_F64, n, colptr.ctypes.data_as(C.c_void_p),
-                rowval.ctypes.data_as(C.c_void_p), nz.ctypes.data_as(C.c_void_p), C.byref(tree), C.byref(copts), 0, C.byref(h))
+                rowval.ctypes.data_as(C.c_void_p), nz.ctypes.data_as(C.c_void_p), C.byref(tree), C.byref(copts),
+                _lib.HS_CSC_ZERO_BASED, C.byref(h))
         if rc != _lib.HS_OK:
             if h:
                 _lib.lib.hs_factor_free(h)
@@ -266,6 +268,16 @@ class DistributedFactor:
         self._iidx = [self.eng.index(i) for i in part.int_idx]
         self._ipad = max(max(len(i) for i in part.int_idx), 1)
 
+    def refactor(self):
+        """Numeric phase again on the stored values (what a timed benchmark step repeats): local subtree, Schur
+        all-gather, fronts above the cut."""
+        g = self.rank
+        nbs = [len(b) for b in self.part.bnd_idx]
+        self.eng.numeric(self.h_sub)
+        mine = self.eng.export_schur(self.h_sub, self.part.sub_nd[g].root, nbs[g], self.pad)
+        self.dist.all_gather(self.schur, mine, group=self.group)
+        self.eng.numeric(self.h_top)
+
     def _allgather_segments(self, x, idx_list, pad):
         torch = self.eng.torch
         mine = self.eng.zeros(pad)
@@ -292,3 +304,57 @@ class DistributedFactor:
         x = self.eng.to_device(b)
         self.ldiv_device(x)
         return self.eng.to_host(x)
+
+
+def gmres_replicated(A_t, b, precond, reltol=1e-9, restart=30, maxiter=30):
+    """Right-preconditioned restarted GMRES (test/rungmres.jl:47 semantics) on device tensors, run identically on every
+    rank: ``A_t`` is a torch sparse CSR matrix, ``precond(v)`` overwrites ``v`` with Pr⁻¹·v (``DistributedFactor.ldiv_device``).
+    Returns ``(x, resnorms, converged)``."""
+    import torch
+    n = b.shape[0]
+    x = torch.zeros_like(b)
+    r = b.clone()
+    beta = float(torch.linalg.vector_norm(r))
+    tol = reltol * beta
+    res, it, resid = [], 0, beta
+    cplx = b.is_complex()
+    while it < maxiter and resid > tol:
+        V = [r / beta]
+        H = np.zeros((restart + 1, restart), dtype=np.complex128 if cplx else np.float64)
+        cs = np.zeros(restart, dtype=H.dtype); sn = np.zeros(restart, dtype=H.dtype)
+        g = np.zeros(restart + 1, dtype=H.dtype); g[0] = beta
+        k = 0
+        while k < restart and it < maxiter and resid > tol:
+            z = precond(V[k].clone())
+            w = torch.mv(A_t, z)
+            for j in range(k + 1):
+                h = torch.vdot(V[j], w)
+                H[j, k] = h.item()
+                w = w - h * V[j]
+            hn = float(torch.linalg.vector_norm(w))
+            H[k + 1, k] = hn
+            V.append(w / hn if hn != 0 else w)
+            for j in range(k):
+                t = cs[j] * H[j, k] + sn[j] * H[j + 1, k]
+                H[j + 1, k] = -np.conj(sn[j]) * H[j, k] + cs[j] * H[j + 1, k]
+                H[j, k] = t
+            a, c = H[k, k], H[k + 1, k]
+            den = np.sqrt(abs(a) ** 2 + abs(c) ** 2)
+            if den == 0: cs[k], sn[k] = 1.0, 0.0
+            elif a == 0: cs[k], sn[k] = 0.0, 1.0
+            else: cs[k], sn[k] = abs(a) / den, (a / abs(a)) * np.conj(c) / den
+            H[k, k] = cs[k] * a + sn[k] * c
+            H[k + 1, k] = 0.0
+            g[k + 1] = -np.conj(sn[k]) * g[k]
+            g[k] = cs[k] * g[k]
+            resid = abs(g[k + 1]); res.append(float(resid))
+            k += 1; it += 1
+        y = np.linalg.solve(np.triu(H[:k, :k]), g[:k]) if k else np.zeros(0)
+        upd = torch.zeros_like(b)
+        for j in range(k):
+            upd = upd + complex(y[j]) * V[j] if cplx else upd + float(np.real(y[j])) * V[j]
+        x = x + precond(upd)
+        if it < maxiter and resid > tol:
+            r = b - torch.mv(A_t, x)
+            beta = float(torch.linalg.vector_norm(r)); resid = beta
+    return x, res, bool(resid <= tol)

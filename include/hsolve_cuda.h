@@ -145,14 +145,19 @@ int32_t hs_symbolic_free(hs_symbolic* s);
  * _factor :14-27, _factor_leaf :30-42, _factor_branch :62-75, _assemble_blocks :115-123,
  * blockfactor/blockldiv/blockrdiv blockmatrix.jl:115-187).
  * A is CSC (SparseMatrixCSC: colptr n+1, rowval nnz, nzval nnz) with `index_base` of the tree.
- * `on_device` != 0: colptr/rowval/nzval are device pointers already resident in HBM (0-based int64). */
+ * `flags`: HS_ON_DEVICE — colptr/rowval/nzval are device pointers already resident in HBM (0-based int64);
+ *          HS_CSC_ZERO_BASED — the host CSC arrays are 0-based whatever the tree's base is (SciPy callers);
+ *          HS_CSC_INT32 — colptr/rowval point to int32 arrays (SciPy's default index type). */
+#define HS_ON_DEVICE 1
+#define HS_CSC_ZERO_BASED 2
+#define HS_CSC_INT32 4
 int32_t hs_factor(hs_ctx* ctx, hs_dtype dtype, int64_t n, const int64_t* colptr, const int64_t* rowval,
-                  const void* nzval, const hs_tree* tree, const hs_opts* opts, int32_t on_device, hs_fac** out);
+                  const void* nzval, const hs_tree* tree, const hs_opts* opts, int32_t flags, hs_fac** out);
 /* same plan and sparsity, new values (the numeric part of `factor` alone); nzval == NULL re-uses the stored values */
 int32_t hs_refactor(hs_fac* fac, const void* nzval, int32_t on_device);
 /* hs_factor without the numeric phase (plan + upload only); follow with hs_schur_import / hs_refactor */
 int32_t hs_analyze(hs_ctx* ctx, hs_dtype dtype, int64_t n, const int64_t* colptr, const int64_t* rowval,
-                   const void* nzval, const hs_tree* tree, const hs_opts* opts, int32_t on_device, hs_fac** out);
+                   const void* nzval, const hs_tree* tree, const hs_opts* opts, int32_t flags, hs_fac** out);
 
 /* ---- subtree-per-GPU plumbing -------------------------------------------------------
  * Disjoint bottom subtrees are factored one per GPU with opts.subtree = 1; each exports the Schur complement of its
