@@ -358,17 +358,23 @@ def main():
         # ---- end to end through the public API with host buffers ------------------------------------
         e2e = None
         if not args.no_e2e:
-            ts = []
+            del F
+            ts, tf_, tg_ = [], [], []
             for _ in range(max(1, min(args.steps, 2))):
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
                 F2 = hs.factor(Ap, nd, nd_loc, swlevel=0, device=local_rank)
+                t1 = time.perf_counter()
                 x2, hist = hs.gmres(Ap, b, Pr=F2, reltol=1e-9, restart=30, maxiter=30, log=True)
                 torch.cuda.synchronize()
-                ts.append(time.perf_counter() - t0)
+                t2 = time.perf_counter()
+                ts.append(t2 - t0); tf_.append(t1 - t0); tg_.append(t2 - t1)
+                st2 = F2.stats()
                 del F2
             e2e = {"value": float(np.mean(ts)), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes(Ap, nd, nd_loc, b),
-                   "d2h_bytes_per_step": int(b.nbytes + 8 * 31), "note": "hs.factor(host CSC) + hs.gmres(host b) incl. plan build"}
+                   "d2h_bytes_per_step": int(b.nbytes + 8 * 31), "note": "hs.factor(host CSC) + hs.gmres(host b) incl. plan build",
+                   "factor_call_s": float(np.mean(tf_)), "gmres_call_s": float(np.mean(tg_)),
+                   "inside_factor_ms": {k: st2[k] for k in ("ms_analyze", "ms_h2d", "ms_factor_total")}}
 
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:

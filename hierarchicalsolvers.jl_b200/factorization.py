@@ -2,7 +2,6 @@
 from __future__ import annotations
 
 import ctypes as C
-import weakref
 
 import numpy as np
 import scipy.sparse as sp
@@ -51,5 +50,6 @@ def factor(A, nd: NestedDissection, nd_loc: NDLoc, opts: SolverOptions = None, d
             _lib.lib.hs_factor_free(h)
         _lib.check(rc)
     hd = _Handle(h, ctx, dtype, n, nd, nd_loc)
-    hd.A_ref = weakref.ref(A.data)  # lets gmres() reuse the device-resident copy of the very same matrix
+    # lets gmres() reuse the device-resident copy when it is handed the very same matrix values
+    hd.A_key = (A.data.__array_interface__["data"][0], A.data.shape[0], A.indices.__array_interface__["data"][0])
     return FactorNode(hd, nd.root)

@@ -47,8 +47,8 @@ def gmres(A, b, Pr: Optional[FactorNode] = None, reltol: float = 1e-9, restart: 
         res = np.zeros(max(maxiter, 1), dtype=np.float64)
         nit, conv = C.c_int64(), C.c_int32()
         ctx = Pr._hd.ctx if Pr is not None else _lib.default_context(device)
-        ref = getattr(Pr._hd, "A_ref", None) if Pr is not None else None
-        same = ref is not None and ref() is A.data
+        key = (A.data.__array_interface__["data"][0], A.data.shape[0], A.indices.__array_interface__["data"][0])
+        same = Pr is not None and getattr(Pr._hd, "A_key", None) == key
         if same:   # the matrix the factorization already holds in HBM
             cp = rv = nzp = None
         else:

@@ -1,0 +1,161 @@
+# HierarchicalSolversCUDA.jl — the Julia-side binding of libhsolve_cuda for bonevbs/HierarchicalSolvers.jl.
+#
+# NOT EXECUTED IN THIS REPOSITORY'S CI: the build image has no Julia.  The same C ABI is exercised from Python
+# (hierarchicalsolvers.jl_b200/_lib.py, tests/); this file is what a maintainer of the reference adds to route
+# `factor` / `ldiv!` to the GPU.  It keeps the reference's host-side symbolic phase (nesteddissection.jl) and replaces
+# storage + numerics (blockmatrix.jl, factornode.jl, factorization.jl) by device-resident fronts.
+#
+#   using HierarchicalSolvers, HierarchicalSolversCUDA
+#   A, b, nd = read_problem(path); nd, nd_loc = symfact!(nd)
+#   perm = postorder(nd); A = permute(A, perm, perm); nd = permuted!(nd, invperm(perm))
+#   F = cufactor(A, nd, nd_loc; swlevel = 0)            # instead of factor(...)
+#   x, ch = gmres(A, b; Pr = F, reltol = 1e-9, restart = 30, log = true, maxiter = 30)
+module HierarchicalSolversCUDA
+
+using LinearAlgebra, SparseArrays
+using HierarchicalSolvers
+import LinearAlgebra: ldiv!
+import HierarchicalSolvers: maxrank, isleaf, isbranch
+
+export CuFactorNode, cufactor
+
+const libhsolve = get(ENV, "LIBHSOLVE_CUDA", "libhsolve_cuda")
+
+# ---- status codes → the exceptions the reference raises (include/hsolve_cuda.h) -------------------------------
+const HS_OK, HS_EARG, HS_EDIM, HS_ETREE, HS_ESINGULAR, HS_ECUDA, HS_ENOMEM, HS_ENOTIMPL, HS_ESIZE = 0:8
+function check(rc::Int32)
+  rc == HS_OK && return
+  msg = unsafe_string(ccall((:hs_last_error, libhsolve), Cstring, ()))
+  rc == HS_EARG      && throw(ArgumentError(msg))
+  rc == HS_EDIM      && throw(DimensionMismatch(msg))
+  rc == HS_ESINGULAR && throw(SingularException(0))
+  rc == HS_ENOMEM    && throw(OutOfMemoryError())
+  throw(ErrorException(msg))     # HS_ETREE is the reference's ErrorException (factorization.jl:25)
+end
+
+# ---- plain-old-data mirrors of the ABI structs ----------------------------------------------------------------
+struct HsOpts             # SolverOptions, HierarchicalSolvers.jl:30-40
+  swlevel::Int64; swsize::Int64; atol::Float64; rtol::Float64; c_tol::Float64
+  leafsize::Int64; kest::Int64; stepsize::Int64; verbose::Int32; subtree::Int32
+end
+HsOpts(o::SolverOptions) = HsOpts(o.swlevel, o.swsize, o.atol, o.rtol, o.c_tol, o.leafsize, o.kest, o.stepsize, o.verbose, 0)
+
+struct HsTree
+  nnodes::Int64
+  left::Ptr{Int64}; right::Ptr{Int64}
+  int_ptr::Ptr{Int64}; int_idx::Ptr{Int64}; bnd_ptr::Ptr{Int64}; bnd_idx::Ptr{Int64}
+  iloc_ptr::Ptr{Int64}; iloc_idx::Ptr{Int64}; bloc_ptr::Ptr{Int64}; bloc_idx::Ptr{Int64}
+  index_base::Int32
+end
+
+# flatten the two parallel BinaryNode trees (nd, nd_loc) of symfact! into post-order ragged arrays
+function flatten(nd::NestedDissection, nd_loc::NestedDissection)
+  left = Int64[]; right = Int64[]
+  ip = Int64[0]; ii = Int64[]; bp = Int64[0]; bi = Int64[]
+  lip = Int64[0]; lii = Int64[]; lbp = Int64[0]; lbi = Int64[]
+  function rec(x, xl)
+    l = isnothing(x.left) ? -1 : rec(x.left, xl.left)
+    r = isnothing(x.right) ? -1 : rec(x.right, xl.right)
+    push!(left, l); push!(right, r)
+    append!(ii, x.int); push!(ip, length(ii)); append!(bi, x.bnd); push!(bp, length(bi))
+    append!(lii, xl.int); push!(lip, length(lii)); append!(lbi, xl.bnd); push!(lbp, length(lbi))
+    return length(left)             # 1-based node id in post-order
+  end
+  rec(nd, nd_loc)
+  return (; left, right, ip, ii, bp, bi, lip, lii, lbp, lbi)
+end
+
+const CTX = Ref{Ptr{Cvoid}}(C_NULL)
+function context()
+  if CTX[] == C_NULL
+    check(ccall((:hs_create, libhsolve), Int32, (Ref{Ptr{Cvoid}}, Int32), CTX, 0))
+  end
+  CTX[]
+end
+
+# ---- the factorization object -------------------------------------------------------------------------------
+mutable struct CuFactorNode{T} <: Factorization{T}
+  handle::Ptr{Cvoid}
+  n::Int
+  node::Int                  # post-order id (0-based) of this node, root = nnodes-1
+  nd::NestedDissection
+  nd_loc::NestedDissection
+  root::Union{CuFactorNode{T}, Nothing}
+end
+Base.eltype(::CuFactorNode{T}) where T = T
+Base.size(F::CuFactorNode) = (F.n, F.n)
+Base.show(io::IO, F::CuFactorNode) = print(io, "CuFactorNode{$(eltype(F))}")
+
+dtype_code(::Type{Float64}) = Int32(0)
+dtype_code(::Type{ComplexF64}) = Int32(1)
+
+"""
+    cufactor(A, nd, nd_loc, opts = SolverOptions(); kw...) -> CuFactorNode
+
+Drop-in for `factor` (src/factorization.jl:5-11).  Copies `A` and the tree to the GPU and factors there.
+"""
+function cufactor(A::SparseMatrixCSC{T,Int}, nd::NestedDissection, nd_loc::NestedDissection,
+                  opts::SolverOptions = SolverOptions(); args...) where T <: Union{Float64, ComplexF64}
+  opts = copy(opts; args...)
+  HierarchicalSolvers.chkopts!(opts)
+  t = flatten(nd, nd_loc)
+  h = Ref{Ptr{Cvoid}}(C_NULL)
+  GC.@preserve A t begin
+    tree = HsTree(length(t.left), pointer(t.left), pointer(t.right), pointer(t.ip), pointer(t.ii), pointer(t.bp), pointer(t.bi),
+                  pointer(t.lip), pointer(t.lii), pointer(t.lbp), pointer(t.lbi), Int32(1))
+    rc = ccall((:hs_factor, libhsolve), Int32,
+               (Ptr{Cvoid}, Int32, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Cvoid}, Ref{HsTree}, Ref{HsOpts}, Int32, Ref{Ptr{Cvoid}}),
+               context(), dtype_code(T), size(A, 1), A.colptr, A.rowval, A.nzval, tree, HsOpts(opts), Int32(0), h)
+  end
+  if rc != HS_OK
+    h[] != C_NULL && ccall((:hs_factor_free, libhsolve), Int32, (Ptr{Cvoid},), h[])
+    check(rc)
+  end
+  F = CuFactorNode{T}(h[], size(A, 1), length(t.left) - 1, nd, nd_loc, nothing)
+  finalizer(F -> ccall((:hs_factor_free, libhsolve), Int32, (Ptr{Cvoid},), F.handle), F)
+  return F
+end
+
+# ---- ldiv!  (src/factornode.jl:62-74) -----------------------------------------------------------------------
+# 3-argument forms write into C.  The 2-argument form is genuinely in place here (the reference's allocates and
+# leaves B untouched, factornode.jl:62 — see SURVEY F6); IterativeSolvers' right-preconditioned update relies on it.
+function ldiv!(C::StridedVecOrMat{T}, F::CuFactorNode{T}, B::StridedVecOrMat{T}) where T
+  size(B, 1) == F.n || throw(DimensionMismatch("B has $(size(B,1)) rows, expected $(F.n)"))
+  Bc = Matrix{T}(reshape(B, F.n, :))            # contiguous staging copy (gmres hands in SubArray columns)
+  GC.@preserve Bc check(ccall((:hs_solve, libhsolve), Int32, (Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Int32),
+                              F.handle, size(Bc, 2), Bc, F.n, Bc, F.n, Int32(0)))
+  copyto!(C, reshape(Bc, size(C)))
+  return C
+end
+ldiv!(F::CuFactorNode{T}, B::StridedVecOrMat{T}) where T = ldiv!(B, F, B)
+Base.:\(F::CuFactorNode{T}, B::StridedVecOrMat{T}) where T = ldiv!(similar(B), F, B)
+
+function maxrank(F::CuFactorNode)             # src/factornode.jl:49-57
+  r = Ref{Int64}(0)
+  check(ccall((:hs_maxrank, libhsolve), Int32, (Ptr{Cvoid}, Ref{Int64}), F.handle, r))
+  return Int(r[])
+end
+
+# ---- FactorNode fields, copied from the device on access (src/factornode.jl:8-22) ----------------------------
+const WHICH = Dict(:D => 0, :S => 1, :L => 2, :R => 3)
+function Base.getproperty(F::CuFactorNode{T}, s::Symbol) where T
+  if haskey(WHICH, s)
+    dims = zeros(Int64, 2)
+    check(ccall((:hs_node_get, libhsolve), Int32, (Ptr{Cvoid}, Int64, Int32, Ptr{Cvoid}, Ptr{Int64}),
+                getfield(F, :handle), getfield(F, :node), Int32(WHICH[s]), C_NULL, dims))
+    M = Matrix{T}(undef, dims[1], dims[2])
+    check(ccall((:hs_node_get, libhsolve), Int32, (Ptr{Cvoid}, Int64, Int32, Ptr{Cvoid}, Ptr{Int64}),
+                getfield(F, :handle), getfield(F, :node), Int32(WHICH[s]), M, dims))
+    return M
+  elseif s === :int;      return getfield(F, :nd).int
+  elseif s === :bnd;      return getfield(F, :nd).bnd
+  elseif s === :int_loc;  return getfield(F, :nd_loc).int
+  elseif s === :bnd_loc;  return getfield(F, :nd_loc).bnd
+  else
+    return getfield(F, s)
+  end
+end
+isleaf(F::CuFactorNode) = HierarchicalSolvers.isleaf(getfield(F, :nd))
+isbranch(F::CuFactorNode) = HierarchicalSolvers.isbranch(getfield(F, :nd))
+
+end # module
