@@ -368,28 +368,37 @@ __global__ void __launch_bounds__(256, 1) k_gemm(const Front* __restrict__ front
     }
   }
   cp_async_wait<0>();
-  // epilogue: C -= acc
+  // epilogue: C -= acc.  All loads of a row group are issued before the first store: written as load-modify-store
+  // per element the compiler has to keep them in program order (the pointers may alias) and the 64 L2 round trips of
+  // a thread serialise — that was half of the kernel time for the K = 64 updates.
 #pragma unroll
   for (int i = 0; i < MI; ++i) {
     const int r = m0 + wm + i * 8 + g;
-    if (r < lo || r >= rhi) continue;
+    const bool rok = r >= lo && r < rhi;
+    T cv[NI][2];
 #pragma unroll
-    for (int j = 0; j < NI; ++j) {
+    for (int j = 0; j < NI; ++j)
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int c = n0 + wn + j * 8 + q * 2 + h;
-        if (c >= chi) continue;
-        T* pc = F + (long long)c * ld + r;
-        if constexpr (!CX) {
-          *pc -= acc[0][i][j][h];
-        } else {
-          T v = *pc;
-          v.x -= acc[0][i][j][h];
-          v.y -= acc[1][i][j][h];
-          *pc = v;
+        cv[j][h] = (rok && c < chi) ? F[(long long)c * ld + r] : hs_zero<T>();
+      }
+#pragma unroll
+    for (int j = 0; j < NI; ++j)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = n0 + wn + j * 8 + q * 2 + h;
+        if (rok && c < chi) {
+          T v = cv[j][h];
+          if constexpr (!CX) {
+            v -= acc[0][i][j][h];
+          } else {
+            v.x -= acc[0][i][j][h];
+            v.y -= acc[1][i][j][h];
+          }
+          F[(long long)c * ld + r] = v;
         }
       }
-    }
   }
 }
 
