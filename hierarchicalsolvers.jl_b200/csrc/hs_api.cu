@@ -133,7 +133,7 @@ template <typename T> static void trsm_dispatch(hs_fac* f, int W, int f0, int na
   if (W == W0) launch_trsm_w<T, W0>(f, f0, nact, J0, j0, NB, cmode, max_cols);
   else if (W == W0 / 2) launch_trsm_w<T, W0 / 2>(f, f0, nact, J0, j0, NB, cmode, max_cols);
   else if (W == W0 / 4) launch_trsm_w<T, W0 / 4>(f, f0, nact, J0, j0, NB, cmode, max_cols);
-  else launch_trsm_w<T, W0 / 8>(f, f0, nact, J0, j0, NB, cmode, max_cols);
+  else if constexpr (W0 / 8 >= 8) launch_trsm_w<T, W0 / 8>(f, f0, nact, J0, j0, NB, cmode, max_cols);
   ++f->stats.launches_factor;
 }
 

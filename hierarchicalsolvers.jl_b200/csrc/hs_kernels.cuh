@@ -82,10 +82,13 @@ __global__ void __launch_bounds__(256) k_extend_add(const Front* __restrict__ fr
   for (int a = threadIdx.x; a < nb; a += blockDim.x) {
     const int pr = map[a];
     if (pr < 0) continue;
+    T v[CB];  // all loads first: source and destination live in the same pool, so interleaved they would serialise
+#pragma unroll
+    for (int b = 0; b < CB; ++b) v[b] = s_pb[b] >= 0 ? S[(long long)(b0 + b) * ch.ld + a] : hs_zero<T>();
 #pragma unroll
     for (int b = 0; b < CB; ++b) {
       const int pc = s_pb[b];
-      if (pc >= 0) P[(long long)pc * pa.ld + pr] = S[(long long)(b0 + b) * ch.ld + a];
+      if (pc >= 0) P[(long long)pc * pa.ld + pr] = v[b];
     }
   }
 }

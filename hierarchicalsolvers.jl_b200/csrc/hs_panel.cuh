@@ -10,27 +10,28 @@ namespace cg = cooperative_groups;
 // ------------------------------------------------------------------------------------------------
 // LU panel with partial pivoting restricted to the pivot block rows (rows < ni)
 // ------------------------------------------------------------------------------------------------
-// Panel = front rows [j0, n) × columns [j0, j0+wc).  Every thread keeps R rows × W columns in registers; a cluster
-// of C CTAs (256 threads each) covers 256·R·C rows.
-//
-// Per column: local |a| arg-max → the CTA's candidate row is parked in shared memory → ONE cluster barrier → warp 0
-// of every CTA pulls the C candidates and the winning row through distributed shared memory → rank-1 update from
-// registers.  Pivoting is IMPLICIT: a row chosen as pivot is frozen where it is (its owner writes it out and stops
-// updating it); rows are moved to their LAPACK positions once, at the end, by CTA 0.  The column loop is rolled:
-// CH columns are processed with static register indices, then every row is rotated left by CH registers, so the
-// loop body stays ~20 KB of code (a fully unrolled panel was 1.5 MB and ran at instruction-fetch speed).
+// Panel = front rows [j0, n) × columns [j0, j0+wc).  The 256 threads of a CTA form a 32×8 grid; thread (tr, tc)
+// keeps rows tr + 32·i (i < 8·R) and columns tc + 8·k (k < W/8) of the CTA's row block in registers, a cluster of C
+// CTAs covers 256·R·C rows.  Per pivot column:
+//   (a) the 32 threads that own the column publish it and |.| of the eligible rows to shared memory      → barrier
+//   (b) every warp finds the CTA's best row redundantly; the 8 threads owning that row publish it
+//   (c) clusters only: one cluster barrier, warp 0 pulls the C candidates and the winning row through DSMEM → barrier
+//   (d) rank-1 update from registers; the pivot row is written out by its owner and frozen.
+// Pivoting is implicit: rows stay where they are until CTA 0 moves them to their LAPACK positions at the end (the
+// interchange sequence `ipiv` is replayed from the pivot order).  Column indices are static in the unrolled outer
+// loop (k = j / 8), so the body is small and stays in the instruction cache.
 struct PanelCand {
   double val;
   int row;
-  int pad;
+  int cta;
 };
 
 template <typename T, int W, int R, bool CL>
 __global__ void __launch_bounds__(256, 1) k_panel(const Front* __restrict__ fronts, T* __restrict__ pool,
                                                    int* __restrict__ ipiv, int f0, int j0, int* __restrict__ info) {
-  constexpr int NT = 256;
-  constexpr int CH = 4;
-  static_assert(W % CH == 0, "panel width must be a multiple of the chunk");
+  constexpr int NT = 256, TR = 32, TC = 8;
+  constexpr int RPT = 8 * R, CPT = W / TC, ROWS = TR * RPT;
+  static_assert(W % TC == 0 && RPT <= 64, "unsupported panel shape");
   cg::cluster_group cluster = cg::this_cluster();
   const int C = CL ? (int)cluster.num_blocks() : 1;
   const int crank = CL ? (int)cluster.block_rank() : 0;
@@ -40,11 +41,15 @@ __global__ void __launch_bounds__(256, 1) k_panel(const Front* __restrict__ fron
   const int wc = min(W, fr.ni - j0);
   const int m = fr.n - j0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tr = tid % TR, tc = tid / TR;
+  const int rbase = crank * ROWS;
   T* F = pool + fr.off;
   const long long ld = fr.ld;
 
-  __shared__ double s_wval[NT / 32];
-  __shared__ int s_wrow[NT / 32];
+  extern __shared__ __align__(16) unsigned char smem_dyn[];
+  T* s_col = reinterpret_cast<T*>(smem_dyn);                 // [2][ROWS]   column j of this CTA's rows
+  double* s_abs = reinterpret_cast<double*>(s_col + 2 * ROWS);  // [2][ROWS] |.| of eligible rows, -1 otherwise
+  T* stage = s_col;                                          // reused after the loop: staging of the row moves
   __shared__ PanelCand s_cand[2];
   __shared__ T s_crow[2][W];
   __shared__ T s_u[W];
@@ -52,124 +57,135 @@ __global__ void __launch_bounds__(256, 1) k_panel(const Front* __restrict__ fron
   __shared__ int s_pivrow[W];
   __shared__ int s_what[W], s_where[W], s_isp[W];
   __shared__ int s_mdst[2 * W], s_msrc[2 * W], s_nmv;
-  extern __shared__ __align__(16) unsigned char smem_dyn[];  // CTA 0: staging of the final row permutation
 
-  T a[R][W];
-  int rows[R];
-  unsigned done = 0;
+  T a[RPT][CPT];
+  unsigned long long done = 0;
 #pragma unroll
-  for (int s = 0; s < R; ++s) {
-    rows[s] = crank * (NT * R) + s * NT + tid;
-    const bool ok = rows[s] < m;
+  for (int i = 0; i < RPT; ++i) {
+    const int r = rbase + tr + TR * i;
 #pragma unroll
-    for (int k = 0; k < W; ++k) a[s][k] = (ok && k < wc) ? F[(long long)(j0 + k) * ld + (j0 + rows[s])] : hs_zero<T>();
+    for (int k = 0; k < CPT; ++k) {
+      const int c = tc + TC * k;
+      a[i][k] = (r < m && c < wc) ? F[(long long)(j0 + c) * ld + (j0 + r)] : hs_zero<T>();
+    }
   }
 
-  for (int jc = 0; jc < wc; jc += CH) {
 #pragma unroll
-    for (int t = 0; t < CH; ++t) {
-      const int j = jc + t;
-      if (j < wc) {
-        const int par = j & 1;
-        // 1. thread-local then warp-level arg-max of |a(:,j)| over the rows still eligible (ties → smallest row)
-        double best = -1.0;
-        int brow = 0x7fffffff;
+  for (int kj = 0; kj < CPT; ++kj) {
+    for (int jt = 0; jt < TC; ++jt) {
+      const int j = kj * TC + jt;
+      if (j >= wc) break;
+      const int par = j & 1;
+      T* colp = s_col + par * ROWS;
+      double* absp = s_abs + par * ROWS;
+      // (a) the owners of column j publish it
+      if (tc == jt) {
 #pragma unroll
-        for (int s = 0; s < R; ++s) {
-          if (!((done >> s) & 1u) && j0 + rows[s] < fr.ni) {
-            const double v = hs_abs1(a[s][t]);
-            if (v > best || (v == best && rows[s] < brow)) { best = v; brow = rows[s]; }
+        for (int i = 0; i < RPT; ++i) {
+          const int rl = tr + TR * i, r = rbase + rl;
+          colp[rl] = a[i][kj];
+          absp[rl] = (!((done >> i) & 1ull) && r < m && j0 + r < fr.ni) ? hs_abs1(a[i][kj]) : -1.0;
+        }
+      }
+      __syncthreads();
+      // (b) every warp finds the CTA's candidate (largest |.|, smallest row on ties)
+      double cb = -1.0;
+      int crl = 0x7fffffff;
+#pragma unroll
+      for (int q = 0; q < ROWS / 32; ++q) {
+        const int rl = lane + 32 * q;
+        const double v = absp[rl];
+        if (v > cb) { cb = v; crl = rl; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, cb, o);
+        const int orl = __shfl_xor_sync(0xffffffffu, crl, o);
+        if (ov > cb || (ov == cb && orl < crl)) { cb = ov; crl = orl; }
+      }
+      if (cb >= 0.0 && tr == crl % TR) {  // the 8 threads that own the candidate row publish it
+        const int ip = crl / TR;
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+          if (i == ip) {
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) s_crow[par][tc + TC * k] = a[i][k];
           }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const double ov = __shfl_xor_sync(0xffffffffu, best, o);
-          const int orow = __shfl_xor_sync(0xffffffffu, brow, o);
-          if (ov > best || (ov == best && orow < brow)) { best = ov; brow = orow; }
-        }
-        if (lane == 0) { s_wval[warp] = best; s_wrow[warp] = brow; }
-        __syncthreads();
-        // 2. CTA-level candidate; its owner parks the whole register row (L entries, pivot, U entries)
-        double cb = -1.0;
-        int cr = 0x7fffffff;
-#pragma unroll
-        for (int w = 0; w < NT / 32; ++w) {
-          const double ov = s_wval[w];
-          const int orow = s_wrow[w];
-          if (ov > cb || (ov == cb && orow < cr)) { cb = ov; cr = orow; }
-        }
-#pragma unroll
-        for (int s = 0; s < R; ++s) {
-          if (rows[s] == cr && cb >= 0.0) {
-#pragma unroll
-            for (int k = 0; k < W; ++k) s_crow[par][k] = a[s][k];
-          }
-        }
-        if (tid == 0) { s_cand[par].val = cb; s_cand[par].row = cr; }
-        // 3. one barrier per column
-        if (CL) cluster.sync(); else __syncthreads();
-        // 4. warp 0 pulls the candidates and the winning row
+      }
+      double gb;
+      int p, gc;
+      const T* urow;
+      if (CL) {
+        if (tid == 0) { s_cand[par].val = cb; s_cand[par].row = cb >= 0.0 ? rbase + crl : 0x7fffffff; }
+        cluster.sync();
+        // (c) warp 0 pulls the candidates and the winning row
         if (warp == 0) {
-          double gb = -1.0;
-          int gr = 0x7fffffff, gc = 0;
+          double wb = -1.0;
+          int wr = 0x7fffffff, wcid = 0;
           if (lane < C) {
-            const PanelCand* rc = CL ? cluster.map_shared_rank(&s_cand[par], lane) : &s_cand[par];
-            gb = rc->val; gr = rc->row; gc = lane;
+            const PanelCand* rc = cluster.map_shared_rank(&s_cand[par], lane);
+            wb = rc->val; wr = rc->row; wcid = lane;
           }
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) {
-            const double ov = __shfl_xor_sync(0xffffffffu, gb, o);
-            const int orow = __shfl_xor_sync(0xffffffffu, gr, o);
-            const int oc = __shfl_xor_sync(0xffffffffu, gc, o);
-            if (ov > gb || (ov == gb && orow < gr)) { gb = ov; gr = orow; gc = oc; }
+            const double ov = __shfl_xor_sync(0xffffffffu, wb, o);
+            const int orow = __shfl_xor_sync(0xffffffffu, wr, o);
+            const int oc = __shfl_xor_sync(0xffffffffu, wcid, o);
+            if (ov > wb || (ov == wb && orow < wr)) { wb = ov; wr = orow; wcid = oc; }
           }
-          const T* src = CL ? cluster.map_shared_rank(&s_crow[par][0], gc) : &s_crow[par][0];
-          if (gb >= 0.0)
+          const T* src = cluster.map_shared_rank(&s_crow[par][0], wcid);
+          if (wb >= 0.0)
             for (int k = lane; k < W; k += 32) s_u[k] = src[k];
-          if (lane == 0) { s_win.val = gb; s_win.row = gr; s_win.pad = gc; }
+          if (lane == 0) { s_win.val = wb; s_win.row = wr; s_win.cta = wcid; }
         }
         __syncthreads();
-        // 5. the pivot row is final: the CTA that owns it writes it out (physical position; moved at the end)
-        const double gb = s_win.val;
-        const int p = s_win.row;
-        if (s_win.pad == crank && gb >= 0.0) {
-          for (int k = tid; k < W; k += NT)
-            if (jc + k < wc) F[(long long)(j0 + jc + k) * ld + (j0 + p)] = s_u[k];
+        gb = s_win.val; p = s_win.row; gc = s_win.cta;
+        urow = s_u;
+      } else {
+        __syncthreads();
+        gb = cb; p = crl; gc = 0;
+        urow = &s_crow[par][0];
+      }
+      // (d) the pivot row is final: its CTA writes it out (physical position; moved at the end) and freezes it
+      if (gc == crank && gb >= 0.0) {
+        if (tid < wc) F[(long long)(j0 + tid) * ld + (j0 + p)] = urow[tid];
+        const int pl = p - rbase;
+        if (tr == pl % TR) done |= 1ull << (pl / TR);
+      }
+      if (crank == 0 && tid == 0) {
+        s_pivrow[j] = p;
+        if (!(gb > 0.0) && atomicCAS(&info[0], 0, 1) == 0) { info[1] = fi; info[2] = j0 + j; }
+      }
+      if (gb > 0.0) {  // an exactly singular column is recorded and skipped, as LAPACK getf2 does
+        const T inv = hs_recip(urow[j]);
+        T l[RPT];
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+          const int rl = tr + TR * i;
+          const bool act = !((done >> i) & 1ull) && rbase + rl < m;
+          l[i] = act ? hs_mul(colp[rl], inv) : hs_zero<T>();
+          if (act && tc == jt) a[i][kj] = l[i];
         }
-        if (crank == 0 && tid == 0) {
-          s_pivrow[j] = p;
-          if (!(gb > 0.0) && atomicCAS(&info[0], 0, 1) == 0) { info[1] = fi; info[2] = j0 + j; }
-        }
 #pragma unroll
-        for (int s = 0; s < R; ++s)
-          if (rows[s] == p) done |= 1u << s;
-        // 6. elimination (an exactly singular column is recorded and skipped, as LAPACK getf2 does)
-        if (gb > 0.0) {
-          const T inv = hs_recip(s_u[t]);
+        for (int k = kj; k < CPT; ++k) {
+          if (k == kj && tc <= jt) continue;
+          const T u = urow[tc + TC * k];
 #pragma unroll
-          for (int s = 0; s < R; ++s) {
-            if (!((done >> s) & 1u) && rows[s] < m) {
-              const T l = hs_mul(a[s][t], inv);
-              a[s][t] = l;
-#pragma unroll
-              for (int k = t + 1; k < W; ++k) a[s][k] = hs_fnma(a[s][k], l, s_u[k]);
-            }
-          }
+          for (int i = 0; i < RPT; ++i) a[i][k] = hs_fnma(a[i][k], l[i], u);
         }
       }
     }
-    // end of chunk: the first CH registers of every live row are final multipliers → store, then rotate the row
+  }
+  // live rows go back to global memory (frozen pivot rows were written when they were chosen)
 #pragma unroll
-    for (int s = 0; s < R; ++s) {
-      if (!((done >> s) & 1u) && rows[s] < m) {
+  for (int i = 0; i < RPT; ++i) {
+    const int r = rbase + tr + TR * i;
+    if (((done >> i) & 1ull) || r >= m) continue;
 #pragma unroll
-        for (int t = 0; t < CH; ++t)
-          if (jc + t < wc) F[(long long)(j0 + jc + t) * ld + (j0 + rows[s])] = a[s][t];
-      }
-#pragma unroll
-      for (int k = 0; k < W - CH; ++k) a[s][k] = a[s][k + CH];
-#pragma unroll
-      for (int k = W - CH; k < W; ++k) a[s][k] = hs_zero<T>();
+    for (int k = 0; k < CPT; ++k) {
+      const int c = tc + TC * k;
+      if (c < wc) F[(long long)(j0 + c) * ld + (j0 + r)] = a[i][k];
     }
   }
   // every row of the panel is in global memory at its physical position; CTA 0 moves rows to their LAPACK places
@@ -198,7 +214,6 @@ __global__ void __launch_bounds__(256, 1) k_panel(const Front* __restrict__ fron
   __syncthreads();
   const int nm = s_nmv;
   if (nm == 0) return;
-  T* stage = reinterpret_cast<T*>(smem_dyn);  // nm × wc
   for (int e = tid; e < nm * wc; e += NT) {
     const int i = e % nm, c = e / nm;
     stage[e] = F[(long long)(j0 + c) * ld + (j0 + s_msrc[i])];
@@ -210,6 +225,13 @@ __global__ void __launch_bounds__(256, 1) k_panel(const Front* __restrict__ fron
   }
 }
 
+template <typename T, int W, int R> constexpr size_t panel_smem() {
+  // max(column/abs double buffers, staging of 2W moved rows × W columns)
+  constexpr size_t colabs = 2 * (size_t)(32 * 8 * R) * (sizeof(T) + sizeof(double));
+  constexpr size_t stg = 2 * (size_t)W * W * sizeof(T);
+  return colabs > stg ? colabs : stg;
+}
+
 // ------------------------------------------------------------------------------------------------
 // panel launch: pick the register tile (W, R) and the cluster size for the tallest active panel
 // ------------------------------------------------------------------------------------------------
@@ -218,12 +240,12 @@ static void launch_panel(hs_fac* f, int f0, int nact, int j0, int C) {
   cudaStream_t st = f->ctx->stream;
   T* pool = (T*)f->pool;
   if (C == 1) {
-    k_panel<T, W, R, false><<<nact, 256, 2 * W * W * sizeof(T), st>>>(f->d_fronts, pool, f->d_ipiv, f0, j0, f->d_info);
+    k_panel<T, W, R, false><<<nact, 256, panel_smem<T, W, R>(), st>>>(f->d_fronts, pool, f->d_ipiv, f0, j0, f->d_info);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(nact * C));
     cfg.blockDim = dim3(256);
-    cfg.dynamicSmemBytes = 2 * W * W * sizeof(T);
+    cfg.dynamicSmemBytes = panel_smem<T, W, R>();
     cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
@@ -250,7 +272,7 @@ static int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 template <typename T> static int choose_width(const hs_fac* f, int max_n) {
   const int W0 = PanelW<T>::W0;
   const int maxC = f->ctx->max_cluster;
-  for (int W = W0, R = 1; R <= 8; W >>= 1, R <<= 1)
+  for (int W = W0, R = 1; R <= 8 && W >= 8; W >>= 1, R <<= 1)
     if ((long long)256 * R * maxC >= max_n) return W;
   return -1;
 }
@@ -263,16 +285,17 @@ static void panel_dispatch(hs_fac* f, int W, int f0, int nact, int j0, int m) {
   if (W == W0) launch_panel<T, W0, 1>(f, f0, nact, j0, C);
   else if (W == W0 / 2) launch_panel<T, W0 / 2, 2>(f, f0, nact, j0, C);
   else if (W == W0 / 4) launch_panel<T, W0 / 4, 4>(f, f0, nact, j0, C);
-  else launch_panel<T, W0 / 8, 8>(f, f0, nact, j0, C);
+  else if constexpr (W0 / 8 >= 8) launch_panel<T, W0 / 8, 8>(f, f0, nact, j0, C);
 }
 
 
 template <typename T, int W, int R> static void set_panel_attrs() {
   CUDA_OK(cudaFuncSetAttribute(k_panel<T, W, R, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-  CUDA_OK(cudaFuncSetAttribute(k_panel<T, W, R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * W * W * (int)sizeof(T)));
-  CUDA_OK(cudaFuncSetAttribute(k_panel<T, W, R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * W * W * (int)sizeof(T)));
+  CUDA_OK(cudaFuncSetAttribute(k_panel<T, W, R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem<T, W, R>()));
+  CUDA_OK(cudaFuncSetAttribute(k_panel<T, W, R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem<T, W, R>()));
 }
 template <typename T> static void panel_setup() {
   constexpr int W0 = PanelW<T>::W0;
-  set_panel_attrs<T, W0, 1>(); set_panel_attrs<T, W0 / 2, 2>(); set_panel_attrs<T, W0 / 4, 4>(); set_panel_attrs<T, W0 / 8, 8>();
+  set_panel_attrs<T, W0, 1>(); set_panel_attrs<T, W0 / 2, 2>(); set_panel_attrs<T, W0 / 4, 4>();
+  if constexpr (W0 / 8 >= 8) set_panel_attrs<T, W0 / 8, 8>();
 }
