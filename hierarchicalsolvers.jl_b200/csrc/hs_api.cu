@@ -51,6 +51,14 @@ extern "C" int32_t hs_create(hs_ctx** out, int32_t device) {
   c->device = device;
   CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   c->own_stream = true;
+  {
+    int lo = 0, hi = 0;  // numerically lower = higher priority
+    CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CUDA_OK(cudaStreamCreateWithPriority(&c->aux_stream, cudaStreamNonBlocking, hi));
+  }
+  CUDA_OK(cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming));
+  CUDA_OK(cudaEventCreateWithFlags(&c->ev_c2, cudaEventDisableTiming));
+  if (getenv("HS_LOOKAHEAD")) c->lookahead_max_fronts = atoi(getenv("HS_LOOKAHEAD"));
   c->profile = getenv("HS_PROFILE") != nullptr;
   // opt in to 16-CTA clusters for the tall panels, and to >48 KB dynamic shared memory for the DMMA tiles
   hs_panel_setup_f64();
@@ -90,6 +98,9 @@ extern "C" int32_t hs_destroy(hs_ctx* ctx) {
   if (!ctx) return HS_OK;
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   cudaFree(ctx->gm_buf);
+  if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+  if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
+  if (ctx->ev_c2) cudaEventDestroy(ctx->ev_c2);
   delete ctx;
   return HS_OK;
 }
@@ -121,19 +132,19 @@ template <typename T> struct PanelW;  // widest register tile per scalar type
 template <> struct PanelW<double> { static constexpr int W0 = 64; };
 template <> struct PanelW<cplx> { static constexpr int W0 = 32; };
 
-template <typename T, int W> static void launch_trsm_w(hs_fac* f, int f0, int nact, int J0, int j0, int NB, int cmode, int max_cols) {
+template <typename T, int W> static void launch_trsm_w(hs_fac* f, int f0, int nact, int J0, int j0, int NB, int cmode, int max_cols, cudaStream_t st) {
   dim3 grid(nact, (max_cols + 127) / 128);
-  k_swap_trsm<T, W><<<grid, 128, 0, f->ctx->stream>>>(f->d_fronts, (T*)f->pool, f->d_ipiv, f0, J0, j0, NB, cmode);
+  k_swap_trsm<T, W><<<grid, 128, 0, st>>>(f->d_fronts, (T*)f->pool, f->d_ipiv, f0, J0, j0, NB, cmode);
   CUDA_OK(cudaGetLastError());
 }
 
-template <typename T> static void trsm_dispatch(hs_fac* f, int W, int f0, int nact, int J0, int j0, int NB, int cmode, int max_cols) {
+template <typename T> static void trsm_dispatch(hs_fac* f, int W, int f0, int nact, int J0, int j0, int NB, int cmode, int max_cols, cudaStream_t st) {
   constexpr int W0 = PanelW<T>::W0;
   if (max_cols <= 0) return;
-  if (W == W0) launch_trsm_w<T, W0>(f, f0, nact, J0, j0, NB, cmode, max_cols);
-  else if (W == W0 / 2) launch_trsm_w<T, W0 / 2>(f, f0, nact, J0, j0, NB, cmode, max_cols);
-  else if (W == W0 / 4) launch_trsm_w<T, W0 / 4>(f, f0, nact, J0, j0, NB, cmode, max_cols);
-  else if constexpr (W0 / 8 >= 8) launch_trsm_w<T, W0 / 8>(f, f0, nact, J0, j0, NB, cmode, max_cols);
+  if (W == W0) launch_trsm_w<T, W0>(f, f0, nact, J0, j0, NB, cmode, max_cols, st);
+  else if (W == W0 / 2) launch_trsm_w<T, W0 / 2>(f, f0, nact, J0, j0, NB, cmode, max_cols, st);
+  else if (W == W0 / 4) launch_trsm_w<T, W0 / 4>(f, f0, nact, J0, j0, NB, cmode, max_cols, st);
+  else if constexpr (W0 / 8 >= 8) launch_trsm_w<T, W0 / 8>(f, f0, nact, J0, j0, NB, cmode, max_cols, st);
   ++f->stats.launches_factor;
 }
 
@@ -160,34 +171,44 @@ template <typename T> static void factor_level(hs_fac* f, const Level& L) {
     // fronts are sorted by ni descending: the active ones (ni > j) are a prefix
     return (int)(std::partition_point(L.ni_sorted.begin(), L.ni_sorted.end(), [&](int v) { return v > j; }) - L.ni_sorted.begin());
   };
-  auto gemm = [&](int nact, int J0, int j0, int mode, int mrows, int mcols) {
+  auto gemm = [&](int nact, int J0, int j0, int mode, int mrows, int mcols, cudaStream_t stream) {
     if (nact <= 0 || mrows <= 0 || mcols <= 0) return;
     PhaseTimer t(f, &f->stats.ms_gemm);
     dim3 grid(nact, (mrows + Cfg::TM - 1) / Cfg::TM + 1, (mcols + Cfg::TN - 1) / Cfg::TN);
-    k_gemm<T><<<grid, 256, smem_gemm, st>>>(f->d_fronts, (T*)f->pool, L.f0, J0, j0, NB, W, mode);
+    k_gemm<T><<<grid, 256, smem_gemm, stream>>>(f->d_fronts, (T*)f->pool, L.f0, J0, j0, NB, W, mode);
     CUDA_OK(cudaGetLastError());
     ++f->stats.gemm_launches;
     ++f->stats.launches_factor;
   };
-  for (int J0 = 0; J0 < L.max_ni; J0 += NB) {
-    const int JE = std::min(J0 + NB, L.max_ni);
-    // phase A: factor the block's columns; interchanges, solves and updates stay inside the block
+  // look-ahead (few, large fronts): while the big trailing update of block k runs on the caller's stream, the panels
+  // of block k+1 — which only need the update of their own columns and occupy one cluster per front — run on a
+  // high-priority second stream.
+  const bool lookahead = !f->ctx->profile && (L.f1 - L.f0) <= f->ctx->lookahead_max_fronts && L.max_ni > NB;
+  cudaStream_t hi = f->ctx->aux_stream;
+  auto phaseA = [&](int J0, int JE, cudaStream_t s_) {
+    // factor the block's columns; interchanges, solves and updates stay inside the block
     for (int j0 = J0; j0 < JE; j0 += W) {
       const int nact = nactive(j0);
       if (nact == 0) break;
       const int m = L.max_n - j0;
       {
         PhaseTimer t(f, &f->stats.ms_panel);
-        hs_panel_launch(f, W, L.f0, nact, j0, m);
+        hs_panel_launch(f, W, L.f0, nact, j0, m, s_);
         ++f->stats.panel_launches;
         ++f->stats.launches_factor;
       }
       {
         PhaseTimer t(f, &f->stats.ms_trsm);
-        trsm_dispatch<T>(f, W, L.f0, nact, J0, j0, NB, 0, JE - J0);
+        trsm_dispatch<T>(f, W, L.f0, nact, J0, j0, NB, 0, JE - J0, s_);
       }
-      gemm(nact, J0, j0, 0, m, JE - j0);
+      gemm(nact, J0, j0, 0, m, JE - j0, s_);
     }
+  };
+  bool a_on_hi = false;  // phase A of the current block was issued on the look-ahead stream
+  for (int J0 = 0; J0 < L.max_ni; J0 += NB) {
+    const int JE = std::min(J0 + NB, L.max_ni);
+    if (a_on_hi) { CUDA_OK(cudaStreamWaitEvent(st, f->ctx->ev_c2, 0)); a_on_hi = false; }
+    else phaseA(J0, JE, st);
     // phase B: the columns outside the block: all interchanges first, then solve / update sub-block by sub-block
     const int nactB = nactive(J0);
     const int mB = L.max_n - J0 - 1;  // at least one pivot column is gone
@@ -204,14 +225,25 @@ template <typename T> static void factor_level(hs_fac* f, const Level& L) {
         if (nact == 0) break;
         {
           PhaseTimer t(f, &f->stats.ms_trsm);
-          trsm_dispatch<T>(f, W, L.f0, nact, J0, j0, NB, 1, mB);
+          trsm_dispatch<T>(f, W, L.f0, nact, J0, j0, NB, 1, mB, st);
         }
-        gemm(nact, J0, j0, 2, JE - j0, mB);
+        gemm(nact, J0, j0, 2, JE - j0, mB, st);
       }
       // phase C: the big update with K = BE − J0
-      gemm(nactB, J0, J0, 1, mB, mB);
+      if (lookahead && JE < L.max_ni) {
+        CUDA_OK(cudaEventRecord(f->ctx->ev_b, st));
+        CUDA_OK(cudaStreamWaitEvent(hi, f->ctx->ev_b, 0));
+        gemm(nactB, J0, J0, 3, mB, NB, hi);                     // the next block's own columns …
+        phaseA(JE, std::min(JE + NB, L.max_ni), hi);            // … and its panels, on the look-ahead stream
+        CUDA_OK(cudaEventRecord(f->ctx->ev_c2, hi));
+        a_on_hi = true;
+        gemm(nactB, J0, J0, 4, mB, mB, st);                     // everything right of the next block
+      } else {
+        gemm(nactB, J0, J0, 1, mB, mB, st);
+      }
     }
   }
+  if (a_on_hi) CUDA_OK(cudaStreamWaitEvent(st, f->ctx->ev_c2, 0));
   {  // flops the GEMM launches of this level issue: Σ_steps 2·(n−j0−wc)²·wc per front
     const double cx = f->dtype == HS_C64 ? 4.0 : 1.0;
     for (int i = L.f0; i < L.f1; ++i) {

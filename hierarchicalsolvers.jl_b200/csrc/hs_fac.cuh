@@ -24,6 +24,9 @@ struct hs_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  cudaStream_t aux_stream = nullptr;  // look-ahead: the big trailing update overlaps the next block's panels
+  cudaEvent_t ev_b = nullptr, ev_c2 = nullptr;
+  int lookahead_max_fronts = 32;
   int max_cluster = 8;
   bool profile = false;
   long long launches = 0;
@@ -92,13 +95,13 @@ void hs_panel_setup_f64();
 void hs_panel_setup_c64();
 int hs_panel_width_f64(const hs_fac* f, int max_n);
 int hs_panel_width_c64(const hs_fac* f, int max_n);
-void hs_panel_launch_f64(hs_fac* f, int W, int f0, int nact, int j0, int m);
-void hs_panel_launch_c64(hs_fac* f, int W, int f0, int nact, int j0, int m);
+void hs_panel_launch_f64(hs_fac* f, int W, int f0, int nact, int j0, int m, cudaStream_t st);
+void hs_panel_launch_c64(hs_fac* f, int W, int f0, int nact, int j0, int m, cudaStream_t st);
 inline int hs_panel_width(const hs_fac* f, int max_n) {
   return f->dtype == HS_F64 ? hs_panel_width_f64(f, max_n) : hs_panel_width_c64(f, max_n);
 }
-inline void hs_panel_launch(hs_fac* f, int W, int f0, int nact, int j0, int m) {
-  if (f->dtype == HS_F64) hs_panel_launch_f64(f, W, f0, nact, j0, m); else hs_panel_launch_c64(f, W, f0, nact, j0, m);
+inline void hs_panel_launch(hs_fac* f, int W, int f0, int nact, int j0, int m, cudaStream_t st) {
+  if (f->dtype == HS_F64) hs_panel_launch_f64(f, W, f0, nact, j0, m, st); else hs_panel_launch_c64(f, W, f0, nact, j0, m, st);
 }
 
 // hs_solve.cu

@@ -205,6 +205,8 @@ __global__ void __launch_bounds__(128) k_laswp(const Front* __restrict__ fronts,
 //   mode 0: K = [j0, j0+wc),  C = rows [j0+wc, n)  × cols [j0+wc, BE)   (inside the block, while it is factored)
 //   mode 2: K = [j0, j0+wc),  C = rows [j0+wc, BE) × cols [BE, n)      (top strip of the outside columns, after it)
 //   mode 1: K = [J0, BE),     C = [BE, n)²                             (the big update, K up to NB)
+//   mode 3 / 4: the big update split for look-ahead: columns of the NEXT outer block [BE, BE2) / the rest [BE2, n),
+//               BE2 = min(BE+NB, ni); mode 4 runs on a second stream while the next block's panels are factored
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -246,9 +248,12 @@ __global__ void __launch_bounds__(256, 1) k_gemm(const Front* __restrict__ front
   const int n = fr.n, ni = fr.ni;
   int kbase, kcount, lo, rhi, clo, chi;  // C = rows [lo, rhi) × cols [clo, chi)
   const int BE = min(J0 + NB, ni);
-  if (mode == 1) {
+  if (mode == 1 || mode >= 3) {
     if (ni <= J0) return;
-    kbase = J0; kcount = BE - J0; lo = BE; rhi = n; clo = BE; chi = n;
+    const int BE2 = min(BE + NB, ni);
+    kbase = J0; kcount = BE - J0; lo = BE; rhi = n;
+    clo = mode == 4 ? BE2 : BE;
+    chi = mode == 3 ? BE2 : n;
   } else {
     if (ni <= j0) return;
     const int wc = min(W, ni - j0);

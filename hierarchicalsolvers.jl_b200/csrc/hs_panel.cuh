@@ -236,8 +236,7 @@ template <typename T, int W, int R> constexpr size_t panel_smem() {
 // panel launch: pick the register tile (W, R) and the cluster size for the tallest active panel
 // ------------------------------------------------------------------------------------------------
 template <typename T, int W, int R>
-static void launch_panel(hs_fac* f, int f0, int nact, int j0, int C) {
-  cudaStream_t st = f->ctx->stream;
+static void launch_panel(hs_fac* f, int f0, int nact, int j0, int C, cudaStream_t st) {
   T* pool = (T*)f->pool;
   if (C == 1) {
     k_panel<T, W, R, false><<<nact, 256, panel_smem<T, W, R>(), st>>>(f->d_fronts, pool, f->d_ipiv, f0, j0, f->d_info);
@@ -278,14 +277,14 @@ template <typename T> static int choose_width(const hs_fac* f, int max_n) {
 }
 
 template <typename T>
-static void panel_dispatch(hs_fac* f, int W, int f0, int nact, int j0, int m) {
+static void panel_dispatch(hs_fac* f, int W, int f0, int nact, int j0, int m, cudaStream_t st) {
   constexpr int W0 = PanelW<T>::W0;
   const int R = W0 / W;
   const int C = pow2_ceil((m + 256 * R - 1) / (256 * R));
-  if (W == W0) launch_panel<T, W0, 1>(f, f0, nact, j0, C);
-  else if (W == W0 / 2) launch_panel<T, W0 / 2, 2>(f, f0, nact, j0, C);
-  else if (W == W0 / 4) launch_panel<T, W0 / 4, 4>(f, f0, nact, j0, C);
-  else if constexpr (W0 / 8 >= 8) launch_panel<T, W0 / 8, 8>(f, f0, nact, j0, C);
+  if (W == W0) launch_panel<T, W0, 1>(f, f0, nact, j0, C, st);
+  else if (W == W0 / 2) launch_panel<T, W0 / 2, 2>(f, f0, nact, j0, C, st);
+  else if (W == W0 / 4) launch_panel<T, W0 / 4, 4>(f, f0, nact, j0, C, st);
+  else if constexpr (W0 / 8 >= 8) launch_panel<T, W0 / 8, 8>(f, f0, nact, j0, C, st);
 }
 
 
