@@ -162,7 +162,7 @@ template <typename T> static void factor_level(hs_fac* f, const Level& L) {
     hs_solve_prep(f, L);
     return;
   }
-  const int W = hs_panel_width(f, L.max_n);
+  const int W = hs_panel_width(f, L.max_n, L.f1 - L.f0);
   if (W < 0) throw hs_error(HS_ESIZE, "front with " + std::to_string(L.max_n) + " rows exceeds the panel kernels");
   const int NB = std::max(W, f->ctx->outer_block / W * W);
   constexpr int smem_gemm = gemm_smem_bytes<T>();

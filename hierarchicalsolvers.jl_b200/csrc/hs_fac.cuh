@@ -93,12 +93,12 @@ struct hs_fac {
 // hs_panel_f64.cu / hs_panel_c64.cu
 void hs_panel_setup_f64();
 void hs_panel_setup_c64();
-int hs_panel_width_f64(const hs_fac* f, int max_n);
-int hs_panel_width_c64(const hs_fac* f, int max_n);
+int hs_panel_width_f64(const hs_fac* f, int max_n, int nfronts);
+int hs_panel_width_c64(const hs_fac* f, int max_n, int nfronts);
 void hs_panel_launch_f64(hs_fac* f, int W, int f0, int nact, int j0, int m, cudaStream_t st);
 void hs_panel_launch_c64(hs_fac* f, int W, int f0, int nact, int j0, int m, cudaStream_t st);
-inline int hs_panel_width(const hs_fac* f, int max_n) {
-  return f->dtype == HS_F64 ? hs_panel_width_f64(f, max_n) : hs_panel_width_c64(f, max_n);
+inline int hs_panel_width(const hs_fac* f, int max_n, int nfronts) {
+  return f->dtype == HS_F64 ? hs_panel_width_f64(f, max_n, nfronts) : hs_panel_width_c64(f, max_n, nfronts);
 }
 inline void hs_panel_launch(hs_fac* f, int W, int f0, int nact, int j0, int m, cudaStream_t st) {
   if (f->dtype == HS_F64) hs_panel_launch_f64(f, W, f0, nact, j0, m, st); else hs_panel_launch_c64(f, W, f0, nact, j0, m, st);

@@ -3,6 +3,8 @@
 
 #include <cooperative_groups.h>
 
+#include <cstdlib>
+
 #include "hs_fac.cuh"
 
 namespace cg = cooperative_groups;
@@ -268,9 +270,16 @@ template <> struct PanelW<cplx> { static constexpr int W0 = 32; };
 static int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 // panel width used for a level whose tallest front has n rows
-template <typename T> static int choose_width(const hs_fac* f, int max_n) {
+template <typename T> static int choose_width(const hs_fac* f, int max_n, int nfronts) {
   const int W0 = PanelW<T>::W0;
   const int maxC = f->ctx->max_cluster;
+  // many fronts per level (more CTAs than SMs): throughput matters, not the latency of one front.  A CTA that holds
+  // more rows of a narrower panel avoids the cluster barrier altogether (HS_PANEL_TALL=0 disables).
+  static const bool tall = !(getenv("HS_PANEL_TALL") && atoi(getenv("HS_PANEL_TALL")) == 0);
+  if (tall && (long long)nfronts * ((max_n + 255) / 256) > 148 && max_n > 256) {
+    for (int W = W0, R = 1; R <= 4 && W >= 8; W >>= 1, R <<= 1)
+      if (256 * R >= max_n) return W;
+  }
   for (int W = W0, R = 1; R <= 8 && W >= 8; W >>= 1, R <<= 1)
     if ((long long)256 * R * maxC >= max_n) return W;
   return -1;
