@@ -297,8 +297,10 @@ template <typename T> static void numeric(hs_fac* f) {
         const Level& Lc = f->levels[li - 1];
         if (Lc.max_nb > 0) {
           constexpr int CB = 8;
-          dim3 g2(Lc.f1 - Lc.f0, (Lc.max_nb + CB - 1) / CB);
-          k_extend_add<T, CB><<<g2, 256, 0, st>>>(f->d_fronts, pool, f->d_cmap, Lc.f0);
+          // one CTA covers ~4096 elements of a child's Schur block: whole small blocks, column groups of large ones
+          const int cols_per_cta = std::max(1, 4096 / Lc.max_nb);
+          dim3 g2(Lc.f1 - Lc.f0, (Lc.max_nb + cols_per_cta - 1) / cols_per_cta);
+          k_extend_add<T, CB><<<g2, 256, 0, st>>>(f->d_fronts, pool, f->d_cmap, Lc.f0, cols_per_cta);
           s.launches_factor += 1;
         }
       }

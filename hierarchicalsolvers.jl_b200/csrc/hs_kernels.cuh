@@ -65,30 +65,46 @@ __global__ void k_scatter_A(const Front* __restrict__ fronts, T* __restrict__ po
 // cmap[a] = row of the parent front that receives the child's boundary row a (-1: dropped).
 template <typename T, int CB>
 __global__ void __launch_bounds__(256) k_extend_add(const Front* __restrict__ fronts, T* __restrict__ pool,
-                                                     const int* __restrict__ cmap, int c0) {
+                                                     const int* __restrict__ cmap, int c0, int cols_per_cta) {
   const int ci = c0 + blockIdx.x;
   const Front ch = fronts[ci];
   if (ch.parent < 0) return;
   const int nb = ch.n - ch.ni;
-  const int b0 = blockIdx.y * CB;
+  const int b0 = blockIdx.y * cols_per_cta;
   if (b0 >= nb) return;
+  const int b1 = min(nb, b0 + cols_per_cta);
   const Front pa = fronts[ch.parent];
   const int* map = cmap + ch.ioff + ch.ni;
   const T* S = pool + ch.off + (long long)ch.ni * ch.ld + ch.ni;
   T* P = pool + pa.off;
-  __shared__ int s_pb[CB];
-  if (threadIdx.x < CB) s_pb[threadIdx.x] = (b0 + threadIdx.x < nb) ? map[b0 + threadIdx.x] : -1;
-  __syncthreads();
-  for (int a = threadIdx.x; a < nb; a += blockDim.x) {
-    const int pr = map[a];
-    if (pr < 0) continue;
-    T v[CB];  // all loads first: source and destination live in the same pool, so interleaved they would serialise
+  // elements (a, b) of the child's Schur block, a fastest: consecutive threads read consecutive rows of one column;
+  // CB elements per thread are loaded before the first store (source and destination live in the same pool)
+  const int total = nb * (b1 - b0);
+  for (int e0 = threadIdx.x; e0 < total; e0 += 256 * CB) {
+    T v[CB];
+    int dst[CB];
 #pragma unroll
-    for (int b = 0; b < CB; ++b) v[b] = s_pb[b] >= 0 ? S[(long long)(b0 + b) * ch.ld + a] : hs_zero<T>();
+    for (int q = 0; q < CB; ++q) {
+      const int e = e0 + q * 256;
+      dst[q] = -1;
+      v[q] = hs_zero<T>();
+      if (e < total) {
+        const int a = e % nb, b = b0 + e / nb;
+        const int pr = map[a], pc = map[b];
+        if (pr >= 0 && pc >= 0) {
+          v[q] = S[(long long)b * ch.ld + a];
+          dst[q] = 1;
+          // destination offset computed again below (keeps the register count down)
+        }
+      }
+    }
 #pragma unroll
-    for (int b = 0; b < CB; ++b) {
-      const int pc = s_pb[b];
-      if (pc >= 0) P[(long long)pc * pa.ld + pr] = v[b];
+    for (int q = 0; q < CB; ++q) {
+      const int e = e0 + q * 256;
+      if (dst[q] >= 0) {
+        const int a = e % nb, b = b0 + e / nb;
+        P[(long long)map[b] * pa.ld + map[a]] = v[q];
+      }
     }
   }
 }
