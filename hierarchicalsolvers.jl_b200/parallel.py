@@ -200,8 +200,8 @@ class CudaEngine:
             _lib.check(_lib.lib.hs_schur_export(h, node, C.c_void_p(buf.data_ptr()), pad))
         return buf
 
-    def analyze_top(self, A, nd, loc, opts):
-        return self._factor(A, nd, loc, opts, False, False)
+    def analyze_top(self, A, nd, loc, opts, subtree=False):
+        return self._factor(A, nd, loc, opts, subtree, False)
 
     def import_schur(self, h, node, buf, pad):
         _lib.check(_lib.lib.hs_schur_import(h, node, C.c_void_p(buf.data_ptr()), pad))
@@ -234,10 +234,15 @@ class CudaEngine:
 # the distributed factorization object
 # ------------------------------------------------------------------------------------------------
 class DistributedFactor:
-    """Collective: every rank of ``group`` constructs it with the same ``A``/tree and calls ``ldiv`` together."""
+    """Collective: every rank of ``group`` constructs it with the same ``A``/tree and calls ``ldiv`` together.
+
+    ``top="tree"`` (default): the fronts above the cut are mapped onto the ranks like the tree itself — a front is
+    factored by the owner of its left child after the right child's Schur block arrived by point-to-point send
+    (subtree-to-subcube mapping), so fronts of one top level run in parallel on different GPUs.
+    ``top="replicated"``: all Schur blocks are all-gathered and every rank factors all fronts above the cut."""
 
     def __init__(self, A, nd: NestedDissection, nd_loc: NDLoc, opts: Optional[SolverOptions] = None, engine=None,
-                 group=None, **kw):
+                 group=None, top: str = "tree", **kw):
         import torch.distributed as dist
         self.dist = dist
         self.group = group
@@ -245,38 +250,104 @@ class DistributedFactor:
         self.world = dist.get_world_size(group)
         opts = (opts or SolverOptions()).copy(**kw)
         chkopts(opts)
+        self.opts = opts
         self.eng = engine if engine is not None else CudaEngine()
         self.part = part = partition_tree(nd, nd_loc, self.world)
         self.n = A.shape[0]
+        self.mode = top if self.world > 1 else "replicated"
         g = self.rank
+        nbs = [len(b) for b in part.bnd_idx]
+        self.schur_bytes = 0
         # 1. my subtree
         self.h_sub = self.eng.factor_subtree(A, part.sub_nd[g], part.sub_loc[g], opts)
-        # 2. exchange the subtree-root Schur complements (concatenation — boundaries are disjoint)
-        nbs = [len(b) for b in part.bnd_idx]
-        self.pad = pad = max(max(nbs), 1)
-        mine = self.eng.export_schur(self.h_sub, part.sub_nd[g].root, nbs[g], pad)
-        self.schur = [self.eng.torch.empty_like(mine) for _ in range(self.world)]
-        dist.all_gather(self.schur, mine, group=group)
-        self.schur_bytes = int(sum(nb * nb for nb in nbs) * mine.element_size())
-        # 3. the fronts above the cut, redundantly on every rank
-        self.h_top = self.eng.analyze_top(A, part.top_nd, part.top_loc, opts)
-        for r in range(self.world):
-            if nbs[r]:
-                self.eng.import_schur(self.h_top, part.top_leaf[r], self.schur[r], pad)
-        self.eng.numeric(self.h_top)
+        if self.mode == "replicated":
+            # 2. exchange the subtree-root Schur complements (concatenation — boundaries are disjoint)
+            self.pad = pad = max(max(nbs), 1)
+            mine = self.eng.export_schur(self.h_sub, part.sub_nd[g].root, nbs[g], pad)
+            self.schur = [self.eng.torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(self.schur, mine, group=group)
+            self.schur_bytes = int(sum(nb * nb for nb in nbs) * mine.element_size())
+            # 3. the fronts above the cut, redundantly on every rank
+            self.h_top = self.eng.analyze_top(A, part.top_nd, part.top_loc, opts)
+            for r in range(self.world):
+                if nbs[r]:
+                    self.eng.import_schur(self.h_top, part.top_leaf[r], self.schur[r], pad)
+            self.eng.numeric(self.h_top)
+            own_idx = [i for i in part.int_idx]
+            own_idx[0] = np.concatenate([own_idx[0], part.top_nd.int_idx])   # rank 0 speaks for the replicated top
+        else:
+            self._build_tree_top(A, opts)
+            own_idx = [np.concatenate([part.int_idx[r]] + [st["int"] for st in self.steps if st["owner"] == r])
+                       for r in range(self.world)]
         self._bidx = [self.eng.index(b) for b in part.bnd_idx]
-        self._iidx = [self.eng.index(i) for i in part.int_idx]
-        self._ipad = max(max(len(i) for i in part.int_idx), 1)
+        self._oidx = [self.eng.index(i) for i in own_idx]
+        self._opad = max(max(len(i) for i in own_idx), 1)
+
+    # -- fronts above the cut, one owner each ------------------------------------------------------------------
+    def _build_tree_top(self, A, opts):
+        part, tn, tl = self.part, self.part.top_nd, self.part.top_loc
+        owner = {leaf: r for r, leaf in enumerate(part.top_leaf)}
+        self.steps = []
+        self.S = {}
+        nbs = [len(b) for b in part.bnd_idx]
+        self.S[part.top_leaf[self.rank]] = self.eng.export_schur(self.h_sub, part.sub_nd[self.rank].root, nbs[self.rank],
+                                                                 max(nbs[self.rank], 1))
+        for t in range(tn.nnodes):          # post-order: children first
+            c1, c2 = int(tn.left[t]), int(tn.right[t])
+            if c1 < 0:
+                continue
+            o, src = owner[c1], owner[c2]
+            owner[t] = o
+            nodes = np.array([c1, c2, t], dtype=np.int64)
+            nd3, loc3, _ = _slice_tree(tn, tl, nodes, {c1, c2})
+            st = dict(t=t, c1=c1, c2=c2, owner=o, src=src, root=(t == tn.nnodes - 1), nd=nd3, loc=loc3,
+                      nb1=len(tn.node(c1).bnd), nb2=len(tn.node(c2).bnd), nbt=len(tn.node(t).bnd),
+                      int=tn.node(t).int.copy(), b2=self.eng.index(tn.node(c2).bnd), h=None)
+            self.steps.append(st)
+        for st in self.steps:
+            self._factor_step(A, st, first=True)
+
+    def _factor_step(self, A, st, first):
+        dist, eng, r = self.dist, self.eng, self.rank
+        o, src, c1, c2, t = st["owner"], st["src"], st["c1"], st["c2"], st["t"]
+        n2 = max(st["nb2"], 1)
+        if r == src and src != o:
+            dist.send(self.S[c2], dst=o, group=self.group)
+        if r == o:
+            if src != o:
+                if first:
+                    self.S[c2] = eng.torch.empty((n2, n2), dtype=self.S[c1].dtype, device=self.S[c1].device)
+                dist.recv(self.S[c2], src=src, group=self.group)
+                self.schur_bytes += int(st["nb2"] ** 2 * self.S[c2].element_size())
+            if first:
+                st["h"] = eng.analyze_top(A, st["nd"], st["loc"], self.opts, subtree=not st["root"])
+                if st["nb1"]:
+                    eng.import_schur(st["h"], 0, self.S[c1], max(st["nb1"], 1))
+                if st["nb2"]:
+                    eng.import_schur(st["h"], 1, self.S[c2], n2)
+            eng.numeric(st["h"])
+            if not st["root"]:
+                self.S[t] = eng.export_schur(st["h"], 2, st["nbt"], max(st["nbt"], 1))
 
     def refactor(self):
-        """Numeric phase again on the stored values (what a timed benchmark step repeats): local subtree, Schur
-        all-gather, fronts above the cut."""
+        """Numeric phase again on the stored values (what a timed benchmark step repeats)."""
         g = self.rank
         nbs = [len(b) for b in self.part.bnd_idx]
         self.eng.numeric(self.h_sub)
-        mine = self.eng.export_schur(self.h_sub, self.part.sub_nd[g].root, nbs[g], self.pad)
-        self.dist.all_gather(self.schur, mine, group=self.group)
-        self.eng.numeric(self.h_top)
+        if self.mode == "replicated":
+            mine = self.eng.export_schur(self.h_sub, self.part.sub_nd[g].root, nbs[g], self.pad)
+            self.dist.all_gather(self.schur, mine, group=self.group)
+            self.eng.numeric(self.h_top)
+            return
+        leaf = self.part.top_leaf[g]
+        self.S[leaf].copy_(self.eng.export_schur(self.h_sub, self.part.sub_nd[g].root, nbs[g], max(nbs[g], 1)))
+        self.schur_bytes = 0
+        for st in self.steps:
+            t_old = self.S.get(st["t"])
+            self._factor_step(None, st, first=False)
+            if t_old is not None and self.rank == st["owner"] and not st["root"]:
+                t_old.copy_(self.S[st["t"]])      # keep the buffer the parent front imported from
+                self.S[st["t"]] = t_old
 
     def _allgather_segments(self, x, idx_list, pad):
         torch = self.eng.torch
@@ -291,13 +362,34 @@ class DistributedFactor:
             if r != self.rank and k:
                 x[idx_list[r]] = parts[r][:k]
 
+    def _p2p_segment(self, x, idx, src, dst):
+        """x[idx] travels from rank src to rank dst (no-op for everybody else)."""
+        if src == dst or idx.shape[0] == 0:
+            return
+        if self.rank == src:
+            self.dist.send(x[idx].contiguous(), dst=dst, group=self.group)
+        elif self.rank == dst:
+            buf = self.eng.zeros(idx.shape[0])
+            self.dist.recv(buf, src=src, group=self.group)
+            x[idx] = buf
+
     def ldiv_device(self, x):
         """In place on a replicated device vector (every rank passes the same values)."""
         self.eng.sweep(self.h_sub, x, 1)                       # forward inside my subtree, updates x[bnd of my root]
-        self._allgather_segments(x, self._bidx, self.pad)      # everyone learns every subtree-root boundary segment
-        self.eng.sweep(self.h_top, x, 3)                       # fronts above the cut (replicated)
+        if self.mode == "replicated":
+            self._allgather_segments(x, self._bidx, max(max(len(b) for b in self.part.bnd_idx), 1))
+            self.eng.sweep(self.h_top, x, 3)                   # fronts above the cut (replicated)
+        else:
+            for st in self.steps:                              # up the tree: right child's boundary goes to the owner
+                self._p2p_segment(x, st["b2"], st["src"], st["owner"])
+                if self.rank == st["owner"]:
+                    self.eng.sweep(st["h"], x, 3 if st["root"] else 1)
+            for st in reversed(self.steps):                    # down the tree
+                if self.rank == st["owner"] and not st["root"]:
+                    self.eng.sweep(st["h"], x, 2)
+                self._p2p_segment(x, st["b2"], st["owner"], st["src"])
         self.eng.sweep(self.h_sub, x, 2)                       # backward inside my subtree
-        self._allgather_segments(x, self._iidx, self._ipad)    # everyone gets every subtree's interior solution
+        self._allgather_segments(x, self._oidx, self._opad)    # everyone gets every owner's part of the solution
         return x
 
     def ldiv(self, b: np.ndarray) -> np.ndarray:

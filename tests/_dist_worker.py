@@ -33,7 +33,7 @@ class OracleEngine:
     def factor_subtree(self, A, nd, loc, opts):
         import scipy.sparse as sp
         a, b = to_oracle_tree(self.orc, nd, loc)
-        return {"F": self.orc._factor(sp.csr_matrix(A), a, b, 1), "top": False}
+        return {"F": self.orc._factor(sp.csr_matrix(A), a, b, 1), "top": False, "A": sp.csr_matrix(A), "a": a, "b": b}
 
     def export_schur(self, h, node, nb, pad):
         F = h["F"]
@@ -44,14 +44,17 @@ class OracleEngine:
         buf[:nb, :nb] = self.torch.from_numpy(S.T.copy())  # column-major block
         return buf
 
-    def analyze_top(self, A, nd, loc, opts):
+    def analyze_top(self, A, nd, loc, opts, subtree=False):
         import scipy.sparse as sp
-        return {"A": sp.csr_matrix(A), "nd": nd, "loc": loc, "ext": {}, "top": True}
+        return {"A": sp.csr_matrix(A), "nd": nd, "loc": loc, "ext": {}, "top": True, "subtree": subtree}
 
     def import_schur(self, h, node, buf, pad):
         h["ext"][node] = buf
 
     def numeric(self, h):
+        if not h["top"]:
+            h["F"] = self.orc._factor(h["A"], h["a"], h["b"], 1)
+            return
         orc, nd, loc = self.orc, h["nd"], h["loc"]
 
         def build(k):
@@ -87,7 +90,7 @@ class OracleEngine:
         if which & 1:
             orc._lsolve(F, v)
             orc._dsolve(F, v)
-        if which == 3 and len(F.bnd):
+        if which == 3 and len(F.bnd) and not h.get("subtree", False) and h["top"]:
             v[F.bnd - 1] = orc._solve(F.S, v[F.bnd - 1])
         if which & 2:
             orc._rsolve_tree(F, v)
@@ -116,8 +119,12 @@ def main():
         eng = OracleEngine()
     prob = hs.grid_problem((grid, grid), kind, nmax=40)
     Ap, nd, nd_loc, perm = hs.prepare(prob.A, prob.elim_tree)
-    DF = DistributedFactor(Ap, nd, nd_loc, engine=eng, swlevel=0)
+    mode = sys.argv[7] if len(sys.argv) > 7 else "tree"
+    DF = DistributedFactor(Ap, nd, nd_loc, engine=eng, swlevel=0, top=mode)
     x = DF.ldiv(prob.b)
+    DF.refactor()
+    x2 = DF.ldiv(prob.b)
+    assert np.array_equal(x, x2), "refactor changed the solution"
     res = np.linalg.norm(Ap @ x - prob.b) / np.linalg.norm(prob.b)
     # every rank must hold the same, correct solution
     import scipy.sparse.linalg as spla

@@ -20,9 +20,9 @@ def _free_port():
     return str(p)
 
 
-def _run_ranks(backend, world, grid, kind, timeout=600):
+def _run_ranks(backend, world, grid, kind, mode="tree", timeout=600):
     port = _free_port()
-    procs = [subprocess.Popen([sys.executable, WORKER, backend, str(r), str(world), port, str(grid), kind],
+    procs = [subprocess.Popen([sys.executable, WORKER, backend, str(r), str(world), port, str(grid), kind, mode],
                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(world)]
     outs = []
     for p in procs:
@@ -70,9 +70,9 @@ def test_partition_tree_invariants(hs, nparts):
         assert len(set(lv[part.cut])) == 1
 
 
-@pytest.mark.parametrize("world", [2, 4])
-def test_gloo_distributed_matches_direct_solve(world):
-    outs = _run_ranks("gloo", world, 33, "poisson")
+@pytest.mark.parametrize("world,mode", [(2, "tree"), (4, "tree"), (3, "tree"), (4, "replicated")])
+def test_gloo_distributed_matches_direct_solve(world, mode):
+    outs = _run_ranks("gloo", world, 33, "poisson", mode)
     assert all("same=True" in o for _, o in outs)
 
 
