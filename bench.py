@@ -205,12 +205,11 @@ def run_distributed(args, hs, torch, world, rank, local_rank, Ap, nd, nd_loc, b,
     hs._lib.check(lib.hs_set_profile(eng.ctx, 1))
     DF.refactor()
     hs._lib.check(lib.hs_set_profile(eng.ctx, 0))
-    st_sub, st_top = eng.stats(DF.h_sub), eng.stats(DF.h_top)
-    stp = dict(st_top)
-    for k in ("gemm_flops", "ms_gemm", "gemm_launches", "ms_assemble", "ms_small", "ms_panel", "ms_trsm", "ms_solve_prep"):
-        stp[k] = st_sub[k] + st_top[k]
-    stp["solve_bytes"] = st_sub["solve_bytes"] + st_top["solve_bytes"]
-    stp["front_bytes"] = st_sub["front_bytes"] + st_top["front_bytes"]
+    sts = [eng.stats(h) for h in DF.local_handles()]
+    stp = dict(sts[0])
+    for k in ("gemm_flops", "ms_gemm", "gemm_launches", "ms_assemble", "ms_small", "ms_panel", "ms_trsm", "ms_solve_prep",
+              "solve_bytes", "front_bytes"):
+        stp[k] = sum(st[k] for st in sts)
     peak, peak_src = fp64_peak(b.dtype == np.complex128)
     e2e = None
     if not args.no_e2e:
@@ -228,7 +227,7 @@ def run_distributed(args, hs, torch, world, rank, local_rank, Ap, nd, nd_loc, b,
     return {"ms_step": float(t[0].item()), "fac_ms": float(t[1].item()), "iters": out["iters"], "resid": resid,
             "roofline": gemm_roofline(stp, peak, peak_src), "e2e": e2e, "clocks": clocks,
             "launches": int(lc1.value - lc0.value) // max(args.steps, 1), "stats": stp, "t_first": t_first,
-            "parallelism": {"scheme": "subtree-per-GPU; Schur blocks of the subtree roots all-gathered (NCCL); top fronts and GMRES replicated",
+            "parallelism": {"scheme": "subtree-per-GPU; fronts above the cut owned by the left child's rank, Schur blocks sent point-to-point (NCCL); GMRES replicated", "top_mode": DF.mode,
                             "cut_nodes": [int(c) for c in DF.part.cut], "schur_bytes_allgathered": DF.schur_bytes,
                             "top_flops_share": float(1.0 - sum(float(np.sum(_ff(sn))) for sn in DF.part.sub_nd) / float(np.sum(DF.part.work)))}}
 

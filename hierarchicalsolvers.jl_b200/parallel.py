@@ -397,6 +397,12 @@ class DistributedFactor:
         self.ldiv_device(x)
         return self.eng.to_host(x)
 
+    def local_handles(self):
+        """Factorization handles this rank holds: its subtree and the fronts above the cut it owns."""
+        if self.mode == "replicated":
+            return [self.h_sub, self.h_top]
+        return [self.h_sub] + [st["h"] for st in self.steps if st["owner"] == self.rank]
+
 
 def gmres_replicated(A_t, b, precond, reltol=1e-9, restart=30, maxiter=30):
     """Right-preconditioned restarted GMRES (test/rungmres.jl:47 semantics) on device tensors, run identically on every
