@@ -352,6 +352,56 @@ __device__ __forceinline__ T diag_cta(const T* __restrict__ Mrows, long long ld,
   return y;
 }
 
+// Rectangular part of a large front as ONE streamed mat-vec over the whole GPU (it holds 2/3 of the front's bytes and
+// has no dependency chain, so it does not belong inside the block-step loop of the cluster kernels):
+//   FWD:  x[bnd] −= L21·t,            t = x[int] after the triangular solve         (rows ni..n, columns 0..ni)
+//   BWD:  work[0:ni] = x[int] − U12·x[bnd]                                            (rows 0..ni, columns ni..n)
+// One CTA per (front, 32-row tile, rhs): lane = row, the 8 warps split the columns, partial sums meet in shared memory.
+constexpr int VB = 2048;  // vector entries staged in shared memory per pass
+template <typename T, bool FWD>
+__global__ void __launch_bounds__(NTH) k_gemv_rect(const Front* __restrict__ fronts, const T* __restrict__ pool,
+                                                    const int* __restrict__ gidx, T* __restrict__ x, long long ldx,
+                                                    T* __restrict__ work, long long wstride, long long ioff0, int f0) {
+  const Front fr = fronts[f0 + blockIdx.x];
+  const int n = fr.n, ni = fr.ni, nb = n - ni;
+  const int nrows = FWD ? nb : ni, ncols = FWD ? ni : nb;
+  const int r0 = blockIdx.y * 32;
+  if (r0 >= nrows) return;
+  const T* M = pool + fr.off + (FWD ? (long long)ni : (long long)ni * fr.ld);  // first row / first column of the block
+  const long long ld = fr.ld;
+  T* xr = x + (long long)blockIdx.z * ldx;
+  T* w = work + (long long)blockIdx.z * wstride + (fr.ioff - ioff0);
+  const int* gi = gidx + fr.ioff;
+  const int* gv = gi + (FWD ? 0 : ni);   // indices of the vector entries
+  const int* gr = gi + (FWD ? ni : 0);   // indices of the rows
+  __shared__ T sv[VB];
+  __shared__ T red[NW][32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r = r0 + lane;
+  const bool ok = r < nrows;
+  T acc = hs_zero<T>();
+  for (int c0 = 0; c0 < ncols; c0 += VB) {
+    const int cw = min(VB, ncols - c0);
+    __syncthreads();
+    for (int k = tid; k < cw; k += NTH) sv[k] = xr[gv[c0 + k]];
+    __syncthreads();
+    if (ok) {
+      const T* p = M + (long long)c0 * ld + r;
+#pragma unroll 16
+      for (int k = warp; k < cw; k += NW) acc = hs_fma(acc, p[(long long)k * ld], sv[k]);
+    }
+  }
+  red[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && ok) {
+    T sum = hs_zero<T>();
+#pragma unroll
+    for (int q = 0; q < NW; ++q) sum = hs_add(sum, red[q][lane]);
+    const int g = gr[r];
+    if (FWD) xr[g] = hs_sub(xr[g], sum); else w[r] = hs_sub(xr[g], sum);
+  }
+}
+
 template <typename T, bool CL>
 __global__ void __launch_bounds__(NTH) k_sv_big_fwd(const Front* __restrict__ fronts, const T* __restrict__ pool,
                                                      const int* __restrict__ gidx, const int* __restrict__ rperm,
@@ -380,8 +430,8 @@ __global__ void __launch_bounds__(NTH) k_sv_big_fwd(const Front* __restrict__ fr
   const int nworkers = C > 1 ? NW * (C - 1) : NW;
   const int me = C > 1 ? (crank - 1) * NW + warp : warp;
   const bool worker = C == 1 || crank > 0;
-  // gather v = [P·x_int; x_bnd]
-  for (int r = crank * NTH + tid; r < n; r += NTH * C) stcg(&w[r], xr[gi[r < ni ? rp[r] : r]]);
+  // gather v = P·x_int (the boundary rows are updated afterwards by k_gemv_rect)
+  for (int r = crank * NTH + tid; r < ni; r += NTH * C) stcg(&w[r], xr[gi[rp[r]]]);
   sync();
   const int B = (ni + DB - 1) / DB;
   if (crank == 0) {  // v_0 = L00⁻¹·v_0
@@ -402,7 +452,7 @@ __global__ void __launch_bounds__(NTH) k_sv_big_fwd(const Front* __restrict__ fr
     if (!last) {
       if (crank == 0) {
         const int nb1 = min(b1 + DB, ni), dn = nb1 - b1;
-        const int cnt = min(64, n - b1);
+        const int cnt = dn;
         const T win = tid < cnt ? ldcg(&w[b1 + tid]) : hs_zero<T>();
         const T y = diag_cta<T>(Fb + b1, ld, db, svb, win, cnt, F + (long long)b1 * ld + b1, dn, 1, sT, spart, su);
         if (tid < cnt) { stcg(&w[b1 + tid], y); if (tid < dn) xr[gi[b1 + tid]] = y; }
@@ -410,10 +460,10 @@ __global__ void __launch_bounds__(NTH) k_sv_big_fwd(const Front* __restrict__ fr
     }
     if (worker) {
       constexpr int TR = TileRows<T>::N;
-      const int rstart = b1 + (last ? 0 : 64);
-      const int ntiles = (n - rstart + TR - 1) / TR;
+      const int rstart = b1 + 64;  // rows of the pivot block below the next diagonal block
+      const int ntiles = last ? 0 : (ni - rstart + TR - 1) / TR;
       for (int t = me; t < ntiles; t += nworkers)
-        tile_update<T>(Fb, ld, db, svb, rstart + t * TR, n, al, w, xr, gi, last, nullptr);
+        tile_update<T>(Fb, ld, db, svb, rstart + t * TR, ni, al, w, xr, gi, false, nullptr);
     }
     if (b + 1 < B) sync();
   }
@@ -446,61 +496,12 @@ __global__ void __launch_bounds__(NTH) k_sv_big_bwd(const Front* __restrict__ fr
   const bool worker = C == 1 || crank > 0;
   const int B = (ni + DB - 1) / DB;
   const int l0 = (B - 1) * DB, dl = ni - l0;
-  // phase 0: t = x_int − U12·x_bnd (boundary values in chunks of 64 through shared memory), then CTA 0 applies the
-  // inverse of the last diagonal block
-  {
-    const int ntop = l0 / 32;
-    T acc_d = hs_zero<T>();           // CTA 0: thread tid < dl accumulates row l0 + tid … via k-split partials
-    T accw[4];                        // worker: up to 4 tiles per warp kept in registers, more go through w
-#pragma unroll
-    for (int q = 0; q < 4; ++q) accw[q] = hs_zero<T>();
-    const int tiles_mine = worker ? (ntop - me + nworkers - 1) / nworkers : 0;
-    const bool inreg = tiles_mine <= 4;
-    if (worker && !inreg)
-      for (int t = me; t < ntop; t += nworkers) { const int r = t * 32 + lane; stcg(&w[r], xr[gi[r]]); }
-    for (int c0 = 0; c0 < nb; c0 += 64) {
-      const int cw = min(64, nb - c0);
-      __syncthreads();
-      if (tid < 64) svb[tid] = tid < cw ? xr[gi[ni + c0 + tid]] : hs_zero<T>();
-      __syncthreads();
-      const T* Fc = F + (long long)(ni + c0) * ld;
-      if (crank == 0) {  // rows of the last diagonal block: k-split over the warps, reduced at the end
-        T a0 = hs_zero<T>(), a1 = hs_zero<T>();
-        for (int k = warp; k < cw; k += NW) {
-          const T vk = svb[k];
-          if (lane < dl) a0 = hs_fma(a0, Fc[(long long)k * ld + l0 + lane], vk);
-          if (lane + 32 < dl) a1 = hs_fma(a1, Fc[(long long)k * ld + l0 + lane + 32], vk);
-        }
-        spart[warp][lane] = a0; spart[warp][lane + 32] = a1;
-        __syncthreads();
-        if (tid < 64) {
-#pragma unroll
-          for (int wv = 0; wv < NW; ++wv) acc_d = hs_add(acc_d, spart[wv][tid]);
-        }
-      }
-      if (worker) {
-        int q = 0;
-        for (int t = me; t < ntop; t += nworkers, ++q) {
-          const int r = t * 32 + lane;
-          const T a = row_dot<T>(Fc + r, ld, cw, svb, true);
-          if (inreg) { if (q < 4) accw[q] = hs_add(accw[q], a); }
-          else stcg(&w[r], hs_sub(ldcg(&w[r]), a));
-        }
-      }
-    }
-    if (worker && inreg) {
-      int q = 0;
-      for (int t = me; t < ntop; t += nworkers, ++q) {
-        const int r = t * 32 + lane;
-        if (q < 4) stcg(&w[r], hs_sub(xr[gi[r]], accw[q]));
-      }
-    }
-    if (crank == 0) {
-      __syncthreads();
-      const T win = tid < dl ? hs_sub(xr[gi[l0 + tid]], acc_d) : hs_zero<T>();
-      const T y = diag_cta<T>(F, ld, 0, svb, win, dl, F + (long long)l0 * ld + l0, dl, 2, sT, spart, su);
-      if (tid < dl) { stcg(&w[l0 + tid], y); xr[gi[l0 + tid]] = y; }
-    }
+  // phase 0: work[0:ni] already holds t = x_int − U12·x_bnd (k_gemv_rect); CTA 0 applies the inverse of the last
+  // diagonal block
+  if (crank == 0) {
+    const T win = tid < dl ? ldcg(&w[l0 + tid]) : hs_zero<T>();
+    const T y = diag_cta<T>(F, ld, 0, svb, win, dl, F + (long long)l0 * ld + l0, dl, 2, sT, spart, su);
+    if (tid < dl) { stcg(&w[l0 + tid], y); xr[gi[l0 + tid]] = y; }
   }
   for (int b = B - 1; b >= 1; --b) {
     sync();
@@ -578,7 +579,14 @@ template <typename T> void run_impl(hs_fac* f, int64_t nrhs, void* xv, int which
   for (size_t li = 0; (which & 1) && li < f->levels.size(); ++li) {  // post-order
     const Level& L = f->levels[li];
     const int nf = L.f1 - L.f0, nbig = nbig_of(L);
-    if (nbig > 0) launch_big<T, true>(f, L, nbig, nrhs, x);
+    if (nbig > 0) {
+      launch_big<T, true>(f, L, nbig, nrhs, x);
+      if (L.max_nb > 0) {
+        dim3 g(nbig, (L.max_nb + 31) / 32, (unsigned)nrhs);
+        k_gemv_rect<T, true><<<g, NTH, 0, st>>>(f->d_fronts, pool, f->d_gidx, x, f->n, (T*)f->d_work, f->max_level_idx, L.ioff0, L.f0);
+        ++s.launches_solve;
+      }
+    }
     if (nf - nbig > 0) {
       dim3 g(nf - nbig, (unsigned)nrhs);
       k_sv_small_fwd<T><<<g, NTH, 0, st>>>(f->d_fronts, pool, f->d_gidx, f->d_rperm, x, f->n, L.f0 + nbig);
@@ -588,7 +596,12 @@ template <typename T> void run_impl(hs_fac* f, int64_t nrhs, void* xv, int which
   for (size_t li = f->levels.size(); (which & 2) && li-- > 0;) {  // pre-order
     const Level& L = f->levels[li];
     const int nf = L.f1 - L.f0, nbig = nbig_of(L);
-    if (nbig > 0) launch_big<T, false>(f, L, nbig, nrhs, x);
+    if (nbig > 0) {
+      dim3 g(nbig, (L.max_ni + 31) / 32, (unsigned)nrhs);
+      k_gemv_rect<T, false><<<g, NTH, 0, st>>>(f->d_fronts, pool, f->d_gidx, x, f->n, (T*)f->d_work, f->max_level_idx, L.ioff0, L.f0);
+      ++s.launches_solve;
+      launch_big<T, false>(f, L, nbig, nrhs, x);
+    }
     if (nf - nbig > 0) {
       dim3 g(nf - nbig, (unsigned)nrhs);
       const size_t sm = (size_t)std::max(L.max_nb, 1) * sizeof(T);
