@@ -151,6 +151,28 @@ def gemm_roofline(stp, peak, peak_src):
             "phase_ms": {k: stp[k] for k in ("ms_assemble", "ms_small", "ms_panel", "ms_trsm", "ms_gemm", "ms_solve_prep")}}
 
 
+def hbm_rooflines(stp, solve_ms):
+    """The two HBM-bound phases north_star names: extend-add (2·esz·Σnb² bytes) and the tree solve
+    (esz·Σ(ni²+2·ni·nb) bytes per right-hand side), against the measured copy bandwidth of MEASURED_PEAKS.json."""
+    peak = 6456.2
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+        src = "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        src = "fallback 6456.2 GB/s (earlier MEASURED_PEAKS.json of this pool)"
+    out = []
+    if stp.get("ms_extend_add", 0) > 0:
+        a = stp["extadd_bytes"] / (stp["ms_extend_add"] * 1e-3) / 1e9
+        out.append({"kernel": "k_extend_add", "bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak,
+                    "traffic": None, "peak_source": src, "bytes": stp["extadd_bytes"], "ms": stp["ms_extend_add"]})
+    if solve_ms and solve_ms > 0:
+        a = stp["solve_bytes"] / (solve_ms * 1e-3) / 1e9
+        out.append({"kernel": "tree solve (k_sv_small_*, k_sv_big_*, k_gemv_rect), one right-hand side", "bound": "hbm", "achieved": a,
+                    "peak": peak, "unit": "GB/s", "frac": a / peak, "traffic": None, "peak_source": src, "bytes": stp["solve_bytes"],
+                    "ms": solve_ms})
+    return out
+
+
 def h2d_bytes(Ap, nd, nd_loc, b):
     tree_bytes = 8 * (2 * nd.nnodes + 4 * (nd.nnodes + 1) + len(nd.int_idx) + len(nd.bnd_idx) + len(nd_loc.iloc_idx) + len(nd_loc.bloc_idx))
     a_bytes = Ap.indptr.size * 8 + Ap.indices.size * 8 + Ap.data.nbytes
@@ -300,6 +322,7 @@ def main():
     lib = hs._lib.lib
     tdt = torch.complex128 if cx else torch.float64
     peak, peak_src = fp64_peak(cx)
+    roofline_hbm = None
     if world > 1:
         line_extra = run_distributed(args, hs, torch, world, rank, local_rank, Ap, nd, nd_loc, b, flops, tdt)
         ms_step, fac_ms_mean, gm_iters, resid = (line_extra.pop(k) for k in ("ms_step", "fac_ms", "iters", "resid"))
@@ -358,6 +381,8 @@ def main():
         hs._lib.check(lib.hs_set_profile(ctx, 0))
         stp = F.stats()
         roofline = gemm_roofline(stp, peak, peak_src)
+        xs = hs.ldiv(F, b)          # one preconditioner application, event-timed inside the library
+        roofline_hbm = hbm_rooflines(stp, F.stats()["ms_solve_total"])
         # ---- end to end through the public API with host buffers ------------------------------------
         e2e = None
         if not args.no_e2e:
@@ -403,7 +428,7 @@ def main():
             "factor_frac_of_fp64_peak": flops / (fac_ms_mean * 1e-3) / 1e12 / peak,
             "solve_bytes_per_rhs": stp["solve_bytes"], "front_bytes": stp["front_bytes"],
             "setup_s": {"generate+symfact": t_setup, "first_factor_incl_plan": t_first},
-            "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu_baseline,
             "clocks": clocks}
     print(json.dumps(line), flush=True)
     if world > 1:

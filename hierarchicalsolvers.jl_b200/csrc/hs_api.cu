@@ -270,7 +270,7 @@ template <typename T> static void numeric(hs_fac* f) {
   cudaStream_t st = f->ctx->stream;
   T* pool = (T*)f->pool;
   hs_stats_t& s = f->stats;
-  s.ms_assemble = s.ms_panel = s.ms_trsm = s.ms_gemm = s.ms_solve_prep = s.ms_small = 0;
+  s.ms_assemble = s.ms_panel = s.ms_trsm = s.ms_gemm = s.ms_solve_prep = s.ms_small = s.ms_extend_add = 0;
   s.launches_factor = 0;
   s.gemm_launches = s.panel_launches = 0;
   s.gemm_flops = 0;
@@ -300,6 +300,7 @@ template <typename T> static void numeric(hs_fac* f) {
           // one CTA covers ~4096 elements of a child's Schur block: whole small blocks, column groups of large ones
           const int cols_per_cta = std::max(1, 4096 / Lc.max_nb);
           dim3 g2(Lc.f1 - Lc.f0, (Lc.max_nb + cols_per_cta - 1) / cols_per_cta);
+          PhaseTimer t2(f, &s.ms_extend_add);
           k_extend_add<T, CB><<<g2, 256, 0, st>>>(f->d_fronts, pool, f->d_cmap, Lc.f0, cols_per_cta);
           s.launches_factor += 1;
         }

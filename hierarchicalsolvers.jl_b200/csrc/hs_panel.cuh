@@ -274,8 +274,9 @@ template <typename T> static int choose_width(const hs_fac* f, int max_n, int nf
   const int W0 = PanelW<T>::W0;
   const int maxC = f->ctx->max_cluster;
   // many fronts per level (more CTAs than SMs): throughput matters, not the latency of one front.  A CTA that holds
-  // more rows of a narrower panel avoids the cluster barrier altogether (HS_PANEL_TALL=0 disables).
-  static const bool tall = !(getenv("HS_PANEL_TALL") && atoi(getenv("HS_PANEL_TALL")) == 0);
+  // more rows of a narrower panel avoids the cluster barrier altogether.  Opt-in (HS_PANEL_TALL=1): it shortens the
+  // panel phase by ~8 ms at 2048² but the K = 16/32 in-block updates it implies cost the DMMA phase ~6 ms.
+  static const bool tall = getenv("HS_PANEL_TALL") && atoi(getenv("HS_PANEL_TALL")) != 0;
   if (tall && (long long)nfronts * ((max_n + 255) / 256) > 148 && max_n > 256) {
     for (int W = W0, R = 1; R <= 4 && W >= 8; W >>= 1, R <<= 1)
       if (256 * R >= max_n) return W;

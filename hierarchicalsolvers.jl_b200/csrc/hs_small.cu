@@ -19,8 +19,8 @@
 
 namespace {
 
-template <typename T, int TR, int TC, int RPT, int CPT>
-__global__ void __launch_bounds__(TR* TC) k_front_small(const Front* __restrict__ fronts, T* __restrict__ pool,
+template <typename T, int TR, int TC, int RPT, int CPT, int MINB>
+__global__ void __launch_bounds__(TR* TC, MINB) k_front_small(const Front* __restrict__ fronts, T* __restrict__ pool,
                                                          int* __restrict__ ipiv, int* __restrict__ rperm, int f0,
                                                          int* __restrict__ info) {
   constexpr int NT = TR * TC;
@@ -160,8 +160,8 @@ __global__ void __launch_bounds__(TR* TC) k_front_small(const Front* __restrict_
   }
 }
 
-template <typename T, int TR, int TC, int RPT, int CPT> void launch(hs_fac* f, int f0, int nf) {
-  k_front_small<T, TR, TC, RPT, CPT><<<nf, TR * TC, 0, f->ctx->stream>>>(f->d_fronts, (T*)f->pool, f->d_ipiv, f->d_rperm, f0, f->d_info);
+template <typename T, int TR, int TC, int RPT, int CPT, int MINB = 1> void launch(hs_fac* f, int f0, int nf) {
+  k_front_small<T, TR, TC, RPT, CPT, MINB><<<nf, TR * TC, 0, f->ctx->stream>>>(f->d_fronts, (T*)f->pool, f->d_ipiv, f->d_rperm, f0, f->d_info);
   CUDA_OK(cudaGetLastError());
 }
 
@@ -177,7 +177,8 @@ int hs_small_max_n(hs_dtype dt) {
 void hs_small_factor(hs_fac* f, const Level& L) {
   const int nf = L.f1 - L.f0, n = L.max_n;
   if (f->dtype == HS_F64) {
-    if (n <= 80) launch<double, 16, 8, 5, 10>(f, L.f0, nf);
+    static const int mb = getenv("HS_SMALL_MINB") ? atoi(getenv("HS_SMALL_MINB")) : 3;
+    if (n <= 80) { if (mb >= 4) launch<double, 16, 8, 5, 10, 4>(f, L.f0, nf); else if (mb == 3) launch<double, 16, 8, 5, 10, 3>(f, L.f0, nf); else launch<double, 16, 8, 5, 10, 1>(f, L.f0, nf); }
     else if (n <= 96) launch<double, 16, 16, 6, 6>(f, L.f0, nf);
     else launch<double, 16, 16, 8, 8>(f, L.f0, nf);
   } else {

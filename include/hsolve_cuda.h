@@ -109,6 +109,7 @@ typedef struct {
   int64_t maxrank;
   double gemm_flops;       /* flops issued by the Schur/trailing-update GEMM launches (2·m²·k per step, ×4 complex) */
   int64_t gemm_launches, panel_launches;
+  double ms_extend_add;    /* child Schur blocks → parent fronts (part of ms_assemble) */
   double ms_small;         /* fused small-front kernel (levels whose fronts fit in registers) */
   double ms_solve_prep;    /* in-place inversion of the diagonal blocks of L11/U11 (part of the factor time) */
 } hs_stats_t;
