@@ -229,3 +229,52 @@ def test_single_dense_front(hs, ni, nb, cx):
         assert rel(F.R, R) < TOL and rel(F.L, L) < TOL and rel(F.S, S) < TOL
     x = hs.ldiv(F, prob.b)
     assert rel(A @ x, prob.b) < TOL
+
+
+@pytest.mark.parametrize("ni,nb,cx", [(1, 0, False), (1, 1, True), (0, 5, False), (64, 10, False), (65, 10, False),
+                                      (63, 65, True), (128, 0, False), (129, 0, False), (96, 0, True), (97, 3, True),
+                                      (256, 1, False), (257, 255, False)])
+def test_front_size_thresholds(hs, ni, nb, cx):
+    """Sizes that sit on the switch points of the kernels: fused register kernel (n ≤ 128 f64 / 96 c64), solve block
+    (64), panel width (64 / 32), outer block (256), one CTA vs cluster (256 rows); plus empty interior / boundary."""
+    prob, A = _single_front_problem(hs, ni, nb, cx, seed=ni + 7 * nb)
+    Ap, nd, nd_loc, perm = hs.prepare(prob.A, prob.elim_tree)
+    F = hs.factor(Ap, nd, nd_loc, swlevel=0)
+    x = hs.ldiv(F, prob.b)
+    assert rel(A @ x, prob.b) < TOL
+    if ni and nb:
+        Aii, Aib, Abi, Abb = A[:ni, :ni], A[:ni, ni:], A[ni:, :ni], A[ni:, ni:]
+        R = np.linalg.solve(Aii, Aib)
+        assert rel(F.R, R) < TOL and rel(F.S, Abb - Abi @ R) < TOL and rel(F.D, Aii) < TOL
+    X = hs.ldiv(F, np.stack([prob.b, 2 * prob.b, -prob.b], axis=1))
+    assert rel(X[:, 1], 2 * x) < 1e-12 and rel(X[:, 2], -x) < 1e-12
+
+
+def test_repeated_factor_free_cycles(hs):
+    """Handles are released (no device-memory growth across factor / free cycles)."""
+    import torch
+    prob = hs.grid_problem((129, 129), "poisson")
+    Ap, nd, nd_loc, _ = hs.prepare(prob.A, prob.elim_tree)
+    F = hs.factor(Ap, nd, nd_loc, swlevel=0)
+    del F
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    for _ in range(5):
+        F = hs.factor(Ap, nd, nd_loc, swlevel=0)
+        x = hs.ldiv(F, prob.b)
+        del F
+    torch.cuda.synchronize()
+    free1 = torch.cuda.mem_get_info()[0]
+    assert free0 - free1 < 64 * 2 ** 20
+
+
+def test_gmres_edge_cases(hs):
+    prob = hs.grid_problem((33, 33), "poisson", nmax=40)
+    Ap, nd, nd_loc, _ = hs.prepare(prob.A, prob.elim_tree)
+    F = hs.factor(Ap, nd, nd_loc, swlevel=0)
+    x, h = hs.gmres(Ap, prob.b, Pr=F, maxiter=0, log=True)           # no iterations allowed: x0 = 0 comes back
+    assert h.iters == 0 and not h.isconverged and np.all(x == 0)
+    x, h = hs.gmres(Ap, prob.b, Pr=None, restart=5, maxiter=12, log=True)   # restarts without preconditioner
+    assert h.iters == 12 and len(h.resnorm) == 12
+    x, h = hs.gmres(Ap, np.zeros_like(prob.b), Pr=F, log=True)        # zero right-hand side converges immediately
+    assert h.iters == 0 and np.all(x == 0)
