@@ -248,7 +248,10 @@ template <> struct GemmCfg<cplx> {
   static constexpr int TM = 128, TN = 64, WM = 32, WN = 32, KC = 8, ST = 4, LDA = 130, LDB = 12;
 };
 template <typename T> constexpr int gemm_smem_bytes() {
-  return GemmCfg<T>::ST * (GemmCfg<T>::KC * GemmCfg<T>::LDA + GemmCfg<T>::TN * GemmCfg<T>::LDB) * (int)sizeof(T);
+  // operand pipeline, or the C tile staged for the epilogue, whichever is larger
+  constexpr int pipe = GemmCfg<T>::ST * (GemmCfg<T>::KC * GemmCfg<T>::LDA + GemmCfg<T>::TN * GemmCfg<T>::LDB) * (int)sizeof(T);
+  constexpr int ctile = GemmCfg<T>::TN * (GemmCfg<T>::TM + 2) * (int)sizeof(T);
+  return pipe > ctile ? pipe : ctile;
 }
 
 template <typename T>
@@ -392,20 +395,38 @@ __global__ void __launch_bounds__(256, 1) k_gemm(const Front* __restrict__ front
     }
   }
   cp_async_wait<0>();
-  // epilogue: C -= acc.  All loads of a row group are issued before the first store: written as load-modify-store
-  // per element the compiler has to keep them in program order (the pointers may alias) and the 64 L2 round trips of
-  // a thread serialise — that was half of the kernel time for the K = 64 updates.
+  // epilogue: C -= acc.  The C tile is pulled into the (now idle) pipeline buffers with one burst of cp.async — one
+  // L2/HBM round trip instead of one per row group — then read-modify-written from shared memory.
+  __syncthreads();  // every warp is done with the operand stages
+  constexpr int LDC = TM + 2;  // ≡ 2 (mod 8) words of 8 B: conflict-free for the accumulator fragment layout
+  T* Cs = smem;                // [TN][LDC]
+  if (al) {
+    constexpr int CV = TM / EPV;
+#pragma unroll 4
+    for (int c = tid; c < TN * CV; c += 256) {
+      const int nn = c / CV, m = (c % CV) * EPV;
+      const int left = rhi - (m0 + m);
+      int bytes = 0;
+      if (n0 + nn < chi && left > 0) bytes = left >= EPV ? 16 : (int)sizeof(T);
+      const T* src = bytes ? F + (long long)(n0 + nn) * ld + (m0 + m) : F;
+      cp_async16(Cs + nn * LDC + m, src, bytes);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+  }
 #pragma unroll
   for (int i = 0; i < MI; ++i) {
-    const int r = m0 + wm + i * 8 + g;
+    const int rl = wm + i * 8 + g, r = m0 + rl;
     const bool rok = r >= lo && r < rhi;
     T cv[NI][2];
 #pragma unroll
     for (int j = 0; j < NI; ++j)
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        const int c = n0 + wn + j * 8 + q * 2 + h;
-        cv[j][h] = (rok && c < chi) ? F[(long long)c * ld + r] : hs_zero<T>();
+        const int cl = wn + j * 8 + q * 2 + h, c = n0 + cl;
+        if (al) cv[j][h] = Cs[cl * LDC + rl];
+        else cv[j][h] = (rok && c < chi) ? F[(long long)c * ld + r] : hs_zero<T>();
       }
 #pragma unroll
     for (int j = 0; j < NI; ++j)
