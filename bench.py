@@ -142,10 +142,25 @@ def fp64_peak(complex_):
     return (37.0 if complex_ else 35.5), "fallback: earlier cuBLAS measurement on this pool"
 
 
+def ncu_traffic(kernel, per_launch=True):
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu pass over the default workload
+    (profiles/r01_traffic_2048.json, tools/profile_run.py 2048); None for any other workload."""
+    try:
+        k = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic_2048.json")))["kernels"][kernel]
+        return k["dram_bytes_per_launch"] if per_launch else k["dram_bytes_total"]
+    except Exception:
+        return None
+
+
+DEFAULT_WORKLOAD = True
+
+
 def gemm_roofline(stp, peak, peak_src):
     gemm_tf = stp["gemm_flops"] / (stp["ms_gemm"] * 1e-3) / 1e12 if stp["ms_gemm"] > 0 else 0.0
     return {"kernel": "k_gemm (FP64 DMMA m8n8k4 Schur/trailing update)", "bound": "tensor", "achieved": gemm_tf,
-            "peak": peak, "unit": "TFLOP/s", "frac": gemm_tf / peak, "traffic": None, "peak_source": peak_src,
+            "peak": peak, "unit": "TFLOP/s", "frac": gemm_tf / peak,
+            "traffic": ncu_traffic("k_gemm") if DEFAULT_WORKLOAD else None, "traffic_unit": "bytes per launch (ncu, all launches averaged)",
+            "peak_source": peak_src,
             "launches": stp["gemm_launches"], "flops_per_launch": stp["gemm_flops"] / max(stp["gemm_launches"], 1),
             "ms_per_launch": stp["ms_gemm"] / max(stp["gemm_launches"], 1),
             "phase_ms": {k: stp[k] for k in ("ms_assemble", "ms_small", "ms_panel", "ms_trsm", "ms_gemm", "ms_solve_prep")}}
@@ -164,11 +179,13 @@ def hbm_rooflines(stp, solve_ms):
     if stp.get("ms_extend_add", 0) > 0:
         a = stp["extadd_bytes"] / (stp["ms_extend_add"] * 1e-3) / 1e9
         out.append({"kernel": "k_extend_add", "bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak,
-                    "traffic": None, "peak_source": src, "bytes": stp["extadd_bytes"], "ms": stp["ms_extend_add"]})
+                    "traffic": ncu_traffic("k_extend_add", False) if DEFAULT_WORKLOAD else None, "peak_source": src, "bytes": stp["extadd_bytes"], "ms": stp["ms_extend_add"]})
     if solve_ms and solve_ms > 0:
         a = stp["solve_bytes"] / (solve_ms * 1e-3) / 1e9
         out.append({"kernel": "tree solve (k_sv_small_*, k_sv_big_*, k_gemv_rect), one right-hand side", "bound": "hbm", "achieved": a,
-                    "peak": peak, "unit": "GB/s", "frac": a / peak, "traffic": None, "peak_source": src, "bytes": stp["solve_bytes"],
+                    "peak": peak, "unit": "GB/s", "frac": a / peak,
+                    "traffic": (sum(ncu_traffic(k, False) or 0 for k in ("k_sv_small_fwd", "k_sv_small_bwd", "k_sv_big_fwd", "k_sv_big_bwd", "k_gemv_rect")) or None)
+                    if DEFAULT_WORKLOAD else None, "peak_source": src, "bytes": stp["solve_bytes"],
                     "ms": solve_ms})
     return out
 
@@ -262,6 +279,8 @@ def _ff(nd):
 
 def main():
     args = parse_args()
+    global DEFAULT_WORKLOAD
+    DEFAULT_WORKLOAD = args.grid == 2048 and args.kind == "poisson" and args.nmax == 100
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
