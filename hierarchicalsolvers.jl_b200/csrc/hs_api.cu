@@ -175,7 +175,7 @@ template <typename T> static void factor_level(hs_fac* f, const Level& L) {
     if (nact <= 0 || mrows <= 0 || mcols <= 0) return;
     PhaseTimer t(f, &f->stats.ms_gemm);
     dim3 grid(nact, (mrows + Cfg::TM - 1) / Cfg::TM + 1, (mcols + Cfg::TN - 1) / Cfg::TN);
-    k_gemm<T><<<grid, 256, smem_gemm, stream>>>(f->d_fronts, (T*)f->pool, L.f0, J0, j0, NB, W, mode);
+    k_gemm<T><<<grid, gemm_threads<T>(), smem_gemm, stream>>>(f->d_fronts, (T*)f->pool, L.f0, J0, j0, NB, W, mode);
     CUDA_OK(cudaGetLastError());
     ++f->stats.gemm_launches;
     ++f->stats.launches_factor;

@@ -242,11 +242,14 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 
 template <typename T> struct GemmCfg;
 template <> struct GemmCfg<double> {
-  static constexpr int TM = 128, TN = 128, WM = 64, WN = 32, KC = 16, ST = 4, LDA = 132, LDB = 20;
+  // 128×64 tile, 4 warps of 64×32: two CTAs fit on an SM (108 KB of shared memory, ~220 registers × 128 threads each),
+  // so one CTA's prologue/epilogue/barrier stalls are covered by the other's MMAs
+  static constexpr int TM = 128, TN = 64, WM = 64, WN = 32, KC = 16, ST = 4, LDA = 132, LDB = 20;
 };
 template <> struct GemmCfg<cplx> {
-  static constexpr int TM = 128, TN = 64, WM = 32, WN = 32, KC = 8, ST = 4, LDA = 130, LDB = 12;
+  static constexpr int TM = 64, TN = 64, WM = 32, WN = 32, KC = 8, ST = 4, LDA = 66, LDB = 12;
 };
+template <typename T> constexpr int gemm_threads() { return (GemmCfg<T>::TM / GemmCfg<T>::WM) * (GemmCfg<T>::TN / GemmCfg<T>::WN) * 32; }
 template <typename T> constexpr int gemm_smem_bytes() {
   // operand pipeline, or the C tile staged for the epilogue, whichever is larger
   constexpr int pipe = GemmCfg<T>::ST * (GemmCfg<T>::KC * GemmCfg<T>::LDA + GemmCfg<T>::TN * GemmCfg<T>::LDB) * (int)sizeof(T);
@@ -255,7 +258,7 @@ template <typename T> constexpr int gemm_smem_bytes() {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256, 1) k_gemm(const Front* __restrict__ fronts, T* __restrict__ pool, int f0, int J0,
+__global__ void __launch_bounds__(GemmCfg<T>::TM / GemmCfg<T>::WM * GemmCfg<T>::TN / GemmCfg<T>::WN * 32) k_gemm(const Front* __restrict__ fronts, T* __restrict__ pool, int f0, int J0,
                                                   int j0, int NB, int W, int mode) {
   using Cfg = GemmCfg<T>;
   constexpr int TM = Cfg::TM, TN = Cfg::TN, WM = Cfg::WM, WN = Cfg::WN, KC = Cfg::KC, ST = Cfg::ST, LDA = Cfg::LDA,
@@ -263,6 +266,7 @@ __global__ void __launch_bounds__(256, 1) k_gemm(const Front* __restrict__ front
   constexpr bool CX = hs_traits<T>::is_complex;
   constexpr int EPV = 16 / (int)sizeof(T);  // elements per 16-byte vector: 2 (f64) or 1 (c64)
   constexpr int MI = WM / 8, NI = WN / 8;
+  constexpr int NT = (TM / WM) * (TN / WN) * 32;  // threads per CTA
   const Front fr = fronts[f0 + blockIdx.x];
   const int n = fr.n, ni = fr.ni;
   int kbase, kcount, lo, rhi, clo, chi;  // C = rows [lo, rhi) × cols [clo, chi)
@@ -298,7 +302,7 @@ __global__ void __launch_bounds__(256, 1) k_gemm(const Front* __restrict__ front
   // warm L2 with the C tile: the epilogue's read-modify-write then does not wait on HBM
   {
     const int lines_per_col = (TM * (int)sizeof(T)) / 128;
-    for (int e = tid; e < TN * lines_per_col; e += 256) {
+    for (int e = tid; e < TN * lines_per_col; e += NT) {
       const int c = n0 + e / lines_per_col, r = m0 + (e % lines_per_col) * (128 / (int)sizeof(T));
       if (c < chi && r < rhi) asm volatile("prefetch.global.L2 [%0];" ::"l"(F + (long long)c * ld + r));
     }
@@ -310,12 +314,12 @@ __global__ void __launch_bounds__(256, 1) k_gemm(const Front* __restrict__ front
     const int krem = kcount - chunk * KC;
     const int kg = kbase + chunk * KC;
     if (EPV > 1 && !al) {
-      for (int c = tid; c < KC * TM; c += 256) {
+      for (int c = tid; c < KC * TM; c += NT) {
         const int k = c / TM, m = c % TM;
         const bool ok = k < krem && m0 + m < rhi;
         cp_async8(As + k * LDA + m, ok ? F + (long long)(kg + k) * ld + (m0 + m) : F, ok ? 8 : 0);
       }
-      for (int c = tid; c < TN * KC; c += 256) {
+      for (int c = tid; c < TN * KC; c += NT) {
         const int nn = c / KC, k = c % KC;
         const bool ok = n0 + nn < chi && k < krem;
         cp_async8(Bs + nn * LDB + k, ok ? F + (long long)(n0 + nn) * ld + (kg + k) : F, ok ? 8 : 0);
@@ -324,8 +328,8 @@ __global__ void __launch_bounds__(256, 1) k_gemm(const Front* __restrict__ front
     }
     constexpr int AV = TM / EPV;  // 16-byte vectors per k-row of the A tile
 #pragma unroll
-    for (int i = 0; i < (KC * AV) / 256; ++i) {
-      const int c = tid + i * 256;
+    for (int i = 0; i < (KC * AV) / NT; ++i) {
+      const int c = tid + i * NT;
       const int k = c / AV, m = (c % AV) * EPV;
       const int left = rhi - (m0 + m);
       int bytes = 0;
@@ -335,8 +339,8 @@ __global__ void __launch_bounds__(256, 1) k_gemm(const Front* __restrict__ front
     }
     constexpr int BV = KC / EPV;  // 16-byte vectors per column of the B tile
 #pragma unroll
-    for (int i = 0; i < (TN * BV) / 256; ++i) {
-      const int c = tid + i * 256;
+    for (int i = 0; i < (TN * BV) / NT; ++i) {
+      const int c = tid + i * NT;
       const int nn = c / BV, k = (c % BV) * EPV;
       int bytes = 0;
       if (n0 + nn < chi && k < krem) bytes = (krem - k) >= EPV ? 16 : (int)sizeof(T);
@@ -403,7 +407,7 @@ __global__ void __launch_bounds__(256, 1) k_gemm(const Front* __restrict__ front
   if (al) {
     constexpr int CV = TM / EPV;
 #pragma unroll 4
-    for (int c = tid; c < TN * CV; c += 256) {
+    for (int c = tid; c < TN * CV; c += NT) {
       const int nn = c / CV, m = (c % CV) * EPV;
       const int left = rhi - (m0 + m);
       int bytes = 0;
