@@ -6,7 +6,7 @@
 //   row ops    k_swap_trsm — row interchanges + unit-lower triangular solve of the U row panel
 //   update     k_gemm    — FP64 / complex-FP64 tensor-core (DMMA m8n8k4) Schur update C -= A·B
 //                                                                                  (factorization.jl:40,72)
-//   solve      k_solve_fwd / k_solve_bwd                        (factornode.jl:77-99)            HBM-bound
+//   solve      hs_solve.cu: k_trtri_diag, k_sv_small_*, k_sv_big_*, k_gemv_rect  (factornode.jl:77-99)  HBM-bound
 #pragma once
 
 #include <cooperative_groups.h>
@@ -449,100 +449,6 @@ __global__ void __launch_bounds__(GemmCfg<T>::TM / GemmCfg<T>::WM * GemmCfg<T>::
         }
       }
   }
-}
-
-// ------------------------------------------------------------------------------------------------
-// tree solve, one level per launch, one CTA per (front, right-hand side)
-// ------------------------------------------------------------------------------------------------
-// forward (factornode.jl:77-82 fused with the L half of :89-99):
-//   t = L11⁻¹·P·x[int];  x[bnd] -= L21·t;  x[int] = t
-template <typename T>
-__global__ void __launch_bounds__(256) k_solve_fwd(const Front* __restrict__ fronts, const T* __restrict__ pool,
-                                                    const int* __restrict__ gidx, const int* __restrict__ rperm,
-                                                    T* __restrict__ x, long long ldx, T* __restrict__ work,
-                                                    long long wstride, long long ioff0, int f0) {
-  const Front fr = fronts[f0 + blockIdx.x];
-  const int n = fr.n, ni = fr.ni;
-  if (ni == 0) return;
-  const long long ld = fr.ld;
-  const T* F = pool + fr.off;
-  T* xr = x + (long long)blockIdx.y * ldx;
-  T* w = work + (long long)blockIdx.y * wstride + (fr.ioff - ioff0);
-  const int* gi = gidx + fr.ioff;
-  const int* rp = rperm + fr.ioff;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  __shared__ T sw[32];
-  for (int k = tid; k < n; k += 256) w[k] = xr[gi[k < ni ? rp[k] : k]];
-  __syncthreads();
-  for (int jb = 0; jb < ni; jb += 32) {
-    const int bw = min(32, ni - jb);
-    if (warp == 0) {
-      T v = lane < bw ? w[jb + lane] : hs_zero<T>();
-      for (int k = 0; k < bw - 1; ++k) {
-        const T vk = hs_shfl(v, k);
-        if (lane > k && lane < bw) v = hs_fnma(v, F[(long long)(jb + k) * ld + (jb + lane)], vk);
-      }
-      if (lane < bw) w[jb + lane] = v;
-      sw[lane] = v;
-    }
-    __syncthreads();
-    for (int r = jb + bw + tid; r < n; r += 256) {
-      T acc = hs_zero<T>();
-      for (int k = 0; k < bw; ++k) acc = hs_fma(acc, F[(long long)(jb + k) * ld + r], sw[k]);
-      w[r] = hs_sub(w[r], acc);
-    }
-    __syncthreads();
-  }
-  for (int k = tid; k < n; k += 256) xr[gi[k]] = w[k];
-}
-
-// backward (U half of factornode.jl:89-99 fused with :83-88):  x[int] = U11⁻¹·(t − U12·x[bnd])
-template <typename T>
-__global__ void __launch_bounds__(256) k_solve_bwd(const Front* __restrict__ fronts, const T* __restrict__ pool,
-                                                    const int* __restrict__ gidx, T* __restrict__ x, long long ldx,
-                                                    T* __restrict__ work, long long wstride, long long ioff0,
-                                                    int f0) {
-  const Front fr = fronts[f0 + blockIdx.x];
-  const int n = fr.n, ni = fr.ni;
-  if (ni == 0) return;
-  const long long ld = fr.ld;
-  const T* F = pool + fr.off;
-  T* xr = x + (long long)blockIdx.y * ldx;
-  T* w = work + (long long)blockIdx.y * wstride + (fr.ioff - ioff0);
-  const int* gi = gidx + fr.ioff;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  __shared__ T sw[32];
-  for (int k = tid; k < n; k += 256) w[k] = xr[gi[k]];
-  __syncthreads();
-  for (int i = tid; i < ni; i += 256) {
-    T acc = hs_zero<T>();
-    for (int c = ni; c < n; ++c) acc = hs_fma(acc, F[(long long)c * ld + i], w[c]);
-    w[i] = hs_sub(w[i], acc);
-  }
-  __syncthreads();
-  const int nblk = (ni + 31) / 32;
-  for (int b = nblk - 1; b >= 0; --b) {
-    const int jb = b * 32;
-    const int bw = min(32, ni - jb);
-    if (warp == 0) {
-      T v = lane < bw ? w[jb + lane] : hs_zero<T>();
-      for (int k = bw - 1; k >= 0; --k) {
-        if (lane == k) v = hs_mul(v, hs_recip(F[(long long)(jb + k) * ld + (jb + k)]));
-        const T vk = hs_shfl(v, k);
-        if (lane < k) v = hs_fnma(v, F[(long long)(jb + k) * ld + (jb + lane)], vk);
-      }
-      if (lane < bw) w[jb + lane] = v;
-      sw[lane] = v;
-    }
-    __syncthreads();
-    for (int r = tid; r < jb; r += 256) {
-      T acc = hs_zero<T>();
-      for (int k = 0; k < bw; ++k) acc = hs_fma(acc, F[(long long)(jb + k) * ld + r], sw[k]);
-      w[r] = hs_sub(w[r], acc);
-    }
-    __syncthreads();
-  }
-  for (int k = tid; k < ni; k += 256) xr[gi[k]] = w[k];
 }
 
 // small helpers

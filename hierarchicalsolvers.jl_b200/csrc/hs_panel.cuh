@@ -99,12 +99,7 @@ __global__ void __launch_bounds__(256, 1) k_panel(const Front* __restrict__ fron
         const double v = absp[rl];
         if (v > cb) { cb = v; crl = rl; }
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const double ov = __shfl_xor_sync(0xffffffffu, cb, o);
-        const int orl = __shfl_xor_sync(0xffffffffu, crl, o);
-        if (ov > cb || (ov == cb && orl < crl)) { cb = ov; crl = orl; }
-      }
+      warp_argmax(cb, crl);
       if (cb >= 0.0 && tr == crl % TR) {  // the 8 threads that own the candidate row publish it
         const int ip = crl / TR;
 #pragma unroll
@@ -129,12 +124,11 @@ __global__ void __launch_bounds__(256, 1) k_panel(const Front* __restrict__ fron
             const PanelCand* rc = cluster.map_shared_rank(&s_cand[par], lane);
             wb = rc->val; wr = rc->row; wcid = lane;
           }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            const double ov = __shfl_xor_sync(0xffffffffu, wb, o);
-            const int orow = __shfl_xor_sync(0xffffffffu, wr, o);
-            const int oc = __shfl_xor_sync(0xffffffffu, wcid, o);
-            if (ov > wb || (ov == wb && orow < wr)) { wb = ov; wr = orow; wcid = oc; }
+          {  // rows are disjoint between CTAs, so the winning row identifies its CTA
+            const int myrow = wr;
+            warp_argmax(wb, wr);
+            wcid = (int)__reduce_min_sync(0xffffffffu, (wb >= 0.0 && myrow == wr) ? (unsigned)wcid : 0xffffffffu);
+            if (wcid < 0 || wcid >= C) wcid = 0;  // no candidate anywhere (cannot happen while j < wc): stay in range
           }
           const T* src = cluster.map_shared_rank(&s_crow[par][0], wcid);
           if (wb >= 0.0)
@@ -160,14 +154,15 @@ __global__ void __launch_bounds__(256, 1) k_panel(const Front* __restrict__ fron
         if (!(gb > 0.0) && atomicCAS(&info[0], 0, 1) == 0) { info[1] = fi; info[2] = j0 + j; }
       }
       if (gb > 0.0) {  // an exactly singular column is recorded and skipped, as LAPACK getf2 does
+        // No per-row predicates here: frozen pivot rows are never searched or stored again, so letting the update
+        // run over their registers is harmless, and rows beyond the front hold zeros.
         const T inv = hs_recip(urow[j]);
         T l[RPT];
 #pragma unroll
-        for (int i = 0; i < RPT; ++i) {
-          const int rl = tr + TR * i;
-          const bool act = !((done >> i) & 1ull) && rbase + rl < m;
-          l[i] = act ? hs_mul(colp[rl], inv) : hs_zero<T>();
-          if (act && tc == jt) a[i][kj] = l[i];
+        for (int i = 0; i < RPT; ++i) l[i] = hs_mul(colp[tr + TR * i], inv);
+        if (tc == jt) {  // warp-uniform: this warp owns column j and keeps the multipliers
+#pragma unroll
+          for (int i = 0; i < RPT; ++i) a[i][kj] = l[i];
         }
 #pragma unroll
         for (int k = kj; k < CPT; ++k) {

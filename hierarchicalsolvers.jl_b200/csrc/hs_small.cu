@@ -78,12 +78,7 @@ __global__ void __launch_bounds__(TR* TC, MINB) k_front_small(const Front* __res
         const double v = s_abs[par][r];
         if (v > best) { best = v; p = r; }
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const double ov = __shfl_xor_sync(0xffffffffu, best, o);
-        const int op = __shfl_xor_sync(0xffffffffu, p, o);
-        if (ov > best || (ov == best && op < p)) { best = ov; p = op; }
-      }
+      warp_argmax(best, p);
       const bool ok = best > 0.0;
       if (!ok) {  // exactly singular column: take the first remaining candidate as a formal pivot, no elimination
         singular = true;

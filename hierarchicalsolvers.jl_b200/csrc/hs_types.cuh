@@ -82,6 +82,20 @@ __host__ __device__ __forceinline__ bool hs_iszero(double a) { return a == 0.0; 
 __host__ __device__ __forceinline__ bool hs_iszero(cplx a) { return a.x == 0.0 && a.y == 0.0; }
 
 #ifdef __CUDACC__
+// warp arg-max of a non-negative double (or -1 = "no candidate") with ties resolved to the smallest index, through
+// three 32-bit REDUX operations instead of five rounds of 64-bit shuffles + compares.  Non-negative IEEE doubles order
+// like their bit patterns; -1.0 is mapped to key 0 and can never win against a real candidate (|v| ≥ 0 maps to ≥ 1).
+__device__ __forceinline__ void warp_argmax(double& val, int& idx) {
+  const unsigned long long bits = val < 0.0 ? 0ull : (unsigned long long)__double_as_longlong(val) + 1ull;
+  const unsigned hi = (unsigned)(bits >> 32), lo = (unsigned)bits;
+  const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+  const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+  const bool win = hi == mhi && lo == mlo;
+  const unsigned widx = __reduce_min_sync(0xffffffffu, win ? (unsigned)idx : 0xffffffffu);
+  const unsigned long long mb = ((unsigned long long)mhi << 32) | mlo;
+  val = mb == 0ull ? -1.0 : __longlong_as_double((long long)(mb - 1ull));
+  idx = (int)widx;
+}
 __device__ __forceinline__ double hs_shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 __device__ __forceinline__ cplx hs_shfl(cplx v, int src) {
   return cplx{__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src)};
