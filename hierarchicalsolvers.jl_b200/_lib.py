@@ -44,7 +44,8 @@ class hs_stats_t(C.Structure):
                 ("ms_solve_bwd", C.c_double), ("ms_solve_total", C.c_double), ("launches_factor", C.c_int64),
                 ("launches_solve", C.c_int64), ("singular_front", C.c_int64), ("singular_col", C.c_int64),
                 ("maxrank", C.c_int64), ("gemm_flops", C.c_double), ("gemm_launches", C.c_int64),
-                ("panel_launches", C.c_int64), ("ms_extend_add", C.c_double), ("ms_small", C.c_double), ("ms_solve_prep", C.c_double)]
+                ("panel_launches", C.c_int64), ("ms_extend_add", C.c_double), ("ms_small", C.c_double), ("ms_solve_prep", C.c_double),
+                ("ms_compress", C.c_double)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -77,6 +78,7 @@ PROTOTYPES = [
     ("hs_solve", C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32]),
     ("hs_node_get", C.c_int32, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, i64p]),
     ("hs_maxrank", C.c_int32, [C.c_void_p, i64p]),
+    ("hs_node_rank", C.c_int32, [C.c_void_p, C.c_int64, i64p, i64p]),
     ("hs_stats", C.c_int32, [C.c_void_p, C.POINTER(hs_stats_t)]),
     ("hs_resolved_swlevel", C.c_int32, [C.c_void_p, i64p]),
     ("hs_gmres", C.c_int32, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,

@@ -64,6 +64,7 @@ extern "C" int32_t hs_create(hs_ctx** out, int32_t device) {
   hs_panel_setup_f64();
   hs_panel_setup_c64();
   hs_solve_setup();
+  hs_comp_setup();
   c->max_cluster = getenv("HS_MAX_CLUSTER") ? atoi(getenv("HS_MAX_CLUSTER")) : 16;
   if (getenv("HS_OUTER_BLOCK")) c->outer_block = std::max(1, atoi(getenv("HS_OUTER_BLOCK")));
   CUDA_OK(cudaFuncSetAttribute(k_gemm<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes<double>()));
@@ -175,7 +176,7 @@ template <typename T> static void factor_level(hs_fac* f, const Level& L) {
     if (nact <= 0 || mrows <= 0 || mcols <= 0) return;
     PhaseTimer t(f, &f->stats.ms_gemm);
     dim3 grid(nact, (mrows + Cfg::TM - 1) / Cfg::TM + 1, (mcols + Cfg::TN - 1) / Cfg::TN);
-    k_gemm<T><<<grid, gemm_threads<T>(), smem_gemm, stream>>>(f->d_fronts, (T*)f->pool, L.f0, J0, j0, NB, W, mode);
+    k_gemm<T><<<grid, gemm_threads<T>(), smem_gemm, stream>>>(f->d_fronts, (T*)f->pool, L.f0, J0, j0, NB, W, mode, nullptr);
     CUDA_OK(cudaGetLastError());
     ++f->stats.gemm_launches;
     ++f->stats.launches_factor;
@@ -270,7 +271,8 @@ template <typename T> static void numeric(hs_fac* f) {
   cudaStream_t st = f->ctx->stream;
   T* pool = (T*)f->pool;
   hs_stats_t& s = f->stats;
-  s.ms_assemble = s.ms_panel = s.ms_trsm = s.ms_gemm = s.ms_solve_prep = s.ms_small = s.ms_extend_add = 0;
+  s.ms_assemble = s.ms_panel = s.ms_trsm = s.ms_gemm = s.ms_solve_prep = s.ms_small = s.ms_extend_add = s.ms_compress = 0;
+  s.maxrank = 0;
   s.launches_factor = 0;
   s.gemm_launches = s.panel_launches = 0;
   s.gemm_flops = 0;
@@ -307,7 +309,20 @@ template <typename T> static void numeric(hs_fac* f) {
       }
       CUDA_OK(cudaGetLastError());
     }
-    factor_level<T>(f, L);
+    // the level's dense fronts, then its compressed ones: low-rank Gauss transforms, LU of the thin bordered fronts,
+    // Schur complement back into the dense slots (hs_compress.cu)
+    for (Level& FL : f->flevels) {
+      if (FL.thin < 0) { if (FL.f0 == L.f0 && FL.pseudo == L.pseudo) factor_level<T>(f, FL); continue; }
+      CompLevel& C = f->clevels[FL.thin];
+      if (C.li != (int)li) continue;
+      {
+        PhaseTimer t(f, &s.ms_compress);
+        hs_comp_prepare(f, C);
+      }
+      factor_level<T>(f, FL);
+      PhaseTimer t(f, &s.ms_compress);
+      hs_comp_schur(f, C);
+    }
   }
   CUDA_OK(cudaEventRecord(f->ev1, st));
   f->ctx->launches += s.launches_factor;
@@ -426,11 +441,22 @@ static void build_plan(hs_fac* f, const hs_tree* t) {
     chk(l, f->bloc_ptr, f->bloc_idx, bnd_idx.data() + bnd_ptr[k]);
     chk(r, f->bloc_ptr, f->bloc_idx, bnd_idx.data() + bnd_ptr[k] + nbl);
   }
-  // front order: deepest level first; inside a level by ni descending (active panels form a prefix)
+  // swlevel < 0 is relative to the tree depth (factorization.jl:8);
+  // compression_flag = (level ≤ swlevel) && (|bnd| ≥ swsize) (factorization.jl:15).  Compressed leaves keep dense
+  // L and R in the reference too (:45-59) and S stays dense here, so only branches change.
+  f->swlevel_resolved = f->opts.swlevel < 0 ? std::max<int64_t>(f->depth + f->opts.swlevel, 0) : f->opts.swlevel;
+  std::vector<char> cflag(nn, 0);
+  if (!f->opts.subtree)
+    for (int64_t k = 0; k < nn; ++k)
+      cflag[k] = f->left[k] >= 0 && f->level[k] <= f->swlevel_resolved && f->node_nb[k] >= f->opts.swsize &&
+                 f->node_ni[k] > 0 && f->node_nb[k] > 0;
+  // front order: deepest level first; inside a level the dense fronts before the compressed ones, each group by ni
+  // descending (active panels form a prefix)
   std::vector<int64_t> order(nn);
   std::iota(order.begin(), order.end(), 0);
   std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
     if (f->level[a] != f->level[b]) return f->level[a] > f->level[b];
+    if (cflag[a] != cflag[b]) return cflag[a] < cflag[b];
     return f->node_ni[a] > f->node_ni[b];
   });
   const bool pseudo = f->node_nb[root] > 0 && !f->opts.subtree;
@@ -459,11 +485,13 @@ static void build_plan(hs_fac* f, const hs_tree* t) {
     if (f->left[k] < 0) { fr.ni_l = -1; fr.nb_l = 0; }
     else { fr.ni_l = (int)nloc(f->iloc_ptr, f->left[k]); fr.nb_l = (int)nloc(f->bloc_ptr, f->left[k]); }
     if (f->levels.empty() || f->level[k] != f->level[order[f->levels.back().f0]]) {
-      Level L; L.f0 = i; L.f1 = i; L.ioff0 = ioff; L.poff0 = poff;
+      Level L; L.f0 = i; L.f1 = i; L.fm = i; L.ioff0 = ioff; L.poff0 = poff;
       f->levels.push_back(L);
     }
     Level& L = f->levels.back();
     L.f1 = i + 1;
+    if (!cflag[k]) L.fm = i + 1;  // dense fronts come first: fm ends up one past the last of them
+    else if (L.fm < L.f0) L.fm = L.f0;
     L.max_n = std::max(L.max_n, fr.n);
     L.max_ni = std::max(L.max_ni, fr.ni);
     L.max_nb = std::max(L.max_nb, fr.n - fr.ni);
@@ -507,7 +535,7 @@ static void build_plan(hs_fac* f, const hs_tree* t) {
     pf.parent = -1;
     pf.ni_l = -1; pf.nb_l = 0;
     pf.flags = 1;
-    Level L; L.f0 = (int)nn; L.f1 = (int)nn + 1; L.max_n = L.max_ni = pf.n; L.max_nb = 0;
+    Level L; L.f0 = (int)nn; L.f1 = (int)nn + 1; L.fm = L.f1; L.max_n = L.max_ni = pf.n; L.max_nb = 0;
     L.ioff0 = ioff; L.ioff1 = ioff + pf.n; L.poff0 = L.poff1 = poff; L.pseudo = true;
     L.ni_sorted.push_back(pf.ni);
     f->levels.push_back(L);
@@ -523,8 +551,65 @@ static void build_plan(hs_fac* f, const hs_tree* t) {
   f->ext_ld.assign(f->fronts.size(), 0);
   f->pool_elems = poff;
   f->idx_total = ioff;
+  // factor / solve levels.  A compressed front gets a second ("thin") descriptor at nfr + its id, rows
+  // [int; r border rows]; the border rows live in virtual slots n + voff + k of the internal solution vector.
+  f->nfr = nfr;
+  f->fronts.resize(2 * (size_t)nfr, Front{});
+  f->flevels.clear(); f->comp.clear(); f->clevels.clear();
+  f->nvirt = 0;
+  for (size_t li = 0; li < f->levels.size(); ++li) {
+    const Level& L = f->levels[li];
+    if (L.fm > L.f0 || L.f1 == L.f0) {
+      Level D = L;
+      D.f1 = L.fm; D.thin = -1;
+      if (L.fm < L.f1) {  // only the dense part
+        D.max_n = D.max_ni = D.max_nb = 0;
+        D.ni_sorted.assign(L.ni_sorted.begin(), L.ni_sorted.begin() + (L.fm - L.f0));
+        for (int i = L.f0; i < L.fm; ++i) {
+          D.max_n = std::max(D.max_n, f->fronts[i].n); D.max_ni = std::max(D.max_ni, f->fronts[i].ni);
+          D.max_nb = std::max(D.max_nb, f->fronts[i].n - f->fronts[i].ni);
+        }
+        D.ioff0 = f->fronts[L.f0].ioff; D.ioff1 = f->fronts[L.fm - 1].ioff + f->fronts[L.fm - 1].n;
+      }
+      f->flevels.push_back(D);
+    }
+    if (L.fm < L.f1) {
+      CompLevel C; C.li = (int)li; C.c0 = (int)f->comp.size();
+      Level Tl; Tl.f0 = nfr + L.fm; Tl.f1 = nfr + L.f1; Tl.fm = Tl.f1; Tl.thin = (int)f->clevels.size();
+      Tl.ioff0 = ioff;
+      for (int i = L.fm; i < L.f1; ++i) {
+        const Front& fd = f->fronts[i];
+        CompFront cf; cf.fi = i; cf.ni = fd.ni; cf.nb = fd.n - fd.ni; cf.rcap = std::min(cf.ni, cf.nb);
+        cf.voff = f->nvirt; f->nvirt += cf.rcap;
+        f->comp.push_back(cf);
+        Front& th = f->fronts[nfr + i];
+        th = fd;
+        th.ioff = ioff; th.parent = -1; th.ni_l = -1; th.nb_l = 0; th.flags = 0;
+        th.n = fd.ni; th.ld = (fd.ni + 1) & ~1;  // set per factorization once the ranks are known
+        for (int q = 0; q < fd.ni; ++q) gidx.push_back(gidx[fd.ioff + q]);
+        for (int q = 0; q < cf.rcap; ++q) gidx.push_back((int)(f->n + cf.voff + q));
+        ioff += fd.ni + cf.rcap;
+        Tl.ni_sorted.push_back(fd.ni);
+        Tl.max_ni = std::max(Tl.max_ni, fd.ni);
+      }
+      Tl.max_n = Tl.max_ni; Tl.max_nb = 0;
+      Tl.ioff1 = ioff;
+      C.c1 = (int)f->comp.size();
+      C.flevel = (int)f->flevels.size();
+      f->flevels.push_back(Tl);
+      f->clevels.push_back(C);
+    }
+  }
+  if ((long long)f->n + f->nvirt >= (1ll << 31)) throw hs_error(HS_ESIZE, "solution vector too long for 32-bit row tables");
+  f->xld = f->n + f->nvirt;
+  cmap.resize(ioff, -1);
   f->max_level_idx = 0;
-  for (auto& L : f->levels) f->max_level_idx = std::max(f->max_level_idx, L.ioff1 - L.ioff0);
+  for (auto& L : f->flevels) f->max_level_idx = std::max(f->max_level_idx, L.ioff1 - L.ioff0 + 0);
+  for (auto& C : f->clevels) {  // the border of a thin front may grow to rcap rows
+    long long span = 0;
+    for (int c = C.c0; c < C.c1; ++c) span += f->comp[c].ni + f->comp[c].rcap;
+    f->max_level_idx = std::max(f->max_level_idx, span);
+  }
   const double cx = f->dtype == HS_C64 ? 4.0 : 1.0;
   hs_stats_t& s = f->stats;
   s.nnodes = nn; s.nlevels = maxlev; s.n = f->n; s.max_ni = max_ni; s.max_nb = max_nb;
@@ -549,6 +634,7 @@ static void build_plan(hs_fac* f, const hs_tree* t) {
   CUDA_OK(cudaMemsetAsync(f->d_ipiv, 0, std::max<size_t>(ioff, 1) * sizeof(int), st));
   CUDA_OK(cudaMemsetAsync(f->d_rperm, 0, std::max<size_t>(ioff, 1) * sizeof(int), st));
   CUDA_OK(cudaStreamSynchronize(st));  // host vectors go out of scope
+  hs_comp_plan(f);
 }
 
 __global__ void k_widen_index(long long* dst, const int* src, long long n, long long base) {
@@ -584,14 +670,6 @@ static int32_t factor_impl(hs_ctx* ctx, hs_dtype dtype, int64_t n, const int64_t
   CUDA_OK(cudaEventCreate(&f->ev0));
   CUDA_OK(cudaEventCreate(&f->ev1));
   build_plan(f.get(), tree);
-  // swlevel < 0 is relative to the tree depth (factorization.jl:8)
-  f->swlevel_resolved = f->opts.swlevel < 0 ? std::max<int64_t>(f->depth + f->opts.swlevel, 0) : f->opts.swlevel;
-  if (f->swlevel_resolved > 0) {
-    // compression_flag = (level ≤ swlevel) && (|bnd| ≥ swsize) (factorization.jl:15)
-    for (int64_t k = 0; k < f->nnodes; ++k)
-      if (f->level[k] <= f->swlevel_resolved && f->node_nb[k] >= f->opts.swsize)
-        return hs_fail(HS_ENOTIMPL, "hs_factor: HSS-compressed fronts (swlevel > 0) are not built yet; pass swlevel = 0");
-  }
   auto t_plan = std::chrono::steady_clock::now();
   f->stats.ms_analyze = std::chrono::duration<double, std::milli>(t_plan - t_begin).count();
   // matrix
@@ -695,6 +773,7 @@ extern "C" int32_t hs_solve_sweep(hs_fac* f, int64_t nrhs, void* x, int64_t ldx,
   if (!f || !x) return hs_fail(HS_EARG, "hs_solve_sweep: null argument");
   if (nrhs <= 0 || !(which & 3)) return HS_OK;
   if (ldx != f->n) return hs_fail(HS_EDIM, "hs_solve_sweep: ldx must equal n");
+  if (f->nvirt) return hs_fail(HS_ENOTIMPL, "hs_solve_sweep: not available for factorizations with compressed fronts");
   CUDA_OK(cudaSetDevice(f->ctx->device));
   if (nrhs > f->rhs_cap) {
     cudaFree(f->d_x); cudaFree(f->d_work);
@@ -737,14 +816,16 @@ template <typename T> static void solve_impl(hs_fac* f, int64_t nrhs, const void
   if (nrhs > f->rhs_cap) {
     cudaFree(f->d_x); cudaFree(f->d_work);
     f->d_x = f->d_work = nullptr;
-    CUDA_OK(cudaMalloc(&f->d_x, (size_t)f->n * nrhs * sizeof(T)));
+    CUDA_OK(cudaMalloc(&f->d_x, (size_t)f->xld * nrhs * sizeof(T)));
     CUDA_OK(cudaMalloc(&f->d_work, std::max<size_t>((size_t)f->max_level_idx * nrhs, 1) * sizeof(T)));
     f->rhs_cap = nrhs;
   }
   T* x = (T*)f->d_x;
   const cudaMemcpyKind kin = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   const cudaMemcpyKind kout = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-  CUDA_OK(cudaMemcpy2DAsync(x, (size_t)f->n * sizeof(T), B, (size_t)ldb * sizeof(T), (size_t)f->n * sizeof(T), nrhs, kin, st));
+  CUDA_OK(cudaMemcpy2DAsync(x, (size_t)f->xld * sizeof(T), B, (size_t)ldb * sizeof(T), (size_t)f->n * sizeof(T), nrhs, kin, st));
+  if (f->nvirt)  // border rows of the thin fronts start from zero
+    CUDA_OK(cudaMemset2DAsync(x + f->n, (size_t)f->xld * sizeof(T), 0, (size_t)f->nvirt * sizeof(T), nrhs, st));
   CUDA_OK(cudaEventRecord(f->ev0, st));
   hs_stats_t& s = f->stats;
   s.launches_solve = 0;
@@ -752,7 +833,7 @@ template <typename T> static void solve_impl(hs_fac* f, int64_t nrhs, const void
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaEventRecord(f->ev1, st));
   f->ctx->launches += s.launches_solve;
-  CUDA_OK(cudaMemcpy2DAsync(X, (size_t)ldx * sizeof(T), x, (size_t)f->n * sizeof(T), (size_t)f->n * sizeof(T), nrhs, kout, st));
+  CUDA_OK(cudaMemcpy2DAsync(X, (size_t)ldx * sizeof(T), x, (size_t)f->xld * sizeof(T), (size_t)f->n * sizeof(T), nrhs, kout, st));
   CUDA_OK(cudaStreamSynchronize(st));
   float ms = 0;
   CUDA_OK(cudaEventElapsedTime(&ms, f->ev0, f->ev1));
@@ -774,8 +855,84 @@ extern "C" int32_t hs_solve(hs_fac* f, int64_t nrhs, const void* B, int64_t ldb,
 // ------------------------------------------------------------------------------------------------
 // introspection: FactorNode fields as the reference defines them (host-side reconstruction from the front)
 // ------------------------------------------------------------------------------------------------
+template <typename T> static void node_get_impl(hs_fac* f, int64_t node, hs_which which, void* out, int64_t* dims);
+
+// compressed node: D, L = Qb·(Rb·Aii⁻¹), R = (Aii⁻¹·Qi)·Ri from the thin front (as an uncompressed front with r
+// boundary rows), S from the dense slot
+template <typename T> static void node_get_compressed(hs_fac* f, int64_t node, const CompFront& cf, hs_which which, void* out,
+                                                      int64_t* dims) {
+  const int fi = cf.fi, ni = cf.ni, nb = cf.nb;
+  cudaStream_t st = f->ctx->stream;
+  T* o = (T*)out;
+  if (which == HS_GET_S || which == HS_GET_FRONT || which == HS_GET_PIV || which == HS_GET_D) {
+    // S lives in the dense slot; D, the raw front and the pivots are those of the thin front
+    const bool thin = which != HS_GET_S;
+    std::swap(f->fronts[fi], f->fronts[f->nfr + fi]);  // node_get_impl reads fronts[node2front[node]]
+    if (!thin) std::swap(f->fronts[fi], f->fronts[f->nfr + fi]);
+    std::vector<CompFront> keep;
+    keep.swap(f->comp);
+    try { node_get_impl<T>(f, node, which, out, dims); } catch (...) {
+      keep.swap(f->comp);
+      if (thin) std::swap(f->fronts[fi], f->fronts[f->nfr + fi]);
+      throw;
+    }
+    keep.swap(f->comp);
+    if (thin) std::swap(f->fronts[fi], f->fronts[f->nfr + fi]);
+    return;
+  }
+  if (which != HS_GET_L && which != HS_GET_R) throw hs_error(HS_EARG, "hs_node_get: unknown field");
+  const bool isL = which == HS_GET_L;
+  if (dims) { dims[0] = isL ? nb : ni; dims[1] = isL ? ni : nb; }
+  if (!out) return;
+  // thin-front quantity through the uncompressed code path: Lt = (Rb·U11⁻¹)·L11⁻¹·P (r×ni), Rt = U11⁻¹·(L11⁻¹PQi) (ni×r)
+  const int r = cf.r;
+  std::vector<T> thinq((size_t)std::max(r, 1) * ni);
+  {
+    std::swap(f->fronts[fi], f->fronts[f->nfr + fi]);
+    std::vector<CompFront> keep;
+    keep.swap(f->comp);
+    int64_t d2[2];
+    try { node_get_impl<T>(f, node, which, thinq.data(), d2); } catch (...) {
+      keep.swap(f->comp);
+      std::swap(f->fronts[fi], f->fronts[f->nfr + fi]);
+      throw;
+    }
+    keep.swap(f->comp);
+    std::swap(f->fronts[fi], f->fronts[f->nfr + fi]);
+  }
+  const T* pool = (const T*)f->pool;
+  if (isL) {
+    std::vector<T> Qb((size_t)nb * std::max(cf.r1, 1));
+    if (cf.r1) CUDA_OK(cudaMemcpy2DAsync(Qb.data(), (size_t)nb * sizeof(T), pool + cf.qb, (size_t)cf.qb_ld * sizeof(T),
+                                         (size_t)nb * sizeof(T), cf.r1, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    for (int j = 0; j < ni; ++j)
+      for (int i = 0; i < nb; ++i) {
+        T acc = hs_zero<T>();
+        for (int k = 0; k < cf.r1; ++k) acc = hs_fma(acc, Qb[(size_t)k * nb + i], thinq[(size_t)j * r + k]);
+        o[(size_t)j * nb + i] = acc;
+      }
+  } else {
+    std::vector<T> Ri((size_t)std::max(cf.r2, 1) * nb);
+    if (cf.r2) CUDA_OK(cudaMemcpy2DAsync(Ri.data(), (size_t)cf.r2 * sizeof(T), pool + cf.ri, (size_t)cf.ri_ld * sizeof(T),
+                                         (size_t)cf.r2 * sizeof(T), nb, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    for (int j = 0; j < nb; ++j)
+      for (int i = 0; i < ni; ++i) {
+        T acc = hs_zero<T>();
+        for (int k = 0; k < cf.r2; ++k) acc = hs_fma(acc, thinq[(size_t)k * ni + i], Ri[(size_t)j * cf.r2 + k]);
+        o[(size_t)j * ni + i] = acc;
+      }
+  }
+}
+
 template <typename T> static void node_get_impl(hs_fac* f, int64_t node, hs_which which, void* out, int64_t* dims) {
-  const Front& fr = f->fronts[f->node2front[node]];
+  const Front& fd = f->fronts[f->node2front[node]];
+  const CompFront* cf = nullptr;
+  for (const CompFront& q : f->comp)
+    if (q.fi == f->node2front[node]) cf = &q;
+  if (cf) { node_get_compressed<T>(f, node, *cf, which, out, dims); return; }
+  const Front& fr = fd;
   const int n = fr.n, ni = fr.ni, nb = n - ni;
   int64_t r = 0, c = 0;
   switch (which) {
@@ -918,6 +1075,16 @@ extern "C" int32_t hs_node_get(hs_fac* f, int64_t node, hs_which which, void* ou
 extern "C" int32_t hs_maxrank(hs_fac* f, int64_t* rank) {
   if (!f || !rank) return hs_fail(HS_EARG, "hs_maxrank: null argument");
   *rank = f->stats.maxrank;  // 0 when nothing is compressed (factornode.jl:49-57)
+  return HS_OK;
+}
+
+extern "C" int32_t hs_node_rank(hs_fac* f, int64_t node, int64_t* rank_l, int64_t* rank_r) {
+  if (!f || !rank_l || !rank_r) return hs_fail(HS_EARG, "hs_node_rank: null argument");
+  if (node < 0 || node >= f->nnodes) return hs_fail(HS_EARG, "hs_node_rank: node out of range");
+  *rank_l = *rank_r = 0;
+  const int fi = f->node2front[node];
+  for (const CompFront& cf : f->comp)
+    if (cf.fi == fi) { *rank_l = cf.r1; *rank_r = cf.r2; }
   return HS_OK;
 }
 

@@ -45,6 +45,51 @@ struct Level {
   long long poff0 = 0, poff1 = 0;
   bool pseudo = false;
   std::vector<int> ni_sorted;  // ni of the fronts in this level (descending)
+  int fm = 0;                  // assembly levels: fronts [fm, f1) are compressed (fm = f1: none)
+  int thin = -1;               // factor/solve levels: index into hs_fac::clevels when this is a level of thin fronts
+};
+
+// ---- compressed path (factorization.jl:78-112): low-rank Gauss transforms ------------------------------------
+// A compressed front keeps its dense slot in the pool for the assembly and for its Schur block S, but what is
+// factored and kept for the solve is the THIN bordered front
+//        [ Aii   Qi ]  ni            Abi ≈ Qb·Rb   (nb×r1 · r1×ni)      L = Qb·(Rb·Aii⁻¹)
+//        [ Rb    0  ]  r             Aib ≈ Qi·Ri   (ni×r2 · r2×nb)      R = (Aii⁻¹·Qi)·Ri
+// whose partial LU yields Rb·U11⁻¹ and L11⁻¹·P·Qi: the solve runs through the ordinary front kernels on ni + r rows,
+// the r border rows living in "virtual" slots appended to the solution vector, plus one thin product with Qb
+// (forward) and one with Ri (backward).
+struct CompFront {
+  int fi = 0;        // dense front id; the thin descriptor is fronts[nfr + fi]
+  int ni = 0, nb = 0;
+  int rcap = 0;      // min(ni, nb)
+  int r1 = 0, r2 = 0, r = 0;
+  long long voff = 0;                   // first virtual slot (x index n + voff)
+  long long qb = 0, vit = 0, ri = 0;    // element offsets from `pool` of Qb (nb×r1), Riᵀ (nb×r2), Ri (r2×nb)
+  int qb_ld = 0, ri_ld = 0;
+};
+struct IdRun {       // one truncated column-pivoted QR (pivoted Cholesky of the Gram matrix), device + host
+  long long moff;    // pool offset of M(0,0);  M is m × ncol with leading dimension ld
+  int m, ncol, ld;
+  int rcap, ldr;     // at most rcap steps; R is ldr × ncol in the workspace at rws
+  int ip;            // ints[ip .. ip+rcap): pivots
+  long long rws;
+  long long st;      // state (doubles): d[2][ncol], then r11
+  int slot;          // ints[1 + slot]: rank (−1 while running)
+  int pad;
+};
+struct LrDesc {      // device image of one compressed front once its ranks are known
+  int fi, thin;
+  int ni, nb;
+  int r1, r2, r, pad;
+  long long voff;
+  long long qb, vit, ri;
+  int qb_ld, ri_ld;
+};
+struct CompLevel {
+  int li = 0;             // assembly level
+  int c0 = 0, c1 = 0;     // range in hs_fac::comp; runs 2·c (Abi) and 2·c + 1 (Aib)
+  int flevel = 0;         // index of the thin level in hs_fac::flevels
+  void* side = nullptr;   // thin fronts + Qb + Ri of this level (sized once the ranks are known)
+  size_t side_bytes = 0;
 };
 
 struct hs_fac {
@@ -59,7 +104,21 @@ struct hs_fac {
   std::vector<int64_t> iloc_ptr, iloc_idx, bloc_ptr, bloc_idx;
   std::vector<int> node_ni, node_nb, node2front;
   std::vector<Front> fronts;
-  std::vector<Level> levels;  // deepest first, root last (+ pseudo front for a non-empty root boundary)
+  std::vector<Level> levels;  // assembly levels: deepest first, root last (+ pseudo front for a non-empty root boundary)
+  std::vector<Level> flevels; // factor / solve levels: per assembly level its dense fronts, then its thin fronts
+  std::vector<CompFront> comp;
+  std::vector<CompLevel> clevels;
+  int nfr = 0;                // number of dense front descriptors; thin descriptors follow at nfr + fi
+  long long nvirt = 0;        // virtual slots appended to the solution vector
+  long long xld = 0;          // leading dimension of the internal solution buffer: n + nvirt
+  std::vector<IdRun> runs;    // two per compressed front
+  void* d_cws = nullptr;      // workspace of a level: R factors, later Aii⁻¹Qi and Abi·Aii⁻¹Qi
+  double* d_cstate = nullptr; // per run: running column norms (2×ncol), r11
+  int* d_cint = nullptr;      // [0] runs finished, [1+slot] ranks, pivots
+  IdRun* d_runs = nullptr;
+  LrDesc* d_lr = nullptr;     // one per compressed front (index = position in `comp`)
+  void* d_gd = nullptr;       // GemmDesc staging
+  size_t gd_cap = 0;
   int root_front = -1, pseudo_front = -1;
   // external leaves (subtree-per-GPU): front id → device buffer its Schur block is imported from
   std::vector<const void*> ext_src;
@@ -84,6 +143,8 @@ struct hs_fac {
     cudaFree(pool); cudaFree(d_fronts); cudaFree(d_gidx); cudaFree(d_ipiv); cudaFree(d_rperm); cudaFree(d_cmap);
     cudaFree(d_own); cudaFree(d_pos); cudaFree(d_info); cudaFree(d_colptr); cudaFree(d_rowval); cudaFree(d_nzval);
     cudaFree(d_x); cudaFree(d_work); cudaFree(d_csr_ptr); cudaFree(d_csr_col); cudaFree(d_csr_val);
+    cudaFree(d_cws); cudaFree(d_cstate); cudaFree(d_cint); cudaFree(d_runs); cudaFree(d_lr); cudaFree(d_gd);
+    for (auto& c : clevels) cudaFree(c.side);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
   }
@@ -113,3 +174,10 @@ void hs_solve_run(hs_fac* f, int64_t nrhs, void* x, int which);  // which: 1 for
 // hs_small.cu
 int hs_small_max_n(hs_dtype dt);
 void hs_small_factor(hs_fac* f, const Level& L);
+
+// hs_compress.cu
+void hs_comp_setup();
+void hs_comp_plan(hs_fac* f);                        // workspaces + device descriptors, after build_plan
+void hs_comp_prepare(hs_fac* f, CompLevel& C);       // IDs of Abi / Aib, ranks, thin fronts (before their LU)
+void hs_comp_schur(hs_fac* f, CompLevel& C);         // S = Abb − (Abi·Aii⁻¹Qi)·Ri (after the thin LU)
+void hs_comp_solve(hs_fac* f, const CompLevel& C, int64_t nrhs, void* x, bool fwd);

@@ -20,7 +20,7 @@ namespace cg = cooperative_groups;
 // ------------------------------------------------------------------------------------------------
 
 // own[g] = front that holds DOF g on this level, pos[g] = its row inside that front
-__global__ void k_fill_owner(const Front* __restrict__ fronts, const int* __restrict__ gidx, int* __restrict__ own,
+static __global__ void k_fill_owner(const Front* __restrict__ fronts, const int* __restrict__ gidx, int* __restrict__ own,
                              int* __restrict__ pos, int f0) {
   const int fi = f0 + blockIdx.x;
   const Front fr = fronts[fi];
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(256) k_extend_add(const Front* __restrict__ fr
 }
 
 // rperm[k] = local row of the ORIGINAL pivot block that ends at row k after all interchanges (so P·x is a gather)
-__global__ void k_rperm(const Front* __restrict__ fronts, const int* __restrict__ ipiv, int* __restrict__ rperm,
+static __global__ void k_rperm(const Front* __restrict__ fronts, const int* __restrict__ ipiv, int* __restrict__ rperm,
                         int f0) {
   extern __shared__ int s_p[];
   const Front fr = fronts[f0 + blockIdx.x];
@@ -257,9 +257,18 @@ template <typename T> constexpr int gemm_smem_bytes() {
   return pipe > ctile ? pipe : ctile;
 }
 
-template <typename T>
+// GEN = true: free-standing batched product C ∓= A·B described by GemmDesc (compressed path); blockIdx.x is the item.
+struct GemmDesc {
+  long long a, b, c;  // element offsets from `pool`: A is M×K (lda), B is K×N (ldb), C is M×N (ldc), all column-major
+  int lda, ldb, ldc;
+  int M, N, K;
+  int sign;           // -1: C -= A·B, +1: C += A·B
+  int pad;
+};
+
+template <typename T, bool GEN = false>
 __global__ void __launch_bounds__(GemmCfg<T>::TM / GemmCfg<T>::WM * GemmCfg<T>::TN / GemmCfg<T>::WN * 32) k_gemm(const Front* __restrict__ fronts, T* __restrict__ pool, int f0, int J0,
-                                                  int j0, int NB, int W, int mode) {
+                                                  int j0, int NB, int W, int mode, const GemmDesc* __restrict__ gdesc) {
   using Cfg = GemmCfg<T>;
   constexpr int TM = Cfg::TM, TN = Cfg::TN, WM = Cfg::WM, WN = Cfg::WN, KC = Cfg::KC, ST = Cfg::ST, LDA = Cfg::LDA,
                 LDB = Cfg::LDB;
@@ -267,31 +276,46 @@ __global__ void __launch_bounds__(GemmCfg<T>::TM / GemmCfg<T>::WM * GemmCfg<T>::
   constexpr int EPV = 16 / (int)sizeof(T);  // elements per 16-byte vector: 2 (f64) or 1 (c64)
   constexpr int MI = WM / 8, NI = WN / 8;
   constexpr int NT = (TM / WM) * (TN / WN) * 32;  // threads per CTA
-  const Front fr = fronts[f0 + blockIdx.x];
-  const int n = fr.n, ni = fr.ni;
   int kbase, kcount, lo, rhi, clo, chi;  // C = rows [lo, rhi) × cols [clo, chi)
-  const int BE = min(J0 + NB, ni);
-  if (mode == 1 || mode >= 3) {
-    if (ni <= J0) return;
-    const int BE2 = min(BE + NB, ni);
-    kbase = J0; kcount = BE - J0; lo = BE; rhi = n;
-    clo = mode == 4 ? BE2 : BE;
-    chi = mode == 3 ? BE2 : n;
+  const T *FA, *FB;   // A(m, k) = FA[k·lda + m], B(k, c) = FB[c·ldb + k]
+  T* F;               // C(m, c) = F[c·ld + m]
+  long long lda, ldb, ld;
+  bool al, plus = false;
+  if constexpr (GEN) {
+    const GemmDesc gd = gdesc[blockIdx.x];
+    kbase = 0; kcount = gd.K; lo = 0; rhi = gd.M; clo = 0; chi = gd.N;
+    FA = pool + gd.a; FB = pool + gd.b; F = pool + gd.c;
+    lda = gd.lda; ldb = gd.ldb; ld = gd.ldc;
+    al = ((gd.a | gd.b | gd.c | gd.lda | gd.ldb | gd.ldc) & (EPV - 1)) == 0;
+    plus = gd.sign > 0;
+    if (kcount <= 0) return;
   } else {
-    if (ni <= j0) return;
-    const int wc = min(W, ni - j0);
-    kbase = j0; kcount = wc; lo = j0 + wc;
-    if (mode == 0) { rhi = n; clo = lo; chi = BE; } else { rhi = BE; clo = BE; chi = n; }
+    const Front fr = fronts[f0 + blockIdx.x];
+    const int n = fr.n, ni = fr.ni;
+    const int BE = min(J0 + NB, ni);
+    if (mode == 1 || mode >= 3) {
+      if (ni <= J0) return;
+      const int BE2 = min(BE + NB, ni);
+      kbase = J0; kcount = BE - J0; lo = BE; rhi = n;
+      clo = mode == 4 ? BE2 : BE;
+      chi = mode == 3 ? BE2 : n;
+    } else {
+      if (ni <= j0) return;
+      const int wc = min(W, ni - j0);
+      kbase = j0; kcount = wc; lo = j0 + wc;
+      if (mode == 0) { rhi = n; clo = lo; chi = BE; } else { rhi = BE; clo = BE; chi = n; }
+    }
+    // rows are loaded in aligned 16-byte pairs; a front whose base is not 16-byte aligned (only the root-boundary
+    // pseudo front can be) takes the 8-byte copy path
+    al = (fr.off & (EPV - 1)) == 0;
+    F = pool + fr.off;
+    FA = F; FB = F;
+    lda = ldb = ld = fr.ld;
   }
   if (lo >= rhi || clo >= chi) return;
-  // rows are loaded in aligned 16-byte pairs; a front whose base is not 16-byte aligned (only the root-boundary
-  // pseudo front can be) takes the 8-byte copy path
-  const bool al = (fr.off & (EPV - 1)) == 0;
   const int rbase = al ? (lo & ~(EPV - 1)) : lo;
   const int m0 = rbase + blockIdx.y * TM, n0 = clo + blockIdx.z * TN;
   if (m0 >= rhi || n0 >= chi) return;
-  T* F = pool + fr.off;
-  const long long ld = fr.ld;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* smem = reinterpret_cast<T*>(smem_raw);
   constexpr int STAGE = KC * LDA + TN * LDB;
@@ -317,12 +341,12 @@ __global__ void __launch_bounds__(GemmCfg<T>::TM / GemmCfg<T>::WM * GemmCfg<T>::
       for (int c = tid; c < KC * TM; c += NT) {
         const int k = c / TM, m = c % TM;
         const bool ok = k < krem && m0 + m < rhi;
-        cp_async8(As + k * LDA + m, ok ? F + (long long)(kg + k) * ld + (m0 + m) : F, ok ? 8 : 0);
+        cp_async8(As + k * LDA + m, ok ? FA + (long long)(kg + k) * lda + (m0 + m) : FA, ok ? 8 : 0);
       }
       for (int c = tid; c < TN * KC; c += NT) {
         const int nn = c / KC, k = c % KC;
         const bool ok = n0 + nn < chi && k < krem;
-        cp_async8(Bs + nn * LDB + k, ok ? F + (long long)(n0 + nn) * ld + (kg + k) : F, ok ? 8 : 0);
+        cp_async8(Bs + nn * LDB + k, ok ? FB + (long long)(n0 + nn) * ldb + (kg + k) : FB, ok ? 8 : 0);
       }
       return;
     }
@@ -334,7 +358,7 @@ __global__ void __launch_bounds__(GemmCfg<T>::TM / GemmCfg<T>::WM * GemmCfg<T>::
       const int left = rhi - (m0 + m);
       int bytes = 0;
       if (k < krem && left > 0) bytes = left >= EPV ? 16 : (int)sizeof(T);
-      const T* src = bytes ? F + (long long)(kg + k) * ld + (m0 + m) : F;
+      const T* src = bytes ? FA + (long long)(kg + k) * lda + (m0 + m) : FA;
       cp_async16(As + k * LDA + m, src, bytes);
     }
     constexpr int BV = KC / EPV;  // 16-byte vectors per column of the B tile
@@ -344,7 +368,7 @@ __global__ void __launch_bounds__(GemmCfg<T>::TM / GemmCfg<T>::WM * GemmCfg<T>::
       const int nn = c / BV, k = (c % BV) * EPV;
       int bytes = 0;
       if (n0 + nn < chi && k < krem) bytes = (krem - k) >= EPV ? 16 : (int)sizeof(T);
-      const T* src = bytes ? F + (long long)(n0 + nn) * ld + (kg + k) : F;
+      const T* src = bytes ? FB + (long long)(n0 + nn) * ldb + (kg + k) : FB;
       cp_async16(Bs + nn * LDB + k, src, bytes);
     }
   };
@@ -440,10 +464,10 @@ __global__ void __launch_bounds__(GemmCfg<T>::TM / GemmCfg<T>::WM * GemmCfg<T>::
         if (rok && c < chi) {
           T v = cv[j][h];
           if constexpr (!CX) {
-            v -= acc[0][i][j][h];
+            v = (GEN && plus) ? v + acc[0][i][j][h] : v - acc[0][i][j][h];
           } else {
-            v.x -= acc[0][i][j][h];
-            v.y -= acc[1][i][j][h];
+            if (GEN && plus) { v.x += acc[0][i][j][h]; v.y += acc[1][i][j][h]; }
+            else { v.x -= acc[0][i][j][h]; v.y -= acc[1][i][j][h]; }
           }
           F[(long long)c * ld + r] = v;
         }

@@ -545,7 +545,7 @@ template <typename T, bool FWD> void launch_big(hs_fac* f, const Level& L, int n
   const int* gidx = f->d_gidx;
   const int* rperm = f->d_rperm;
   T* work = (T*)f->d_work;
-  long long ldx = f->n, ws = f->max_level_idx, ioff0 = L.ioff0;
+  long long ldx = f->xld, ws = f->max_level_idx, ioff0 = L.ioff0;
   int f0 = L.f0;
   if (C == 1) {
     dim3 g(nbig, (unsigned)nrhs);
@@ -576,36 +576,38 @@ template <typename T> void run_impl(hs_fac* f, int64_t nrhs, void* xv, int which
   auto nbig_of = [&](const Level& L) {
     return (int)(std::partition_point(L.ni_sorted.begin(), L.ni_sorted.end(), [&](int v) { return v > DB; }) - L.ni_sorted.begin());
   };
-  for (size_t li = 0; (which & 1) && li < f->levels.size(); ++li) {  // post-order
-    const Level& L = f->levels[li];
+  for (size_t li = 0; (which & 1) && li < f->flevels.size(); ++li) {  // post-order
+    const Level& L = f->flevels[li];
     const int nf = L.f1 - L.f0, nbig = nbig_of(L);
     if (nbig > 0) {
       launch_big<T, true>(f, L, nbig, nrhs, x);
       if (L.max_nb > 0) {
         dim3 g(nbig, (L.max_nb + 31) / 32, (unsigned)nrhs);
-        k_gemv_rect<T, true><<<g, NTH, 0, st>>>(f->d_fronts, pool, f->d_gidx, x, f->n, (T*)f->d_work, f->max_level_idx, L.ioff0, L.f0);
+        k_gemv_rect<T, true><<<g, NTH, 0, st>>>(f->d_fronts, pool, f->d_gidx, x, f->xld, (T*)f->d_work, f->max_level_idx, L.ioff0, L.f0);
         ++s.launches_solve;
       }
     }
     if (nf - nbig > 0) {
       dim3 g(nf - nbig, (unsigned)nrhs);
-      k_sv_small_fwd<T><<<g, NTH, 0, st>>>(f->d_fronts, pool, f->d_gidx, f->d_rperm, x, f->n, L.f0 + nbig);
+      k_sv_small_fwd<T><<<g, NTH, 0, st>>>(f->d_fronts, pool, f->d_gidx, f->d_rperm, x, f->xld, L.f0 + nbig);
       ++s.launches_solve;
     }
+    if (L.thin >= 0) hs_comp_solve(f, f->clevels[L.thin], nrhs, x, true);   // x[bnd] += Qb·(border rows)
   }
-  for (size_t li = f->levels.size(); (which & 2) && li-- > 0;) {  // pre-order
-    const Level& L = f->levels[li];
+  for (size_t li = f->flevels.size(); (which & 2) && li-- > 0;) {  // pre-order
+    const Level& L = f->flevels[li];
     const int nf = L.f1 - L.f0, nbig = nbig_of(L);
+    if (L.thin >= 0) hs_comp_solve(f, f->clevels[L.thin], nrhs, x, false);  // border rows ← Ri·x[bnd]
     if (nbig > 0) {
       dim3 g(nbig, (L.max_ni + 31) / 32, (unsigned)nrhs);
-      k_gemv_rect<T, false><<<g, NTH, 0, st>>>(f->d_fronts, pool, f->d_gidx, x, f->n, (T*)f->d_work, f->max_level_idx, L.ioff0, L.f0);
+      k_gemv_rect<T, false><<<g, NTH, 0, st>>>(f->d_fronts, pool, f->d_gidx, x, f->xld, (T*)f->d_work, f->max_level_idx, L.ioff0, L.f0);
       ++s.launches_solve;
       launch_big<T, false>(f, L, nbig, nrhs, x);
     }
     if (nf - nbig > 0) {
       dim3 g(nf - nbig, (unsigned)nrhs);
       const size_t sm = (size_t)std::max(L.max_nb, 1) * sizeof(T);
-      k_sv_small_bwd<T><<<g, NTH, sm, st>>>(f->d_fronts, pool, f->d_gidx, x, f->n, L.f0 + nbig);
+      k_sv_small_bwd<T><<<g, NTH, sm, st>>>(f->d_fronts, pool, f->d_gidx, x, f->xld, L.f0 + nbig);
       ++s.launches_solve;
     }
   }

@@ -96,6 +96,13 @@ class FactorNode:
         _lib.check(_lib.lib.hs_stats(self._hd.h, C.byref(s)))
         return s.asdict()
 
+    def ranks(self):
+        """``(rank(F.L), rank(F.R))`` of this node — ``LowRankMatrix`` ranks of a compressed node
+        (factorization.jl:173,179), ``(0, 0)`` when ``L`` and ``R`` are dense."""
+        rl, rr = C.c_int64(), C.c_int64()
+        _lib.check(_lib.lib.hs_node_rank(self._hd.h, self._k, C.byref(rl), C.byref(rr)))
+        return int(rl.value), int(rr.value)
+
     def resolved_swlevel(self) -> int:
         v = C.c_int64()
         _lib.check(_lib.lib.hs_resolved_swlevel(self._hd.h, C.byref(v)))

@@ -112,6 +112,7 @@ typedef struct {
   double ms_extend_add;    /* child Schur blocks → parent fronts (part of ms_assemble) */
   double ms_small;         /* fused small-front kernel (levels whose fronts fit in registers) */
   double ms_solve_prep;    /* in-place inversion of the diagonal blocks of L11/U11 (part of the factor time) */
+  double ms_compress;      /* compressed fronts: pivoted QR of A_bi / A_ib, thin fronts, Schur complement      */
 } hs_stats_t;
 
 typedef enum { HS_GET_D = 0, HS_GET_S = 1, HS_GET_L = 2, HS_GET_R = 3, HS_GET_FRONT = 4, HS_GET_PIV = 5 } hs_which;
@@ -183,6 +184,9 @@ int32_t hs_solve(hs_fac* fac, int64_t nrhs, const void* B, int64_t ldb, void* X,
  * [int_loc; bnd_loc]); HS_GET_FRONT returns the raw partially factored front, HS_GET_PIV its pivots (int64). */
 int32_t hs_node_get(hs_fac* fac, int64_t node, hs_which which, void* out, int64_t* dims);
 int32_t hs_maxrank(hs_fac* fac, int64_t* rank);              /* factornode.jl:49-57 */
+/* rank(F.L), rank(F.R) of one node (LowRankMatrix, factorization.jl:173,179); 0, 0 for an uncompressed node whose
+ * L and R are dense.  For a compressed node hs_node_get returns the dense products L = U·Vᴴ, R = U·Vᴴ. */
+int32_t hs_node_rank(hs_fac* fac, int64_t node, int64_t* rank_l, int64_t* rank_r);
 int32_t hs_stats(hs_fac* fac, hs_stats_t* out);
 int32_t hs_resolved_swlevel(hs_fac* fac, int64_t* swlevel);  /* factorization.jl:8 */
 

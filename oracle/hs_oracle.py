@@ -320,10 +320,10 @@ class FactorNode:
         return _blockfact_dense(self.D) if isinstance(self.D, BlockFactorization) else self.D
 
     def L_dense(self):
-        return self.L.dense() if isinstance(self.L, BlockMatrix) else self.L
+        return self.L.dense() if hasattr(self.L, "dense") else self.L
 
     def R_dense(self):
-        return self.R.dense() if isinstance(self.R, BlockMatrix) else self.R
+        return self.R.dense() if hasattr(self.R, "dense") else self.R
 
 
 def _blockfact_dense(F: BlockFactorization) -> np.ndarray:
@@ -362,10 +362,11 @@ def _sub(A, rows, cols) -> np.ndarray:
 
 
 def factor(A, nd: NDNode, nd_loc: NDNode, swlevel: int = 0, **opts) -> FactorNode:
-    """factorization.jl:5-11, uncompressed path only in this file (``swlevel = 0``); the compressed path
-    lives in ``oracle/hs_oracle_hss.py``."""
+    """factorization.jl:5-11.  ``swlevel = 0`` (nothing compressed) is handled in this file; any other value goes
+    to the compressed path in ``oracle/hs_oracle_hss.py``."""
     if swlevel != 0:
-        raise NotImplementedError("compressed path: see oracle/hs_oracle_hss.py")
+        import hs_oracle_hss
+        return hs_oracle_hss.factor(A, nd, nd_loc, swlevel=swlevel, **opts)
     A = sp.csr_matrix(A)
     return _factor(A, nd, nd_loc, 1)
 

@@ -1,0 +1,126 @@
+"""CPU ORACLE, compressed path — test infrastructure only.  NEVER imported by the product package.
+
+Restatement of the reference's ``compression_flag == true`` branch (src/factorization.jl:78-112) in the form the
+CUDA library implements in this round:
+
+* the Gauss transforms ``L ≈ Abi·Aii⁻¹`` and ``R ≈ Aii⁻¹·Aib`` are low-rank, from a truncated column-pivoted QR of
+  the dense coupling blocks (dense-children methods, factorization.jl:171-182) — followed line by line;
+* the Schur complement operator ``S = Abb − (Abi·R.U)·R.Vᴴ`` (factorization.jl:228-249) is *evaluated densely and
+  kept dense*.  The reference hands that operator to ``HssMatrices.randcompress_adaptive`` (factorization.jl:110,
+  third party, source absent) and stores the HSS approximation; here the HSS tolerance is taken to zero.  Because
+  every ``S`` stays dense, the HSS-children methods (``_assemble_blocks`` :126-140, ``_equilibrate_clusters``
+  :143-168, all-HSS ``blockfactor`` blockmatrix.jl:121-130, HSS Gauss transforms :184-209) are never reached.
+* compressed leaves (factorization.jl:45-59) keep dense ``L``, ``R`` exactly like the reference; only their ``S`` would
+  be HSS there — with a dense ``S`` they coincide with the uncompressed leaf.
+
+PARITY UNPINNED (see hs_oracle.py).  ``pqrfact`` is LowRankApprox.jl 0.4.3 (Manifest.toml:427-431, not vendored):
+its truncation rule is RECALLED: partial column-pivoted QR ``A[:,p] ≈ Q·R`` cut at the first
+``k`` with ``|R[k,k]| ≤ max(atol, rtol·|R[1,1]|)``.
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.linalg as sla
+import scipy.sparse as sp
+
+import hs_oracle as base
+from hs_oracle import (BlockMatrix, FactorNode, _assemble_blocks, _factor_leaf, blockfactor, blockldiv_inplace,
+                        blockrdiv_inplace, isbranch, isleaf)
+
+
+class LowRankMatrix:
+    """``LowRankApprox.LowRankMatrix(U, V)`` ≡ ``U·Vᴴ``."""
+
+    def __init__(self, U, V):
+        self.U = np.asarray(U)
+        self.V = np.asarray(V)
+
+    @property
+    def rank(self) -> int:
+        return self.U.shape[1]
+
+    @property
+    def shape(self):
+        return (self.U.shape[0], self.V.shape[0])
+
+    def matmul(self, X):
+        return self.U @ (self.V.conj().T @ X)
+
+    def dense(self):
+        return self.U @ self.V.conj().T
+
+
+def pqrfact(M: np.ndarray, atol: float, rtol: float):
+    """``pqrfact(M; sketch=:none, atol, rtol)`` → ``(Q, R[:, invperm(p)])`` with ``M ≈ Q·R[:, invperm(p)]``."""
+    m, n = M.shape
+    if m == 0 or n == 0:
+        return np.zeros((m, 0), dtype=M.dtype), np.zeros((0, n), dtype=M.dtype)
+    Q, R, p = sla.qr(M, mode="economic", pivoting=True)
+    d = np.abs(np.diag(R))
+    ptol = max(atol, rtol * d[0]) if len(d) else 0.0
+    below = np.nonzero(d <= ptol)[0]
+    k = int(below[0]) if len(below) else len(d)
+    Rk = np.zeros((k, n), dtype=R.dtype)
+    Rk[:, p] = R[:k]          # R[:, invperm(p)]
+    return Q[:, :k], Rk
+
+
+def _lgauss_transform(D, Abi: BlockMatrix, atol, rtol) -> LowRankMatrix:
+    """factorization.jl:171-176."""
+    Q, Rp = pqrfact(Abi.dense(), atol, rtol)
+    L = LowRankMatrix(Q, Rp.conj().T)
+    L.V = blockrdiv_inplace(L.V.conj().T, D).conj().T if L.rank else L.V
+    return L
+
+
+def _rgauss_transform(D, Aib: BlockMatrix, atol, rtol) -> LowRankMatrix:
+    """factorization.jl:177-182."""
+    Q, Rp = pqrfact(Aib.dense(), atol, rtol)
+    R = LowRankMatrix(Q, Rp.conj().T)
+    R.U = blockldiv_inplace(D, R.U) if R.rank else R.U
+    return R
+
+
+def _factor_branch_compressed(A, Fl, Fr, nd, nd_loc, atol, rtol) -> FactorNode:
+    """factorization.jl:78-112 with the Schur operator of :228-249 evaluated densely (module docstring)."""
+    int1 = nd.left.bnd[nd_loc.left.int - 1]
+    bnd1 = nd.left.bnd[nd_loc.left.bnd - 1]
+    int2 = nd.right.bnd[nd_loc.right.int - 1]
+    bnd2 = nd.right.bnd[nd_loc.right.bnd - 1]
+    Aii, Aib, Abi, Abb = _assemble_blocks(A, Fl.S, Fr.S, int1, int2, bnd1, bnd2)
+    D = blockfactor(Aii)                                   # :94
+    L = _lgauss_transform(D, Abi, 0.5 * atol, 0.5 * rtol)  # :99
+    R = _rgauss_transform(D, Aib, 0.5 * atol, 0.5 * rtol)  # :100
+    U = Abi.dense() @ R.U                                  # :230  U = Abi*R
+    S = Abb.dense() - U @ R.V.conj().T                     # :242,:248
+    perm = np.concatenate([nd_loc.int, nd_loc.bnd]) - 1    # :107
+    return FactorNode(D, S[np.ix_(perm, perm)], L, R, nd.int, nd.bnd, nd_loc.int, nd_loc.bnd, Fl, Fr)
+
+
+def factor(A, nd, nd_loc, swlevel=5, swsize=1, atol=1e-6, rtol=1e-6, **_unused) -> FactorNode:
+    """factorization.jl:5-11 — options as ``SolverOptions`` (HierarchicalSolvers.jl:30-40 defaults)."""
+    A = sp.csr_matrix(A)
+    sw = max(base.depth(nd) + swlevel, 0) if swlevel < 0 else swlevel   # :8
+    return _factor(A, nd, nd_loc, 1, sw, swsize, atol, rtol)
+
+
+def _factor(A, nd, nd_loc, level, swlevel, swsize, atol, rtol) -> FactorNode:
+    """factorization.jl:14-27."""
+    compression_flag = level <= swlevel and len(nd.bnd) >= swsize   # :15
+    if isleaf(nd):
+        return _factor_leaf(A, nd, nd_loc)     # :30-42 and :45-59 coincide while S stays dense
+    elif isbranch(nd):
+        Fl = _factor(A, nd.left, nd_loc.left, level + 1, swlevel, swsize, atol, rtol)
+        Fr = _factor(A, nd.right, nd_loc.right, level + 1, swlevel, swsize, atol, rtol)
+        if compression_flag:
+            return _factor_branch_compressed(A, Fl, Fr, nd, nd_loc, atol, rtol)
+        return base._factor_branch(A, Fl, Fr, nd, nd_loc)
+    raise RuntimeError("Expected nested dissection to be a binary tree. Found a node with only one child.")
+
+
+def node_ranks(F: FactorNode):
+    """(rank(L), rank(R)) per node in post-order; (0, 0) for uncompressed nodes."""
+    out = []
+    for X in base.nodes_postorder(F):
+        out.append((X.L.rank if isinstance(X.L, LowRankMatrix) else 0, X.R.rank if isinstance(X.R, LowRankMatrix) else 0))
+    return out

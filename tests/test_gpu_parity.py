@@ -171,8 +171,8 @@ def test_errors_match_reference_exceptions(hs):
     F = hs.factor(Ap, nd, nd_loc, swlevel=0)
     with pytest.raises(hs.DimensionMismatch):
         hs.ldiv(F, np.zeros(Ap.shape[0] + 1))
-    with pytest.raises(NotImplementedError):
-        hs.factor(Ap, nd, nd_loc, swlevel=3, swsize=1)           # compressed path not built yet
+    Fc = hs.factor(Ap, nd, nd_loc, swlevel=3, swsize=1)           # compressed path (tests/test_gpu_compress.py)
+    assert hs.maxrank(Fc) > 0 and Fc.resolved_swlevel() == 3
 
 
 def test_pivoting_is_exercised(hs, orc):
