@@ -7,7 +7,11 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <cstdio>
+#include <exception>
+#include <mutex>
 #include <numeric>
+#include <thread>
 
 #include "hs_fac.cuh"
 #include "hs_internal.h"
@@ -358,7 +362,56 @@ template <typename V> static void dev_upload(V** dst, const V* src, size_t count
   if (count) CUDA_OK(cudaMemcpyAsync(*dst, src, count * sizeof(V), cudaMemcpyHostToDevice, st));
 }
 
+// host-side loops over millions of index entries run on a few threads (the plan build is inside the end-to-end time)
+template <typename Fn> static void parallel_for(int64_t n, Fn&& fn) {
+  static const unsigned nt_max = [] {
+    const char* e = getenv("HS_HOST_THREADS");
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    return e ? (unsigned)std::max(1, atoi(e)) : std::min(hw, 16u);
+  }();
+  const unsigned nt = (unsigned)std::min<int64_t>(nt_max, (n + 16383) / 16384);
+  if (nt <= 1) { fn((int64_t)0, n); return; }
+  std::vector<std::thread> th;
+  std::exception_ptr ep;
+  std::mutex mu;
+  const int64_t chunk = (n + nt - 1) / nt;
+  for (unsigned t = 0; t < nt; ++t) {
+    const int64_t lo = t * chunk, hi = std::min<int64_t>(n, lo + chunk);
+    if (lo >= hi) break;
+    th.emplace_back([&, lo, hi] {
+      try { fn(lo, hi); } catch (...) { std::lock_guard<std::mutex> g(mu); if (!ep) ep = std::current_exception(); }
+    });
+  }
+  for (auto& x : th) x.join();
+  if (ep) std::rethrow_exception(ep);
+}
+
+// int table whose pages are first touched by the threads that fill it (std::vector would zero-fill it serially)
+struct IntBuf {
+  std::unique_ptr<int[]> p;
+  size_t n = 0, cap = 0;
+  void alloc(size_t c) { p.reset(new int[std::max<size_t>(c, 1)]); cap = c; n = 0; }
+  void set_size(size_t m) { if (m > cap) throw hs_error(HS_ECUDA, "plan table overflow"); n = m; }
+  void resize(size_t m, int fill) { const size_t o = n; set_size(m); for (size_t i = o; i < m; ++i) p[i] = fill; }
+  void push_back(int v) { set_size(n + 1); p[n - 1] = v; }
+  int* data() { return p.get(); }
+  size_t size() const { return n; }
+  int& operator[](size_t i) { return p[i]; }
+};
+
+struct PlanClock {
+  bool on = getenv("HS_PLAN_TIMING") != nullptr;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  void tick(const char* what) {
+    if (!on) return;
+    auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[plan] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+
 static void build_plan(hs_fac* f, const hs_tree* t) {
+  PlanClock clk;
   const int64_t nn = t->nnodes, base = t->index_base;
   if (nn <= 0) throw hs_error(HS_EARG, "hs_factor: empty tree");
   f->nnodes = nn;
@@ -400,14 +453,27 @@ static void build_plan(hs_fac* f, const hs_tree* t) {
   }
   const int64_t maxlev = *std::max_element(f->level.begin(), f->level.end());
   f->depth = maxlev;
+  clk.tick("tree links + levels");
   auto copy0 = [&](const int64_t* ptr, const int64_t* idx, std::vector<int64_t>& p, std::vector<int64_t>& v) {
     p.assign(ptr, ptr + nn + 1);
-    v.assign(idx, idx + p[nn]);
-    for (auto& x : v) x -= base;
+    if (p[0] != 0 || p[nn] < 0) throw hs_error(HS_EARG, "hs_factor: malformed index pointer array");
+    for (int64_t k = 0; k < nn; ++k)
+      if (p[k + 1] < p[k]) throw hs_error(HS_EARG, "hs_factor: malformed index pointer array");
+    v.resize(p[nn]);
+    int64_t* dst = v.data();
+    parallel_for(p[nn], [&](int64_t lo, int64_t hi) { for (int64_t q = lo; q < hi; ++q) dst[q] = idx[q] - base; });
   };
-  std::vector<int64_t> int_ptr, int_idx, bnd_ptr, bnd_idx;
-  copy0(t->int_ptr, t->int_idx, int_ptr, int_idx);
-  copy0(t->bnd_ptr, t->bnd_idx, bnd_ptr, bnd_idx);
+  // int / bnd (global DOFs) are only read while the plan is built: used in place, `base` applied on the fly
+  auto copy_ptr = [&](const int64_t* ptr, std::vector<int64_t>& p) {
+    p.assign(ptr, ptr + nn + 1);
+    if (p[0] != 0) throw hs_error(HS_EARG, "hs_factor: malformed index pointer array");
+    for (int64_t k = 0; k < nn; ++k)
+      if (p[k + 1] < p[k]) throw hs_error(HS_EARG, "hs_factor: malformed index pointer array");
+  };
+  std::vector<int64_t> int_ptr, bnd_ptr;
+  copy_ptr(t->int_ptr, int_ptr);
+  copy_ptr(t->bnd_ptr, bnd_ptr);
+  const int64_t *int_idx = t->int_idx, *bnd_idx = t->bnd_idx;
   copy0(t->iloc_ptr, t->iloc_idx, f->iloc_ptr, f->iloc_idx);
   copy0(t->bloc_ptr, t->bloc_idx, f->bloc_ptr, f->bloc_idx);
   f->node_ni.resize(nn);
@@ -417,12 +483,20 @@ static void build_plan(hs_fac* f, const hs_tree* t) {
     f->node_nb[k] = (int)(bnd_ptr[k + 1] - bnd_ptr[k]);
     if ((int64_t)f->node_ni[k] + f->node_nb[k] > (1 << 30)) throw hs_error(HS_ESIZE, "front too large");
   }
-  for (int64_t v : int_idx) if (v < 0 || v >= f->n) throw hs_error(HS_EARG, "hs_factor: DOF index out of range in int");
-  for (int64_t v : bnd_idx) if (v < 0 || v >= f->n) throw hs_error(HS_EARG, "hs_factor: DOF index out of range in bnd");
+  clk.tick("copy index sets");
+  parallel_for(int_ptr[nn], [&](int64_t lo, int64_t hi) {
+    for (int64_t q = lo; q < hi; ++q)
+      if (int_idx[q] < base || int_idx[q] - base >= f->n) throw hs_error(HS_EARG, "hs_factor: DOF index out of range in int");
+  });
+  parallel_for(bnd_ptr[nn], [&](int64_t lo, int64_t hi) {
+    for (int64_t q = lo; q < hi; ++q)
+      if (bnd_idx[q] < base || bnd_idx[q] - base >= f->n) throw hs_error(HS_EARG, "hs_factor: DOF index out of range in bnd");
+  });
   // consistency of (nd, nd_loc): a branch's sets are the concatenation of its children's selected boundary rows
   // (nesteddissection.jl:64-65, factorization.jl:63-64)
   auto nloc = [&](const std::vector<int64_t>& p, int64_t k) { return p[k + 1] - p[k]; };
-  for (int64_t k = 0; k < nn; ++k) {
+  parallel_for(nn, [&](int64_t klo, int64_t khi) {
+  for (int64_t k = klo; k < khi; ++k) {
     if (f->left[k] < 0) continue;
     const int64_t l = f->left[k], r = f->right[k];
     const int64_t nil = nloc(f->iloc_ptr, l), nir = nloc(f->iloc_ptr, r), nbl = nloc(f->bloc_ptr, l), nbr = nloc(f->bloc_ptr, r);
@@ -436,11 +510,13 @@ static void build_plan(hs_fac* f, const hs_tree* t) {
           throw hs_error(HS_EARG, "hs_factor: (nd, nd_loc) inconsistent — was the tree produced by symfact!?");
       }
     };
-    chk(l, f->iloc_ptr, f->iloc_idx, int_idx.data() + int_ptr[k]);
-    chk(r, f->iloc_ptr, f->iloc_idx, int_idx.data() + int_ptr[k] + nil);
-    chk(l, f->bloc_ptr, f->bloc_idx, bnd_idx.data() + bnd_ptr[k]);
-    chk(r, f->bloc_ptr, f->bloc_idx, bnd_idx.data() + bnd_ptr[k] + nbl);
+    chk(l, f->iloc_ptr, f->iloc_idx, int_idx + int_ptr[k]);
+    chk(r, f->iloc_ptr, f->iloc_idx, int_idx + int_ptr[k] + nil);
+    chk(l, f->bloc_ptr, f->bloc_idx, bnd_idx + bnd_ptr[k]);
+    chk(r, f->bloc_ptr, f->bloc_idx, bnd_idx + bnd_ptr[k] + nbl);
   }
+  });
+  clk.tick("validate");
   // swlevel < 0 is relative to the tree depth (factorization.jl:8);
   // compression_flag = (level ≤ swlevel) && (|bnd| ≥ swsize) (factorization.jl:15).  Compressed leaves keep dense
   // L and R in the reference too (:45-59) and S stays dense here, so only branches change.
@@ -465,7 +541,7 @@ static void build_plan(hs_fac* f, const hs_tree* t) {
   f->node2front.assign(nn, -1);
   for (int i = 0; i < (int)nn; ++i) f->node2front[order[i]] = i;
   f->root_front = f->node2front[root];
-  std::vector<int> gidx, cmap;
+  IntBuf gidx, cmap;
   long long poff = 0, ioff = 0;
   const long long align = 32;
   f->levels.clear();
@@ -499,10 +575,6 @@ static void build_plan(hs_fac* f, const hs_tree* t) {
     poff += ((long long)fr.ld * fr.n + align - 1) / align * align;
     ioff += fr.n;
     L.ioff1 = ioff; L.poff1 = poff;
-    // per-row tables
-    gidx.insert(gidx.end(), int_idx.begin() + int_ptr[k], int_idx.begin() + int_ptr[k + 1]);
-    gidx.insert(gidx.end(), bnd_idx.begin() + bnd_ptr[k], bnd_idx.begin() + bnd_ptr[k + 1]);
-    cmap.resize(ioff, -1);
     const double ni = fr.ni, nb = fr.n - fr.ni;
     flops += 2.0 / 3.0 * ni * ni * ni + 2.0 * ni * ni * nb + 2.0 * ni * nb * nb;
     sbytes += ni * ni + 2.0 * ni * nb;
@@ -510,9 +582,30 @@ static void build_plan(hs_fac* f, const hs_tree* t) {
     max_ni = std::max<int64_t>(max_ni, fr.ni);
     max_nb = std::max<int64_t>(max_nb, fr.n - fr.ni);
   }
+  clk.tick("front descriptors");
+  // per-row tables: global DOF of every front row
+  {
+    size_t cap = (size_t)ioff + (pseudo ? f->node_nb[root] : 0);
+    for (int64_t k = 0; k < nn; ++k)
+      if (cflag[k]) cap += (size_t)f->node_ni[k] + std::min(f->node_ni[k], f->node_nb[k]);  // thin descriptors
+    gidx.alloc(cap); cmap.alloc(cap);
+    gidx.set_size(ioff); cmap.set_size(ioff);
+  }
+  parallel_for(nn, [&](int64_t lo, int64_t hi) {
+    for (int64_t i = lo; i < hi; ++i) {
+      const int64_t k = order[i];
+      int* g = gidx.data() + f->fronts[i].ioff;
+      int* cm = cmap.data() + f->fronts[i].ioff;
+      for (int q = 0; q < f->fronts[i].n; ++q) cm[q] = -1;
+      for (int64_t q = int_ptr[k]; q < int_ptr[k + 1]; ++q) *g++ = (int)(int_idx[q] - base);
+      for (int64_t q = bnd_ptr[k]; q < bnd_ptr[k + 1]; ++q) *g++ = (int)(bnd_idx[q] - base);
+    }
+  });
+  clk.tick("gidx");
   // child → parent row maps: the children's S[perm,perm] lands as diagonal blocks of the parent front
   // (factorization.jl:41,74 and :118-121)
-  for (int64_t k = 0; k < nn; ++k) {
+  parallel_for(nn, [&](int64_t klo, int64_t khi) {
+  for (int64_t k = klo; k < khi; ++k) {
     if (f->left[k] < 0) continue;
     const int64_t l = f->left[k], r = f->right[k];
     const int nil = (int)nloc(f->iloc_ptr, l), nbl = (int)nloc(f->bloc_ptr, l), nip = f->node_ni[k];
@@ -525,6 +618,8 @@ static void build_plan(hs_fac* f, const hs_tree* t) {
     fill(l, 0, 0);
     fill(r, nil, nbl);
   }
+  });
+  clk.tick("cmap");
   if (pseudo) {  // root boundary solve `F.S \ C[F.bnd,:]` (factornode.jl:72) as one more dense front
     const Front& rf = f->fronts[f->root_front];
     Front& pf = f->fronts[nn];
@@ -540,7 +635,7 @@ static void build_plan(hs_fac* f, const hs_tree* t) {
     L.ni_sorted.push_back(pf.ni);
     f->levels.push_back(L);
     f->pseudo_front = (int)nn;
-    gidx.insert(gidx.end(), bnd_idx.begin() + bnd_ptr[root], bnd_idx.begin() + bnd_ptr[root + 1]);
+    for (int64_t q = bnd_ptr[root]; q < bnd_ptr[root + 1]; ++q) gidx.push_back((int)(bnd_idx[q] - base));
     ioff += pf.n;
     cmap.resize(ioff, -1);
     const double ni = pf.ni;
@@ -620,8 +715,10 @@ static void build_plan(hs_fac* f, const hs_tree* t) {
   s.singular_front = s.singular_col = -1;
   s.maxrank = 0;
   // upload
+  clk.tick("levels + stats");
   cudaStream_t st = f->ctx->stream;
   CUDA_OK(cudaMalloc(&f->pool, std::max<size_t>((size_t)poff, 1) * f->esz));
+  clk.tick("cudaMalloc pool");
   dev_upload(&f->d_fronts, f->fronts.data(), f->fronts.size(), st);
   dev_upload(&f->d_gidx, gidx.data(), gidx.size(), st);
   dev_upload(&f->d_cmap, cmap.data(), cmap.size(), st);
@@ -634,6 +731,7 @@ static void build_plan(hs_fac* f, const hs_tree* t) {
   CUDA_OK(cudaMemsetAsync(f->d_ipiv, 0, std::max<size_t>(ioff, 1) * sizeof(int), st));
   CUDA_OK(cudaMemsetAsync(f->d_rperm, 0, std::max<size_t>(ioff, 1) * sizeof(int), st));
   CUDA_OK(cudaStreamSynchronize(st));  // host vectors go out of scope
+  clk.tick("upload tables");
   hs_comp_plan(f);
 }
 

@@ -124,22 +124,50 @@ __global__ void __launch_bounds__(256) k_id_step(const IdRun* __restrict__ runs,
     ints[R.ip + k] = p;
   }
   const double inv = 1.0 / rkk;
-  for (int j = blockIdx.y * 8 + warp; j < R.ncol; j += gridDim.y * 8) {
-    const double dj = din[j];
-    T* Rj = ws + R.rws + (long long)j * R.ldr;
-    if (dj < 0.0 || j == p) {  // an earlier pivot (its row-k entry vanishes) or this step's pivot
-      if (lane == 0) { Rj[k] = j == p ? from_real(rkk, (T*)nullptr) : hs_zero<T>(); dout[j] = -1.0; }
-      continue;
+  // two columns per warp and trip: twice the loads in flight
+  const int stride = gridDim.y * 8;
+  for (int ja = blockIdx.y * 8 + warp; ja < R.ncol; ja += 2 * stride) {
+    const int jb = ja + stride;
+    const bool hb = jb < R.ncol;
+    const double da = din[ja], db = hb ? din[jb] : -1.0;
+    T* Ra = ws + R.rws + (long long)ja * R.ldr;
+    T* Rb = ws + R.rws + (long long)(hb ? jb : ja) * R.ldr;
+    const bool sa = da < 0.0 || ja == p, sb = !hb || db < 0.0 || jb == p;  // earlier pivots / this step's pivot
+    T acca = hs_zero<T>(), accb = hs_zero<T>();
+    if (!sa && !sb) {
+      const T* Ma = pool + R.moff + (long long)ja * R.ld;
+      const T* Mb = pool + R.moff + (long long)jb * R.ld;
+      T a2 = hs_zero<T>(), b2 = hs_zero<T>();
+#pragma unroll 4
+      for (int i = lane; i < R.m; i += 32) { const T c = colp[i]; acca = cjfma(acca, c, Ma[i]); accb = cjfma(accb, c, Mb[i]); }
+      for (int l = lane; l < k; l += 32) { const T c = rp[l]; a2 = cjfma(a2, c, Ra[l]); b2 = cjfma(b2, c, Rb[l]); }
+      acca = hs_sub(acca, a2); accb = hs_sub(accb, b2);
+    } else {
+      if (!sa) {
+        const T* Ma = pool + R.moff + (long long)ja * R.ld;
+        T a2 = hs_zero<T>();
+#pragma unroll 4
+        for (int i = lane; i < R.m; i += 32) acca = cjfma(acca, colp[i], Ma[i]);
+        for (int l = lane; l < k; l += 32) a2 = cjfma(a2, rp[l], Ra[l]);
+        acca = hs_sub(acca, a2);
+      }
+      if (!sb) {
+        const T* Mb = pool + R.moff + (long long)jb * R.ld;
+        T b2 = hs_zero<T>();
+#pragma unroll 4
+        for (int i = lane; i < R.m; i += 32) accb = cjfma(accb, colp[i], Mb[i]);
+        for (int l = lane; l < k; l += 32) b2 = cjfma(b2, rp[l], Rb[l]);
+        accb = hs_sub(accb, b2);
+      }
     }
-    const T* Mj = pool + R.moff + (long long)j * R.ld;
-    T acc = hs_zero<T>(), acc2 = hs_zero<T>();
-    for (int i = lane; i < R.m; i += 32) acc = cjfma(acc, colp[i], Mj[i]);
-    for (int l = lane; l < k; l += 32) acc2 = cjfma(acc2, rp[l], Rj[l]);
-    acc = wsum(hs_sub(acc, acc2));
+    acca = wsum(acca); accb = wsum(accb);
     if (lane == 0) {
-      const T v = scal(acc, inv);
-      Rj[k] = v;
-      dout[j] = fmax(dj - abs2(v), 0.0);
+      if (sa) { Ra[k] = ja == p ? from_real(rkk, (T*)nullptr) : hs_zero<T>(); dout[ja] = -1.0; }
+      else { const T v = scal(acca, inv); Ra[k] = v; dout[ja] = fmax(da - abs2(v), 0.0); }
+      if (hb) {
+        if (sb) { Rb[k] = jb == p ? from_real(rkk, (T*)nullptr) : hs_zero<T>(); dout[jb] = -1.0; }
+        else { const T v = scal(accb, inv); Rb[k] = v; dout[jb] = fmax(db - abs2(v), 0.0); }
+      }
     }
   }
 }
@@ -332,7 +360,7 @@ template <typename T> void prepare_impl(hs_fac* f, CompLevel& C) {
     CUDA_OK(cudaGetLastError());
     ++f->stats.launches_factor;
   }
-  const int ny = std::max(1, std::min((max_ncol + 7) / 8, (2 * 148 + nruns - 1) / nruns));
+  const int ny = std::max(1, std::min((max_ncol + 15) / 16, (6 * 148 + nruns - 1) / nruns));
   const double atol = 0.5 * f->opts.atol, rtol = 0.5 * f->opts.rtol;  // factorization.jl:99-100
   int k = 0, done = 0;
   while (done < nruns && k <= max_rcap) {

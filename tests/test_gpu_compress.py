@@ -112,3 +112,23 @@ def test_compression_options_semantics(hs, orc):
     x1 = hs.ldiv(F, prob.b)
     F.refactor(A)
     assert np.allclose(hs.ldiv(F, prob.b), x1, rtol=1e-12, atol=0)
+
+
+def test_baseline_config2_standin(hs, orc):
+    """BASELINE config 2 (poisson2d_p1_h128_nmax100 + compression, test/rungmres.jl:39) on the 129×129 stand-in.  With
+    rungmres.jl's swsize = 480 no boundary of the 5-point stand-in qualifies (SURVEY §8d), so swsize = 64 is used;
+    atol = rtol = 1e-2, swlevel = -2 as in the script."""
+    import hs_oracle_hss as oh
+    prob = hs.grid_problem((129, 129), "poisson", nmax=100)
+    opts = dict(swlevel=-2, swsize=64, atol=1e-2, rtol=1e-2, kest=200, stepsize=100, leafsize=120)
+    Ap, Fo, F = _both(hs, orc, prob, **opts)
+    assert hs.maxrank(F) > 0 and abs(hs.maxrank(F) - orc.maxrank(Fo)) <= 1
+    ro = oh.node_ranks(Fo)
+    assert sum(r != (0, 0) for r in ro) == sum(F.node(k).ranks() != (0, 0) for k in range(len(ro))) > 0
+    b = prob.b
+    _, reso, convo = orc.gmres(Ap, b, Pr=lambda v: orc.ldiv(Fo, v), reltol=1e-9, restart=30, maxiter=30)
+    xs, ch = hs.gmres(sp.csc_matrix(Ap), b, Pr=F, reltol=1e-9, restart=30, maxiter=30, log=True)
+    assert ch.isconverged == convo and abs(ch.iters - len(reso)) <= 1
+    # same preconditioner quality: residual histories agree to the compression tolerance
+    m = min(ch.iters, len(reso))
+    assert np.allclose(np.log10(np.asarray(ch.resnorm)[:m]), np.log10(np.asarray(reso)[:m]), atol=0.5)
