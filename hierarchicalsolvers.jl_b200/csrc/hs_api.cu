@@ -59,7 +59,10 @@ extern "C" int32_t hs_create(hs_ctx** out, int32_t device) {
     int lo = 0, hi = 0;  // numerically lower = higher priority
     CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     CUDA_OK(cudaStreamCreateWithPriority(&c->aux_stream, cudaStreamNonBlocking, hi));
+    if (!getenv("HS_NO_PREP_OVERLAP")) CUDA_OK(cudaStreamCreateWithPriority(&c->prep_stream, cudaStreamNonBlocking, lo));
   }
+  CUDA_OK(cudaEventCreateWithFlags(&c->ev_p0, cudaEventDisableTiming));
+  CUDA_OK(cudaEventCreateWithFlags(&c->ev_p1, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&c->ev_c2, cudaEventDisableTiming));
   if (getenv("HS_LOOKAHEAD")) c->lookahead_max_fronts = atoi(getenv("HS_LOOKAHEAD"));
@@ -104,6 +107,9 @@ extern "C" int32_t hs_destroy(hs_ctx* ctx) {
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   cudaFree(ctx->gm_buf);
   if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+  if (ctx->prep_stream) cudaStreamDestroy(ctx->prep_stream);
+  if (ctx->ev_p0) cudaEventDestroy(ctx->ev_p0);
+  if (ctx->ev_p1) cudaEventDestroy(ctx->ev_p1);
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
   if (ctx->ev_c2) cudaEventDestroy(ctx->ev_c2);
   delete ctx;
@@ -132,6 +138,22 @@ struct PhaseTimer {
     }
   }
 };
+
+// solve preparation (in-place inversion of the diagonal blocks of L11/U11): nothing in the rest of the factorization
+// reads a finished pivot block, so it runs on a low-priority side stream; numeric() joins it at the end.  Thin fronts
+// need it at once (hs_comp_schur back-substitutes with the inverted blocks).
+static void solve_prep(hs_fac* f, const Level& L) {
+  hs_ctx* c = f->ctx;
+  if (c->profile || L.thin >= 0 || !c->prep_stream) {
+    PhaseTimer t(f, &f->stats.ms_solve_prep);
+    hs_solve_prep(f, L, c->stream);
+    return;
+  }
+  CUDA_OK(cudaEventRecord(c->ev_p0, c->stream));
+  CUDA_OK(cudaStreamWaitEvent(c->prep_stream, c->ev_p0, 0));
+  hs_solve_prep(f, L, c->prep_stream);
+  c->prep_pending = true;
+}
 
 template <typename T> struct PanelW;  // widest register tile per scalar type
 template <> struct PanelW<double> { static constexpr int W0 = 64; };
@@ -163,8 +185,7 @@ template <typename T> static void factor_level(hs_fac* f, const Level& L) {
       PhaseTimer t(f, &f->stats.ms_small);
       hs_small_factor(f, L);
     }
-    PhaseTimer t(f, &f->stats.ms_solve_prep);
-    hs_solve_prep(f, L);
+    solve_prep(f, L);
     return;
   }
   const int W = hs_panel_width(f, L.max_n, L.f1 - L.f0);
@@ -266,8 +287,7 @@ template <typename T> static void factor_level(hs_fac* f, const Level& L) {
     CUDA_OK(cudaGetLastError());
     f->stats.launches_factor += 1;
     // solve preparation: invert the diagonal blocks of L11/U11 in place (see hs_solve.cu)
-    PhaseTimer t(f, &f->stats.ms_solve_prep);
-    hs_solve_prep(f, L);
+    solve_prep(f, L);
   }
 }
 
@@ -328,6 +348,11 @@ template <typename T> static void numeric(hs_fac* f) {
       hs_comp_schur(f, C);
     }
   }
+  if (f->ctx->prep_pending) {
+    CUDA_OK(cudaEventRecord(f->ctx->ev_p1, f->ctx->prep_stream));
+    CUDA_OK(cudaStreamWaitEvent(st, f->ctx->ev_p1, 0));
+    f->ctx->prep_pending = false;
+  }
   CUDA_OK(cudaEventRecord(f->ev1, st));
   f->ctx->launches += s.launches_factor;
   int info[4];
@@ -386,19 +411,6 @@ template <typename Fn> static void parallel_for(int64_t n, Fn&& fn) {
   if (ep) std::rethrow_exception(ep);
 }
 
-// int table whose pages are first touched by the threads that fill it (std::vector would zero-fill it serially)
-struct IntBuf {
-  std::unique_ptr<int[]> p;
-  size_t n = 0, cap = 0;
-  void alloc(size_t c) { p.reset(new int[std::max<size_t>(c, 1)]); cap = c; n = 0; }
-  void set_size(size_t m) { if (m > cap) throw hs_error(HS_ECUDA, "plan table overflow"); n = m; }
-  void resize(size_t m, int fill) { const size_t o = n; set_size(m); for (size_t i = o; i < m; ++i) p[i] = fill; }
-  void push_back(int v) { set_size(n + 1); p[n - 1] = v; }
-  int* data() { return p.get(); }
-  size_t size() const { return n; }
-  int& operator[](size_t i) { return p[i]; }
-};
-
 struct PlanClock {
   bool on = getenv("HS_PLAN_TIMING") != nullptr;
   std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
@@ -454,15 +466,6 @@ static void build_plan(hs_fac* f, const hs_tree* t) {
   const int64_t maxlev = *std::max_element(f->level.begin(), f->level.end());
   f->depth = maxlev;
   clk.tick("tree links + levels");
-  auto copy0 = [&](const int64_t* ptr, const int64_t* idx, std::vector<int64_t>& p, std::vector<int64_t>& v) {
-    p.assign(ptr, ptr + nn + 1);
-    if (p[0] != 0 || p[nn] < 0) throw hs_error(HS_EARG, "hs_factor: malformed index pointer array");
-    for (int64_t k = 0; k < nn; ++k)
-      if (p[k + 1] < p[k]) throw hs_error(HS_EARG, "hs_factor: malformed index pointer array");
-    v.resize(p[nn]);
-    int64_t* dst = v.data();
-    parallel_for(p[nn], [&](int64_t lo, int64_t hi) { for (int64_t q = lo; q < hi; ++q) dst[q] = idx[q] - base; });
-  };
   // int / bnd (global DOFs) are only read while the plan is built: used in place, `base` applied on the fly
   auto copy_ptr = [&](const int64_t* ptr, std::vector<int64_t>& p) {
     p.assign(ptr, ptr + nn + 1);
@@ -474,8 +477,21 @@ static void build_plan(hs_fac* f, const hs_tree* t) {
   copy_ptr(t->int_ptr, int_ptr);
   copy_ptr(t->bnd_ptr, bnd_ptr);
   const int64_t *int_idx = t->int_idx, *bnd_idx = t->bnd_idx;
-  copy0(t->iloc_ptr, t->iloc_idx, f->iloc_ptr, f->iloc_idx);
-  copy0(t->bloc_ptr, t->bloc_idx, f->bloc_ptr, f->bloc_idx);
+  auto copy_loc = [&](const int64_t* ptr, const int64_t* idx, std::vector<int64_t>& p, IntBuf& v) {
+    copy_ptr(ptr, p);
+    v.reserve(p[nn]);
+    v.set_size(p[nn]);
+    int* dst = v.data();
+    parallel_for(p[nn], [&](int64_t lo, int64_t hi) {
+      for (int64_t q = lo; q < hi; ++q) {
+        const int64_t a = idx[q] - base;
+        if (a < 0 || a >= (1ll << 30)) throw hs_error(HS_EARG, "hs_factor: nd_loc position out of range");
+        dst[q] = (int)a;
+      }
+    });
+  };
+  copy_loc(t->iloc_ptr, t->iloc_idx, f->iloc_ptr, f->iloc_idx);
+  copy_loc(t->bloc_ptr, t->bloc_idx, f->bloc_ptr, f->bloc_idx);
   f->node_ni.resize(nn);
   f->node_nb.resize(nn);
   for (int64_t k = 0; k < nn; ++k) {
@@ -502,7 +518,7 @@ static void build_plan(hs_fac* f, const hs_tree* t) {
     const int64_t nil = nloc(f->iloc_ptr, l), nir = nloc(f->iloc_ptr, r), nbl = nloc(f->bloc_ptr, l), nbr = nloc(f->bloc_ptr, r);
     if (nil + nir != f->node_ni[k] || nbl + nbr != f->node_nb[k])
       throw hs_error(HS_EDIM, "hs_factor: node " + std::to_string(k) + " int/bnd sizes do not match its children's nd_loc");
-    auto chk = [&](int64_t c, const std::vector<int64_t>& lp, const std::vector<int64_t>& li, const int64_t* dst) {
+    auto chk = [&](int64_t c, const std::vector<int64_t>& lp, IntBuf& li, const int64_t* dst) {
       for (int64_t q = lp[c]; q < lp[c + 1]; ++q) {
         const int64_t a = li[q];
         if (a < 0 || a >= f->node_nb[c]) throw hs_error(HS_EARG, "hs_factor: nd_loc position out of range");
@@ -541,7 +557,7 @@ static void build_plan(hs_fac* f, const hs_tree* t) {
   f->node2front.assign(nn, -1);
   for (int i = 0; i < (int)nn; ++i) f->node2front[order[i]] = i;
   f->root_front = f->node2front[root];
-  IntBuf gidx, cmap;
+  IntBuf &gidx = f->ctx->sc_gidx, &cmap = f->ctx->sc_cmap;  // grow-only scratch: no page faults after the first call
   long long poff = 0, ioff = 0;
   const long long align = 32;
   f->levels.clear();
@@ -588,7 +604,7 @@ static void build_plan(hs_fac* f, const hs_tree* t) {
     size_t cap = (size_t)ioff + (pseudo ? f->node_nb[root] : 0);
     for (int64_t k = 0; k < nn; ++k)
       if (cflag[k]) cap += (size_t)f->node_ni[k] + std::min(f->node_ni[k], f->node_nb[k]);  // thin descriptors
-    gidx.alloc(cap); cmap.alloc(cap);
+    gidx.reserve(cap); cmap.reserve(cap);
     gidx.set_size(ioff); cmap.set_size(ioff);
   }
   parallel_for(nn, [&](int64_t lo, int64_t hi) {
@@ -767,46 +783,63 @@ static int32_t factor_impl(hs_ctx* ctx, hs_dtype dtype, int64_t n, const int64_t
   check_opts(f->opts);
   CUDA_OK(cudaEventCreate(&f->ev0));
   CUDA_OK(cudaEventCreate(&f->ev1));
-  build_plan(f.get(), tree);
+  // the matrix goes to the device on a second host thread (pageable copies block their caller) while this one builds
+  // the plan; it uses the look-ahead stream, which is idle until the numeric phase
+  const int64_t base = (flags & HS_CSC_ZERO_BASED) ? 0 : tree->index_base;
+  hs_fac* fp = f.get();
+  double ms_up = 0;
+  auto upload = [&, fp]() {
+    auto t0 = std::chrono::steady_clock::now();
+    CUDA_OK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->aux_stream;
+    CUDA_OK(cudaMalloc((void**)&fp->d_colptr, (size_t)(n + 1) * sizeof(long long)));
+    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    int64_t last = 0;
+    if (on_device) {
+      CUDA_OK(cudaMemcpyAsync(&last, colptr + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+      CUDA_OK(cudaStreamSynchronize(st));
+    } else last = idx32 ? (int64_t)((const int32_t*)colptr)[n] : colptr[n];
+    fp->nnz = last - (on_device ? 0 : base);
+    if (fp->nnz < 0) throw hs_error(HS_EARG, "hs_factor: negative nnz");
+    CUDA_OK(cudaMalloc((void**)&fp->d_rowval, std::max<size_t>(fp->nnz, 1) * sizeof(long long)));
+    CUDA_OK(cudaMalloc(&fp->d_nzval, std::max<size_t>(fp->nnz, 1) * fp->esz));
+    if (idx32) {
+      // int32 index arrays (SciPy): stage in a scratch buffer, widen to int64 on the device
+      int* t32 = nullptr;
+      CUDA_OK(cudaMalloc((void**)&t32, (size_t)(n + 1 + std::max<int64_t>(fp->nnz, 1)) * sizeof(int)));
+      CUDA_OK(cudaMemcpyAsync(t32, colptr, (size_t)(n + 1) * sizeof(int), kind, st));
+      CUDA_OK(cudaMemcpyAsync(t32 + n + 1, rowval, (size_t)fp->nnz * sizeof(int), kind, st));
+      k_widen_index<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(fp->d_colptr, t32, n + 1, base);
+      if (fp->nnz) k_widen_index<<<(unsigned)((fp->nnz + 255) / 256), 256, 0, st>>>(fp->d_rowval, t32 + n + 1, fp->nnz, base);
+      CUDA_OK(cudaStreamSynchronize(st));
+      cudaFree(t32);
+    } else {
+      CUDA_OK(cudaMemcpyAsync(fp->d_colptr, colptr, (size_t)(n + 1) * sizeof(long long), kind, st));
+      CUDA_OK(cudaMemcpyAsync(fp->d_rowval, rowval, (size_t)fp->nnz * sizeof(long long), kind, st));
+      if (!on_device && base != 0) {
+        k_shift_index<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(fp->d_colptr, n + 1, base);
+        if (fp->nnz) k_shift_index<<<(unsigned)((fp->nnz + 255) / 256), 256, 0, st>>>(fp->d_rowval, fp->nnz, base);
+      }
+    }
+    CUDA_OK(cudaMemcpyAsync(fp->d_nzval, nzval, (size_t)fp->nnz * fp->esz, kind, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    ms_up = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  };
+  std::exception_ptr up_err;
+  std::thread up_thread([&] { try { upload(); } catch (...) { up_err = std::current_exception(); } });
+  try { build_plan(f.get(), tree); } catch (...) { up_thread.join(); throw; }
   auto t_plan = std::chrono::steady_clock::now();
   f->stats.ms_analyze = std::chrono::duration<double, std::milli>(t_plan - t_begin).count();
-  // matrix
-  cudaStream_t st = ctx->stream;
-  const int64_t base = (flags & HS_CSC_ZERO_BASED) ? 0 : tree->index_base;
-  CUDA_OK(cudaMalloc((void**)&f->d_colptr, (size_t)(n + 1) * sizeof(long long)));
-  const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-  int64_t last = 0;
-  if (on_device) {
-    CUDA_OK(cudaMemcpyAsync(&last, colptr + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaStreamSynchronize(st));
-  } else last = idx32 ? (int64_t)((const int32_t*)colptr)[n] : colptr[n];
-  f->nnz = last - (on_device ? 0 : base);
-  if (f->nnz < 0) return hs_fail(HS_EARG, "hs_factor: negative nnz");
-  CUDA_OK(cudaMalloc((void**)&f->d_rowval, std::max<size_t>(f->nnz, 1) * sizeof(long long)));
-  CUDA_OK(cudaMalloc(&f->d_nzval, std::max<size_t>(f->nnz, 1) * f->esz));
-  if (idx32) {
-    // int32 index arrays (SciPy): stage in a scratch buffer, widen to int64 on the device
-    int* t32 = nullptr;
-    CUDA_OK(cudaMalloc((void**)&t32, (size_t)(n + 1 + std::max<int64_t>(f->nnz, 1)) * sizeof(int)));
-    CUDA_OK(cudaMemcpyAsync(t32, colptr, (size_t)(n + 1) * sizeof(int), kind, st));
-    CUDA_OK(cudaMemcpyAsync(t32 + n + 1, rowval, (size_t)f->nnz * sizeof(int), kind, st));
-    k_widen_index<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(f->d_colptr, t32, n + 1, base);
-    if (f->nnz) k_widen_index<<<(unsigned)((f->nnz + 255) / 256), 256, 0, st>>>(f->d_rowval, t32 + n + 1, f->nnz, base);
-    CUDA_OK(cudaStreamSynchronize(st));
-    cudaFree(t32);
-  } else {
-    CUDA_OK(cudaMemcpyAsync(f->d_colptr, colptr, (size_t)(n + 1) * sizeof(long long), kind, st));
-    CUDA_OK(cudaMemcpyAsync(f->d_rowval, rowval, (size_t)f->nnz * sizeof(long long), kind, st));
-    if (!on_device && base != 0) {
-      k_shift_index<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(f->d_colptr, n + 1, base);
-      if (f->nnz) k_shift_index<<<(unsigned)((f->nnz + 255) / 256), 256, 0, st>>>(f->d_rowval, f->nnz, base);
-    }
-  }
-  CUDA_OK(cudaMemcpyAsync(f->d_nzval, nzval, (size_t)f->nnz * f->esz, kind, st));
-  CUDA_OK(cudaStreamSynchronize(st));
-  auto t_h2d = std::chrono::steady_clock::now();
-  f->stats.ms_h2d = std::chrono::duration<double, std::milli>(t_h2d - t_plan).count();
+  up_thread.join();
+  if (up_err) std::rethrow_exception(up_err);
+  f->stats.ms_h2d = ms_up;  // overlapped with ms_analyze
+  if (getenv("HS_PLAN_TIMING"))
+    fprintf(stderr, "[factor] plan %.2f ms, upload %.2f ms (overlapped), joined at %.2f ms\n", f->stats.ms_analyze, ms_up,
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
   if (do_numeric) { if (dtype == HS_F64) numeric<double>(f.get()); else numeric<cplx>(f.get()); }
+  if (getenv("HS_PLAN_TIMING"))
+    fprintf(stderr, "[factor] numeric done at %.2f ms\n",
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
   *out = f.release();
   if ((*out)->stats.singular_front >= 0 || (*out)->stats.singular_col >= 0)
     return hs_fail(HS_ESINGULAR, "hs_factor: exactly singular pivot block in node " + std::to_string((*out)->stats.singular_front) +

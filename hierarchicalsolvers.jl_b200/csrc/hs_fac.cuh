@@ -17,6 +17,21 @@
                      std::string(#call) + ": " + cudaGetErrorString(e__));                              \
   } while (0)
 
+#include <memory>
+
+// int table whose pages are first touched by the threads that fill it (std::vector would zero-fill it serially)
+struct IntBuf {
+  std::unique_ptr<int[]> p;
+  size_t n = 0, cap = 0;
+  void reserve(size_t c) { if (c > cap || !p) { p.reset(new int[std::max<size_t>(c, 1)]); cap = c; } n = 0; }
+  void set_size(size_t m) { if (m > cap) throw hs_error(HS_ECUDA, "plan table overflow"); n = m; }
+  void resize(size_t m, int fill) { const size_t o = n; set_size(m); for (size_t i = o; i < m; ++i) p[i] = fill; }
+  void push_back(int v) { set_size(n + 1); p[n - 1] = v; }
+  int* data() { return p.get(); }
+  size_t size() const { return n; }
+  int& operator[](size_t i) { return p[i]; }
+};
+
 // ------------------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------------------
@@ -26,6 +41,9 @@ struct hs_ctx {
   bool own_stream = false;
   cudaStream_t aux_stream = nullptr;  // look-ahead: the big trailing update overlaps the next block's panels
   cudaEvent_t ev_b = nullptr, ev_c2 = nullptr;
+  cudaStream_t prep_stream = nullptr;  // solve preparation of a finished level runs beside the next levels' factorization
+  cudaEvent_t ev_p0 = nullptr, ev_p1 = nullptr;
+  bool prep_pending = false;
   int lookahead_max_fronts = 32;
   int max_cluster = 8;
   bool profile = false;
@@ -33,6 +51,7 @@ struct hs_ctx {
   void* gm_buf = nullptr;   // GMRES workspace (Krylov basis + work vectors), grow-only, reused across hs_gmres calls
   size_t gm_bytes = 0;
   int outer_block = 256;  // NB of the two-level blocked LU (HS_OUTER_BLOCK)
+  IntBuf sc_gidx, sc_cmap;  // plan-build scratch (row tables before their upload), grow-only
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -101,7 +120,8 @@ struct hs_fac {
   int64_t swlevel_resolved = 0, depth = 0;
   // host copies of the symbolic data (0-based)
   std::vector<int64_t> left, right, parent, level;
-  std::vector<int64_t> iloc_ptr, iloc_idx, bloc_ptr, bloc_idx;
+  std::vector<int64_t> iloc_ptr, bloc_ptr;
+  IntBuf iloc_idx, bloc_idx;   // positions inside the node's bnd (0-based)
   std::vector<int> node_ni, node_nb, node2front;
   std::vector<Front> fronts;
   std::vector<Level> levels;  // assembly levels: deepest first, root last (+ pseudo front for a non-empty root boundary)
@@ -168,7 +188,7 @@ inline void hs_panel_launch(hs_fac* f, int W, int f0, int nact, int j0, int m, c
 // hs_solve.cu
 void hs_solve_setup();
 int hs_solve_block(hs_dtype dt);
-void hs_solve_prep(hs_fac* f, const Level& L);
+void hs_solve_prep(hs_fac* f, const Level& L, cudaStream_t st);
 void hs_solve_run(hs_fac* f, int64_t nrhs, void* x, int which);  // which: 1 forward, 2 backward, 3 both
 
 // hs_small.cu

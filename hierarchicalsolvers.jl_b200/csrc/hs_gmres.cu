@@ -8,7 +8,9 @@
 #include <thrust/execution_policy.h>
 #include <thrust/scan.h>
 
+#include <chrono>
 #include <complex>
+#include <cstdio>
 
 #include "hs_fac.cuh"
 
@@ -140,6 +142,15 @@ void gmres_impl(hs_ctx* ctx, hs_fac* f, long long n, const long long* rptr, cons
                 const void* b_host, void* x_host, double reltol, int64_t restart, int64_t maxiter, double* resnorm,
                 int64_t* niter, int32_t* converged, int on_device) {
   cudaStream_t st = ctx->stream;
+  const bool timing = getenv("HS_PLAN_TIMING") != nullptr;
+  auto tg0 = std::chrono::steady_clock::now();
+  auto tick = [&](const char* what) {
+    if (!timing) return;
+    cudaStreamSynchronize(st);
+    auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[gmres] %-24s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - tg0).count());
+    tg0 = t1;
+  };
   T *V = nullptr, *w = nullptr, *z = nullptr, *x = nullptr, *bdev = nullptr;
   cplx *part = nullptr, *dres = nullptr;
   // one grow-only workspace per context: cudaMalloc/cudaFree of the ~1 GB Krylov basis per call would dominate
@@ -162,6 +173,7 @@ void gmres_impl(hs_ctx* ctx, hs_fac* f, long long n, const long long* rptr, cons
     part = (cplx*)p; p += up(RED_BLOCKS * sizeof(cplx));
     dres = (cplx*)p;
   }
+  tick("workspace");
   const unsigned gb = (unsigned)((n + 255) / 256);
   auto dot = [&](const T* a, const T* bb) -> zc {
     ctx->launches += 2;
@@ -191,6 +203,7 @@ void gmres_impl(hs_ctx* ctx, hs_fac* f, long long n, const long long* rptr, cons
   // r0 = b (x0 = 0)
   CUDA_OK(cudaMemcpyAsync(w, bdev, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, st));
   double beta = std::sqrt(dot(w, w).real());
+  tick("b to device + norm");
   const double tol = reltol * beta;
   double resid = beta;
   int64_t it = 0;
@@ -254,8 +267,10 @@ void gmres_impl(hs_ctx* ctx, hs_fac* f, long long n, const long long* rptr, cons
     }
   }
   CUDA_OK(cudaGetLastError());
+  tick("iterations");
   CUDA_OK(cudaMemcpyAsync(x_host, x, (size_t)n * sizeof(T), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaStreamSynchronize(st));
+  tick("x to host");
   *niter = it;
   *converged = resid <= tol;
 }
@@ -301,6 +316,7 @@ void gmres_entry(hs_ctx* ctx, long long n, const int64_t* colptr, const int64_t*
     own = true;
   }
   (void)own;
+  if (getenv("HS_PLAN_TIMING")) { cudaStreamSynchronize(st); fprintf(stderr, "[gmres] matrix ready (%s)\n", colptr ? "host CSC given" : "taken from the factorization"); }
   gmres_impl<T>(ctx, f, n, rptr, ccol, cval, b, x, reltol, restart, maxiter, resnorm, niter, converged, on_device);
 }
 

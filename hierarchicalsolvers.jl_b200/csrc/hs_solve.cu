@@ -524,11 +524,11 @@ __global__ void __launch_bounds__(NTH) k_sv_big_bwd(const Front* __restrict__ fr
   }
 }
 
-template <typename T> void prep_impl(hs_fac* f, const Level& L) {
+template <typename T> void prep_impl(hs_fac* f, const Level& L, cudaStream_t st) {
   if (L.max_ni == 0) return;
   dim3 grid(L.f1 - L.f0, (L.max_ni + DB - 1) / DB);
   const int dbm = std::min(DB, L.max_ni), lds = dbm | 1;
-  k_trtri_diag<T><<<grid, 128, (size_t)2 * lds * lds * sizeof(T), f->ctx->stream>>>(f->d_fronts, (T*)f->pool, L.f0, lds);
+  k_trtri_diag<T><<<grid, 128, (size_t)2 * lds * lds * sizeof(T), st>>>(f->d_fronts, (T*)f->pool, L.f0, lds);
   CUDA_OK(cudaGetLastError());
   f->stats.launches_factor += 1;
 }
@@ -633,8 +633,8 @@ void hs_solve_setup() {
 
 int hs_solve_block(hs_dtype) { return DB; }
 
-void hs_solve_prep(hs_fac* f, const Level& L) {
-  if (f->dtype == HS_F64) prep_impl<double>(f, L); else prep_impl<cplx>(f, L);
+void hs_solve_prep(hs_fac* f, const Level& L, cudaStream_t st) {
+  if (f->dtype == HS_F64) prep_impl<double>(f, L, st); else prep_impl<cplx>(f, L, st);
 }
 
 void hs_solve_run(hs_fac* f, int64_t nrhs, void* x, int which) {
