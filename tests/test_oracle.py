@@ -72,3 +72,63 @@ def test_parse_elimtree_errors(hs, orc):
         orc.parse_elimtree(*args(bad))
     nd = orc.parse_elimtree(*args(pad))
     assert orc.depth(nd) >= 2
+
+
+# ---- compressed branch (oracle/hs_oracle_hss.py) ------------------------------------------------------------------
+def test_oracle_compressed_converges_to_uncompressed(hs, orc):
+    """With a vanishing tolerance the low-rank Gauss transforms are exact: same solution as the uncompressed path."""
+    prob = hs.grid_problem((33, 33), "helmholtz", nmax=40)
+    Ap, nd, nd_loc, _ = orc.prepare(prob.A, prob.elim_tree)
+    F0 = orc.factor(Ap, nd, nd_loc)
+    Fc = orc.factor(Ap, nd, nd_loc, swlevel=-1, swsize=4, atol=1e-14, rtol=1e-14)
+    assert orc.maxrank(Fc) > 0
+    x0, xc = orc.ldiv(F0, prob.b), orc.ldiv(Fc, prob.b)
+    assert np.linalg.norm(xc - x0) / np.linalg.norm(x0) < 1e-9
+
+
+@pytest.mark.parametrize("tol", [1e-2, 1e-5])
+def test_oracle_compressed_gauss_transforms_within_tolerance(hs, orc, tol):
+    """L ≈ Abi·Aii⁻¹ and R ≈ Aii⁻¹·Aib come from a QR truncated at |R[k,k]| ≤ max(atol/2, rtol/2·|R[1,1]|)
+    (factorization.jl:99-100,171-182): the neglected part of Abi / Aib is bounded by that threshold times √(columns left),
+    ranks shrink with the tolerance, the preconditioned GMRES still converges."""
+    import hs_oracle_hss as oh
+    prob = hs.grid_problem((65, 65), "poisson", nmax=40)
+    Ap, nd, nd_loc, _ = orc.prepare(prob.A, prob.elim_tree)
+    Fc = orc.factor(Ap, nd, nd_loc, swlevel=-2, swsize=16, atol=tol, rtol=tol)
+    F0 = orc.factor(Ap, nd, nd_loc)
+    checked = 0
+    for nc, n0 in zip(orc.nodes_postorder(Fc), orc.nodes_postorder(F0)):
+        if not isinstance(nc.L, oh.LowRankMatrix):
+            continue
+        checked += 1
+        D = nc.D_dense()
+        Abi_lr = nc.L_dense() @ D          # the truncated Abi
+        Aib_lr = D @ nc.R_dense()
+        # exact blocks of the *compressed* factorization's own front: Abi = L_exact·D of a dense re-factorization is not
+        # available, so compare ranks and the defining property of pqrfact on the reconstructed blocks instead
+        for X, r in ((Abi_lr, nc.L.rank), (Aib_lr, nc.R.rank)):
+            assert np.linalg.matrix_rank(X, tol=1e-9 * np.linalg.norm(X, 2)) == r
+        assert nc.L.rank <= min(len(nc.int), len(nc.bnd)) and nc.R.rank <= min(len(nc.int), len(nc.bnd))
+    assert checked > 0
+    ranks = [max(r) for r in oh.node_ranks(Fc)]
+    assert orc.maxrank(Fc) == max(ranks) > 0
+    x, res, conv = orc.gmres(Ap, prob.b, Pr=lambda v: orc.ldiv(Fc, v), reltol=1e-9, restart=30, maxiter=30)
+    assert conv and np.linalg.norm(Ap @ x - prob.b) / np.linalg.norm(prob.b) < 1e-8
+    if tol == 1e-5:
+        F2 = orc.factor(Ap, nd, nd_loc, swlevel=-2, swsize=16, atol=1e-2, rtol=1e-2)
+        assert orc.maxrank(F2) < orc.maxrank(Fc)
+
+
+def test_oracle_pqrfact_truncation_rule():
+    import hs_oracle_hss as oh
+    rng = np.random.default_rng(3)
+    U, _ = np.linalg.qr(rng.standard_normal((40, 12)))
+    V, _ = np.linalg.qr(rng.standard_normal((30, 12)))
+    sv = 10.0 ** -np.arange(12)
+    M = (U * sv) @ V.T
+    Q, R = oh.pqrfact(M, atol=0.0, rtol=1e-5)
+    assert 4 <= Q.shape[1] <= 7 and R.shape == (Q.shape[1], 30)
+    assert np.linalg.norm(M - Q @ R, 2) < 1e-4
+    assert np.allclose(Q.T @ Q, np.eye(Q.shape[1]), atol=1e-12)
+    Q0, R0 = oh.pqrfact(np.zeros((5, 4)), atol=1e-3, rtol=1e-3)
+    assert Q0.shape == (5, 0) and R0.shape == (0, 4)
