@@ -43,6 +43,7 @@ def parse_args():
     ap.add_argument("--cpu-grid", type=int, default=384, help="grid side of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-compressed", action="store_true", help="skip the informational compressed-fronts variant")
     return ap.parse_args()
 
 
@@ -423,6 +424,23 @@ def main():
                    "factor_call_s": float(np.mean(tf_)), "gmres_call_s": float(np.mean(tg_)),
                    "inside_factor_ms": {k: st2[k] for k in ("ms_analyze", "ms_h2d", "ms_factor_total")}}
 
+    # ---- informational: the same workload with compressed upper fronts (rungmres.jl:39: swlevel=-2, swsize=480) ----
+    compressed = None
+    if world == 1 and not args.no_compressed:
+        try:
+            copts = dict(swlevel=-2, swsize=480, atol=1e-5, rtol=1e-5)
+            Fc = hs.factor(Ap, nd, nd_loc, device=local_rank, **copts)
+            Fc.refactor(Ap)   # steady state: side buffers sized
+            xc, hc = hs.gmres(Ap, b, Pr=Fc, reltol=1e-9, restart=30, maxiter=30, log=True)
+            sc = Fc.stats()
+            compressed = {"opts": copts, "factor_ms": sc["ms_factor_total"], "maxrank": int(hs.maxrank(Fc)),
+                          "gmres_iters": hc.iters, "converged": bool(hc.isconverged), "apply_ms": sc["ms_solve_total"],
+                          "residual": float(np.linalg.norm(Ap @ xc - b) / np.linalg.norm(b)),
+                          "note": "not part of `value`; low-rank Gauss transforms, dense Schur complements (DESIGN.md §4a)"}
+            del Fc
+        except Exception as exc:  # informational only
+            compressed = {"error": repr(exc)}
+
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:
         g = min(args.cpu_grid, args.grid)
@@ -449,6 +467,8 @@ def main():
             "setup_s": {"generate+symfact": t_setup, "first_factor_incl_plan": t_first},
             "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu_baseline,
             "clocks": clocks}
+    if compressed is not None:
+        line["compressed_variant"] = compressed
     print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist

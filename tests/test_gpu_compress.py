@@ -132,3 +132,24 @@ def test_baseline_config2_standin(hs, orc):
     # same preconditioner quality: residual histories agree to the compression tolerance
     m = min(ch.iters, len(reso))
     assert np.allclose(np.log10(np.asarray(ch.resnorm)[:m]), np.log10(np.asarray(reso)[:m]), atol=0.5)
+
+
+@pytest.mark.parametrize("kind", ["poisson", "helmholtz"])
+def test_compressed_root_with_boundary(hs, orc, kind):
+    """A root that keeps a boundary is compressed like any other node (factorization.jl:15) and its dense Schur
+    complement is then factored for `C[F.bnd,:] = F.S \\ C[F.bnd,:]` (factornode.jl:72)."""
+    from test_gpu_parity import _subtree_problem
+    prob = _subtree_problem(hs, (49, 49), kind)
+    rng = np.random.default_rng(5)
+    A = sp.csr_matrix(prob.A).copy()
+    A.data = A.data * (1.0 + 0.3 * rng.random(A.nnz))
+    prob.A = sp.csc_matrix(A)
+    opts = dict(swlevel=2, swsize=8, atol=1e-4, rtol=1e-4)
+    Ap, Fo, F = _both(hs, orc, prob, **opts)
+    assert F.ranks() == (Fo.L.rank, Fo.R.rank) and F.ranks()[0] > 0        # the root itself is compressed
+    assert len(Fo.bnd) > 0
+    for name, Xo in (("D", Fo.D_dense()), ("L", Fo.L_dense()), ("R", Fo.R_dense()), ("S", Fo.S)):
+        Xg = getattr(F, name)
+        assert np.linalg.norm(Xg - Xo) / np.linalg.norm(Xo) < 1e-7, name
+    B = rng.standard_normal((Ap.shape[0], 2)).astype(Fo.S.dtype)
+    assert np.linalg.norm(hs.ldiv(F, B) - orc.ldiv(Fo, B)) / np.linalg.norm(B) < 1e-7
