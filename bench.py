@@ -322,7 +322,6 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         import torch.distributed as dist
-        os.environ.setdefault("NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = hs._lib.default_context(local_rank)
     stream = torch.cuda.Stream() if world == 1 else torch.cuda.current_stream()
