@@ -1225,6 +1225,15 @@ extern "C" int32_t hs_stats(hs_fac* f, hs_stats_t* out) {
   return HS_OK;
 }
 
+extern "C" int32_t hs_matrix_device(hs_fac* f, const int64_t** colptr, const int64_t** rowval, const void** nzval, int64_t* nnz) {
+  if (!f || !colptr || !rowval || !nzval || !nnz) return hs_fail(HS_EARG, "hs_matrix_device: null argument");
+  *colptr = (const int64_t*)f->d_colptr;
+  *rowval = (const int64_t*)f->d_rowval;
+  *nzval = f->d_nzval;
+  *nnz = f->nnz;
+  return HS_OK;
+}
+
 extern "C" int32_t hs_resolved_swlevel(hs_fac* f, int64_t* sw) {
   if (!f || !sw) return hs_fail(HS_EARG, "hs_resolved_swlevel: null argument");
   *sw = f->swlevel_resolved;

@@ -63,28 +63,30 @@ def _slice_tree(nd: NestedDissection, loc: NDLoc, nodes: np.ndarray, as_leaf: se
     out.analyzed = True
     out.depth = nd.depth
 
+    leaf_mask = np.isin(nodes, np.fromiter(as_leaf, dtype=np.int64, count=len(as_leaf))) if as_leaf else np.zeros(len(nodes), bool)
+
     def remap(child):
         c = child[nodes].copy()
         m = c >= 0
         c[m] = newid[c[m]]
-        for k, g in enumerate(nodes):
-            if int(g) in as_leaf:
-                c[k] = -1
+        c[leaf_mask] = -1
         return c
 
     out.left, out.right = remap(nd.left), remap(nd.right)
 
     def ragged(ptr, idx, drop=()):
+        # vectorised gather of the ragged rows `nodes` (no Python loop: the trees have 10^5 nodes)
+        ptr = np.asarray(ptr, dtype=np.int64)
         lens = (ptr[1:] - ptr[:-1])[nodes].copy()
-        parts = []
-        for k, g in enumerate(nodes):
-            if int(g) in drop:
-                lens[k] = 0
-            else:
-                parts.append(idx[ptr[g]:ptr[g + 1]])
+        if drop:
+            lens[leaf_mask] = 0
         p = np.zeros(len(nodes) + 1, dtype=np.int64)
         np.cumsum(lens, out=p[1:])
-        return p, (np.concatenate(parts) if parts else np.zeros(0, np.int64)).astype(np.int64)
+        total = int(p[-1])
+        if total == 0:
+            return p, np.zeros(0, np.int64)
+        src = np.repeat(ptr[nodes] - p[:-1], lens) + np.arange(total, dtype=np.int64)
+        return p, np.asarray(idx)[src].astype(np.int64, copy=False)
 
     out.int_ptr, out.int_idx = ragged(nd.int_ptr, nd.int_idx, drop=as_leaf)
     out.bnd_ptr, out.bnd_idx = ragged(nd.bnd_ptr, nd.bnd_idx)
@@ -100,13 +102,18 @@ def partition_tree(nd: NestedDissection, nd_loc: NDLoc, nparts: int) -> TreePart
     nd._need_analyzed()
     nn = nd.nnodes
     w = _front_flops(nd)
-    sub = w.copy()            # work of the whole subtree below each node (post-order: children come first)
-    size = np.ones(nn, dtype=np.int64)
+    # work / node count of the whole subtree below each node (post-order: children come first); plain lists, the
+    # loop runs over 10^5 nodes
+    sub_l, size_l = w.tolist(), [1] * nn
+    left_l, right_l = np.asarray(nd.left).tolist(), np.asarray(nd.right).tolist()
     for k in range(nn):
-        for c in (nd.left[k], nd.right[k]):
-            if c >= 0:
-                sub[k] += sub[c]
-                size[k] += size[c]
+        c = left_l[k]
+        if c >= 0:
+            sub_l[k] += sub_l[c]; size_l[k] += size_l[c]
+        c = right_l[k]
+        if c >= 0:
+            sub_l[k] += sub_l[c]; size_l[k] += size_l[c]
+    sub, size = np.asarray(sub_l), np.asarray(size_l, dtype=np.int64)
     open_ = [nn - 1]
     while len(open_) < nparts:
         cand = [k for k in open_ if nd.left[k] >= 0]
@@ -167,27 +174,49 @@ class CudaEngine:
                 pass
 
     def _csc(self, A):
+        """(n, colptr, rowval, nzval, flags) as the C ABI takes them; SciPy's 0-based int32 arrays go through unchanged
+        (``HS_CSC_INT32``), and the result is cached: every upper front of the tree mapping passes the same matrix."""
         A = sp.csc_matrix(A)
+        key = (A.data.__array_interface__["data"][0], A.indices.__array_interface__["data"][0], A.data.shape[0])
+        if getattr(self, "_csc_key", None) == key:
+            return self._csc_val
         cx = np.iscomplexobj(A.data)
         self.cx = cx
         self.np_dtype = np.complex128 if cx else np.float64
         self.t_dtype = self.torch.complex128 if cx else self.torch.float64
-        return (A.shape[0], _lib.as_i64(A.indptr), _lib.as_i64(A.indices), np.ascontiguousarray(A.data, dtype=self.np_dtype))
+        flags = _lib.HS_CSC_ZERO_BASED
+        if A.indices.dtype == np.int32 and A.indptr.dtype == np.int32:
+            colptr, rowval = np.ascontiguousarray(A.indptr), np.ascontiguousarray(A.indices)
+            flags |= _lib.HS_CSC_INT32
+        else:
+            colptr, rowval = _lib.as_i64(A.indptr), _lib.as_i64(A.indices)
+        self._csc_key = key
+        self._csc_val = (A.shape[0], colptr, rowval, np.ascontiguousarray(A.data, dtype=self.np_dtype), flags)
+        return self._csc_val
 
     def _factor(self, A, nd, loc, opts, subtree, numeric):
-        n, colptr, rowval, nz = self._csc(A)
+        n, colptr, rowval, nz, flags = self._csc(A)
         tree, keep = _tree_struct(nd, loc)
         copts = to_c(opts, subtree=subtree)
         h = C.c_void_p()
         fn = _lib.lib.hs_factor if numeric else _lib.lib.hs_analyze
-        rc = fn(self.ctx, _lib.HS_C64 if self.cx else _lib.HS_F64, n, colptr.ctypes.data_as(C.c_void_p),
-                rowval.ctypes.data_as(C.c_void_p), nz.ctypes.data_as(C.c_void_p), C.byref(tree), C.byref(copts),
-                _lib.HS_CSC_ZERO_BASED, C.byref(h))
+        dev = getattr(self, "_dev_csc", None)
+        if dev is not None and dev[0] == self._csc_key:
+            # the matrix is already in HBM (an earlier factorization of this engine holds it): device-to-device copy
+            cp, rv, nzp = dev[1]
+            flags = _lib.HS_CSC_ZERO_BASED | _lib.HS_ON_DEVICE
+        else:
+            cp, rv, nzp = (a.ctypes.data_as(C.c_void_p) for a in (colptr, rowval, nz))
+        rc = fn(self.ctx, _lib.HS_C64 if self.cx else _lib.HS_F64, n, cp, rv, nzp, C.byref(tree), C.byref(copts), flags, C.byref(h))
         if rc != _lib.HS_OK:
             if h:
                 _lib.lib.hs_factor_free(h)
             _lib.check(rc)
         self.handles.append(h)
+        if dev is None or dev[0] != self._csc_key:
+            dcp, drv, dnz, nnz = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int64()
+            _lib.check(_lib.lib.hs_matrix_device(h, C.byref(dcp), C.byref(drv), C.byref(dnz), C.byref(nnz)))
+            self._dev_csc = (self._csc_key, (dcp, drv, dnz))
         return h
 
     def factor_subtree(self, A, nd, loc, opts):

@@ -189,6 +189,10 @@ int32_t hs_maxrank(hs_fac* fac, int64_t* rank);              /* factornode.jl:49
 int32_t hs_node_rank(hs_fac* fac, int64_t node, int64_t* rank_l, int64_t* rank_r);
 int32_t hs_stats(hs_fac* fac, hs_stats_t* out);
 int32_t hs_resolved_swlevel(hs_fac* fac, int64_t* swlevel);  /* factorization.jl:8 */
+/* Device-resident copy of the matrix a factorization holds (0-based int64 colptr / rowval, nzval of the factorization's
+ * dtype): lets further hs_factor / hs_analyze calls on the same matrix (the upper fronts of the subtree-per-GPU mapping)
+ * pass HS_ON_DEVICE | HS_CSC_ZERO_BASED instead of uploading the CSC arrays again.  Valid until hs_factor_free(fac). */
+int32_t hs_matrix_device(hs_fac* fac, const int64_t** colptr, const int64_t** rowval, const void** nzval, int64_t* nnz);
 
 /* ---- GMRES with the factorization as right preconditioner (test/rungmres.jl:47-48) ---------------
  * device-resident restarted GMRES (modified Gram-Schmidt, Givens), x0 = 0, stops when the running residual
