@@ -45,7 +45,7 @@ class hs_stats_t(C.Structure):
                 ("launches_solve", C.c_int64), ("singular_front", C.c_int64), ("singular_col", C.c_int64),
                 ("maxrank", C.c_int64), ("gemm_flops", C.c_double), ("gemm_launches", C.c_int64),
                 ("panel_launches", C.c_int64), ("ms_extend_add", C.c_double), ("ms_small", C.c_double), ("ms_solve_prep", C.c_double),
-                ("ms_compress", C.c_double)]
+                ("ms_compress", C.c_double), ("lowrank_bytes", C.c_double)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -308,6 +308,7 @@ template <typename T> static void numeric(hs_fac* f) {
     if (!L.pseudo) {
       PhaseTimer t(f, &s.ms_assemble);
       CUDA_OK(cudaMemsetAsync(pool + L.poff0, 0, (size_t)(L.poff1 - L.poff0) * sizeof(T), st));
+      if (L.tpoff1 > L.tpoff0) CUDA_OK(cudaMemsetAsync(pool + L.tpoff0, 0, (size_t)(L.tpoff1 - L.tpoff0) * sizeof(T), st));
       dim3 grid(nf, (L.max_n + 255) / 256);
       k_fill_owner<<<grid, 256, 0, st>>>(f->d_fronts, f->d_gidx, f->d_own, f->d_pos, L.f0);
       k_scatter_A<T><<<grid, 256, 0, st>>>(f->d_fronts, pool, f->d_gidx, f->d_own, f->d_pos, f->d_colptr,
@@ -348,6 +349,8 @@ template <typename T> static void numeric(hs_fac* f) {
       hs_comp_schur(f, C);
     }
   }
+  s.lowrank_bytes = 0;
+  for (const CompLevel& C : f->clevels) s.lowrank_bytes += (double)C.side_bytes;
   if (f->ctx->prep_pending) {
     CUDA_OK(cudaEventRecord(f->ctx->ev_p1, f->ctx->prep_stream));
     CUDA_OK(cudaStreamWaitEvent(st, f->ctx->ev_p1, 0));
@@ -560,6 +563,12 @@ static void build_plan(hs_fac* f, const hs_tree* t) {
   IntBuf &gidx = f->ctx->sc_gidx, &cmap = f->ctx->sc_cmap;  // grow-only scratch: no page faults after the first call
   long long poff = 0, ioff = 0;
   const long long align = 32;
+  // Dense slots of compressed fronts are transient: they are needed while their level is processed and when the
+  // parent level is assembled, so they live in two arenas used alternately by level parity (HS_KEEP_SCHUR=1 keeps
+  // them, e.g. to read F.S of a compressed node back).  The root stays persistent (its S may be factored in place).
+  f->transient_schur = !(getenv("HS_KEEP_SCHUR") && atoi(getenv("HS_KEEP_SCHUR")) != 0);
+  std::vector<long long> toff(nn, -1);
+  long long arena[2] = {0, 0}, tcur = 0;
   f->levels.clear();
   double flops = 0, sbytes = 0, ebytes = 0;
   int64_t max_ni = 0, max_nb = 0;
@@ -579,6 +588,7 @@ static void build_plan(hs_fac* f, const hs_tree* t) {
     if (f->levels.empty() || f->level[k] != f->level[order[f->levels.back().f0]]) {
       Level L; L.f0 = i; L.f1 = i; L.fm = i; L.ioff0 = ioff; L.poff0 = poff;
       f->levels.push_back(L);
+      tcur = 0;
     }
     Level& L = f->levels.back();
     L.f1 = i + 1;
@@ -588,7 +598,15 @@ static void build_plan(hs_fac* f, const hs_tree* t) {
     L.max_ni = std::max(L.max_ni, fr.ni);
     L.max_nb = std::max(L.max_nb, fr.n - fr.ni);
     L.ni_sorted.push_back(fr.ni);
-    poff += ((long long)fr.ld * fr.n + align - 1) / align * align;
+    const long long slot = ((long long)fr.ld * fr.n + align - 1) / align * align;
+    if (cflag[k] && f->transient_schur && k != root) {
+      const int par = (int)((f->levels.size() - 1) & 1);
+      toff[i] = tcur; tcur += slot;
+      arena[par] = std::max(arena[par], tcur);
+      L.tpoff1 = tcur;  // relative to the arena until the arenas are placed (below)
+    } else {
+      poff += slot;
+    }
     ioff += fr.n;
     L.ioff1 = ioff; L.poff1 = poff;
     const double ni = fr.ni, nb = fr.n - fr.ni;
@@ -597,6 +615,18 @@ static void build_plan(hs_fac* f, const hs_tree* t) {
     ebytes += 2.0 * nb * nb;
     max_ni = std::max<int64_t>(max_ni, fr.ni);
     max_nb = std::max<int64_t>(max_nb, fr.n - fr.ni);
+  }
+  {  // place the two arenas behind the persistent fronts
+    const long long abase[2] = {poff, poff + arena[0]};
+    for (size_t li = 0; li < f->levels.size(); ++li) {
+      Level& L = f->levels[li];
+      if (L.tpoff1 == 0) continue;
+      L.tpoff0 = abase[li & 1];
+      L.tpoff1 += abase[li & 1];
+      for (int i = L.fm; i < L.f1; ++i)
+        if (toff[i] >= 0) f->fronts[i].off = abase[li & 1] + toff[i];
+    }
+    poff += arena[0] + arena[1];
   }
   clk.tick("front descriptors");
   // per-row tables: global DOF of every front row
@@ -869,6 +899,9 @@ extern "C" int32_t hs_schur_export(hs_fac* f, int64_t node, void* dst, int64_t l
   if (ld < nb) return hs_fail(HS_EDIM, "hs_schur_export: leading dimension smaller than the boundary");
   if (f->pseudo_front >= 0 && f->node2front[node] == f->root_front)
     return hs_fail(HS_EARG, "hs_schur_export: the root boundary block was factored for the solve; factor with opts.subtree = 1");
+  if (f->transient_schur && f->node2front[node] != f->root_front)
+    for (const CompFront& cf : f->comp)
+      if (cf.fi == f->node2front[node]) return hs_fail(HS_EARG, "hs_schur_export: Schur block of a compressed front is transient (HS_KEEP_SCHUR=1 keeps it)");
   CUDA_OK(cudaSetDevice(f->ctx->device));
   if (nb) {
     const char* src = (const char*)f->pool + ((size_t)fr.off + (size_t)fr.ni * fr.ld + fr.ni) * f->esz;
@@ -995,6 +1028,9 @@ template <typename T> static void node_get_compressed(hs_fac* f, int64_t node, c
   const int fi = cf.fi, ni = cf.ni, nb = cf.nb;
   cudaStream_t st = f->ctx->stream;
   T* o = (T*)out;
+  if (which == HS_GET_S && f->transient_schur && f->node2front[node] != f->root_front)
+    throw hs_error(HS_EARG, "hs_node_get: the dense Schur block of a compressed front is transient (its slot is reused two levels up); "
+                            "set HS_KEEP_SCHUR=1 before hs_factor to keep it");
   if (which == HS_GET_S || which == HS_GET_FRONT || which == HS_GET_PIV || which == HS_GET_D) {
     // S lives in the dense slot; D, the raw front and the pivots are those of the thin front
     const bool thin = which != HS_GET_S;

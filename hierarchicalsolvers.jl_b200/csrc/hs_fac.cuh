@@ -62,6 +62,7 @@ struct Level {
   int max_n = 0, max_ni = 0, max_nb = 0;
   long long ioff0 = 0, ioff1 = 0;
   long long poff0 = 0, poff1 = 0;
+  long long tpoff0 = 0, tpoff1 = 0;  // dense slots of the level's compressed fronts inside a transient arena
   bool pseudo = false;
   std::vector<int> ni_sorted;  // ni of the fronts in this level (descending)
   int fm = 0;                  // assembly levels: fronts [fm, f1) are compressed (fm = f1: none)
@@ -129,6 +130,7 @@ struct hs_fac {
   std::vector<CompFront> comp;
   std::vector<CompLevel> clevels;
   int nfr = 0;                // number of dense front descriptors; thin descriptors follow at nfr + fi
+  bool transient_schur = true; // dense slots of compressed fronts are recycled two levels up
   long long nvirt = 0;        // virtual slots appended to the solution vector
   long long xld = 0;          // leading dimension of the internal solution buffer: n + nvirt
   std::vector<IdRun> runs;    // two per compressed front

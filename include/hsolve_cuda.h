@@ -113,6 +113,8 @@ typedef struct {
   double ms_small;         /* fused small-front kernel (levels whose fronts fit in registers) */
   double ms_solve_prep;    /* in-place inversion of the diagonal blocks of L11/U11 (part of the factor time) */
   double ms_compress;      /* compressed fronts: pivoted QR of A_bi / A_ib, thin fronts, Schur complement      */
+  double lowrank_bytes;    /* device bytes of the thin fronts + low-rank factors of compressed fronts (their dense
+                              slots are transient and counted once, as two arenas, in front_bytes)            */
 } hs_stats_t;
 
 typedef enum { HS_GET_D = 0, HS_GET_S = 1, HS_GET_L = 2, HS_GET_R = 3, HS_GET_FRONT = 4, HS_GET_PIV = 5 } hs_which;

@@ -22,7 +22,15 @@ def _perturbed(hs, shape, kind, nmax, seed=0):
     return prob
 
 
-def _both(hs, orc, prob, **opts):
+def hs_front_bytes_dense(hs, prob):
+    Ap, nd, nd_loc, _ = hs.prepare(prob.A, prob.elim_tree)
+    return hs.factor(Ap, nd, nd_loc, swlevel=0).stats()["front_bytes"]
+
+
+def _both(hs, orc, prob, keep_schur=False, **opts):
+    """Oracle and GPU factorizations of the same problem.  ``keep_schur``: keep the dense Schur blocks of compressed
+    fronts (HS_KEEP_SCHUR=1) so that ``F.S`` of those nodes can be read back; by default their slots are transient."""
+    import os
     Ap, nd, nd_loc, perm = orc.prepare(prob.A, prob.elim_tree)
     Fo = orc.factor(Ap, nd, nd_loc, **opts)
     hnd = hs.from_elimtree(prob.elim_tree)
@@ -30,7 +38,15 @@ def _both(hs, orc, prob, **opts):
     p = hs.postorder(hnd)
     A = hs.permute(prob.A, p, p)
     hnd = hs.permuted(hnd, hs.invperm(p))
-    F = hs.factor(A, hnd, hloc, **opts)
+    old = os.environ.pop("HS_KEEP_SCHUR", None)
+    if keep_schur:
+        os.environ["HS_KEEP_SCHUR"] = "1"
+    try:
+        F = hs.factor(A, hnd, hloc, **opts)
+    finally:
+        os.environ.pop("HS_KEEP_SCHUR", None)
+        if old is not None:
+            os.environ["HS_KEEP_SCHUR"] = old
     return Ap, Fo, F
 
 
@@ -39,7 +55,7 @@ def _both(hs, orc, prob, **opts):
 def test_compressed_nodes_match_oracle(hs, orc, kind, shape, tol):
     import hs_oracle_hss as oh
     prob = _perturbed(hs, shape, kind, nmax=40)
-    Ap, Fo, F = _both(hs, orc, prob, swlevel=-2, swsize=16, atol=tol, rtol=tol)
+    Ap, Fo, F = _both(hs, orc, prob, keep_schur=True, swlevel=-2, swsize=16, atol=tol, rtol=tol)
     ranks_o = oh.node_ranks(Fo)
     nodes_o = orc.nodes_postorder(Fo)
     ncomp = 0
@@ -56,6 +72,13 @@ def test_compressed_nodes_match_oracle(hs, orc, kind, shape, tol):
             assert err < 1e-7, f"node {k} {name}: rel err {err:.2e}"
     assert ncomp > 0
     assert hs.maxrank(F) == orc.maxrank(Fo) > 0
+    # default mode: the dense slots of compressed fronts are transient (recycled two levels up) — same preconditioner,
+    # F.S of a compressed node is no longer available
+    _, _, F = _both(hs, orc, prob, swlevel=-2, swsize=16, atol=tol, rtol=tol)
+    kc = next(k for k, r in enumerate(ranks_o) if r != (0, 0) and k != len(ranks_o) - 1)
+    with pytest.raises(hs.ArgumentError):
+        F.node(kc).S
+    assert F.stats()["front_bytes"] < hs_front_bytes_dense(hs, prob)
     # the preconditioner application and the GMRES history
     b = prob.b
     xo, xg = orc.ldiv(Fo, b), hs.ldiv(F, b)
