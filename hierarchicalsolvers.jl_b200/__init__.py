@@ -6,7 +6,8 @@ Host mirror (Python, because Julia is absent from this image) over the C ABI of 
 """
 from . import _lib
 from .options import SolverOptions, chkopts
-from .problems import ElimTree, Problem, grid_problem, grid_elimtree, grid_operator, read_problem, write_problem
+from .problems import (ElimTree, Problem, grid_problem, grid_elimtree, grid_operator, read_problem, write_problem,
+                       nested_dissection)
 from .nesteddissection import (NestedDissection, parse_elimtree, from_elimtree, symfact, postorder, permuted, invperm,
                                permute, contigious, getinterior, getboundary, depth)
 from .factornode import FactorNode, ldiv, maxrank, isleaf, isbranch, eltype
@@ -21,7 +22,7 @@ __all__ = [
     "FactorNode", "ldiv", "maxrank", "isleaf", "isbranch", "eltype",
     "factor", "gmres", "ConvergenceHistory",
     "ElimTree", "Problem", "grid_problem", "grid_elimtree", "grid_operator", "read_problem", "write_problem",
-    "SingularException", "DimensionMismatch", "ArgumentError", "HSolveError",
+    "SingularException", "DimensionMismatch", "ArgumentError", "HSolveError", "nested_dissection",
 ]
 
 

@@ -61,6 +61,9 @@ PROTOTYPES = [
     ("hs_device_count", C.c_int32, []),
     ("hs_set_profile", C.c_int32, [C.c_void_p, C.c_int32]),
     ("hs_launch_count", C.c_int32, [C.c_void_p, i64p]),
+    ("hs_nd_create", C.c_int32, [C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.POINTER(C.c_void_p)]),
+    ("hs_nd_elimtree", C.c_int32, [C.c_void_p, C.POINTER(hs_elimtree)]),
+    ("hs_nd_free", C.c_int32, [C.c_void_p]),
     ("hs_symfact", C.c_int32, [C.POINTER(hs_elimtree), C.c_int32, C.POINTER(C.c_void_p)]),
     ("hs_symbolic_tree", C.c_int32, [C.c_void_p, C.POINTER(hs_tree)]),
     ("hs_symbolic_perm", C.c_int32, [C.c_void_p, C.POINTER(i64p), i64p]),

@@ -30,6 +30,7 @@ __all__ = [
     "grid_operator",
     "read_problem",
     "write_problem",
+    "nested_dissection",
 ]
 
 
@@ -290,3 +291,40 @@ def grid_problem(shape, kind: str = "poisson", nmax: int = 100, ppw: float = 10.
         b = b.astype(np.complex128)
     tree = grid_elimtree(shape, nmax)
     return Problem(A, b, tree, name=f"{kind}{len(shape)}d_{'x'.join(map(str, shape))}_nmax{nmax}")
+
+
+def nested_dissection(A, nmax: int = 100) -> ElimTree:
+    """Elimination tree (the ``elim_tree`` schema of util/read_problem.jl:14-20) for an arbitrary sparse matrix, by
+    recursive graph bisection of the pattern of ``A + Aᵀ`` with METIS until a part holds at most ``nmax`` DOFs
+    (``hs_nd_create``, csrc/hs_ordering.cpp).  The reference has no ordering code — its trees come with the problem
+    files — so this is what makes matrices without such a file usable: ``from_elimtree(nested_dissection(A))`` →
+    ``symfact`` → ``postorder`` / ``permute`` → ``factor`` as in test/rungmres.jl:15-19."""
+    import ctypes as C
+
+    from . import _lib
+    A = sp.csc_matrix(A)
+    if A.shape[0] != A.shape[1]:
+        raise _lib.DimensionMismatch(_lib.HS_EDIM, "A must be square")
+    n = A.shape[0]
+    flags = _lib.HS_CSC_ZERO_BASED
+    if A.indices.dtype == np.int32 and A.indptr.dtype == np.int32:
+        colptr, rowval = np.ascontiguousarray(A.indptr), np.ascontiguousarray(A.indices)
+        flags |= _lib.HS_CSC_INT32
+    else:
+        colptr, rowval = _lib.as_i64(A.indptr), _lib.as_i64(A.indices)
+    h = C.c_void_p()
+    _lib.check(_lib.lib.hs_nd_create(n, colptr.ctypes.data_as(C.c_void_p), rowval.ctypes.data_as(C.c_void_p), flags, 1,
+                                     int(nmax), C.byref(h)))
+    try:
+        et = _lib.hs_elimtree()
+        _lib.check(_lib.lib.hs_nd_elimtree(h, C.byref(et)))
+        nn = int(et.nnodes)
+
+        def arr(p, m):
+            return np.ctypeslib.as_array(p, shape=(m,)).astype(np.int64, copy=True) if m else np.zeros(0, np.int64)
+        iptr, bptr = arr(et.inter_ptr, nn + 1), arr(et.bound_ptr, nn + 1)
+        out = ElimTree(arr(et.fathers, nn), arr(et.lsons, nn), arr(et.rsons, nn), iptr, arr(et.inter_idx, int(iptr[-1])),
+                       bptr, arr(et.bound_idx, int(bptr[-1])))
+    finally:
+        _lib.lib.hs_nd_free(h)
+    return out

@@ -138,6 +138,17 @@ int32_t hs_device_count(void);
  * (nesteddissection.jl:105-148, :29-69, :73-79, :82-88; driver order test/rungmres.jl:15-19).
  * `apply_postorder` != 0 renumbers DOFs by the post-order permutation exactly as rungmres.jl:17-19 does;
  * the caller must then factor permute(A, perm, perm).  perm is reported with `index_base`. */
+/* ---- elimination tree for a general sparsity pattern ----------------------------------
+ * The reference loads `elim_tree` from the problem file (util/read_problem.jl:14-20) and has no ordering code.  This
+ * builds the same schema by recursive graph bisection of the pattern of A + Aᵀ (METIS, the static library of the CUDA
+ * toolkit) until a part holds at most `nmax` DOFs.  A is CSC (only colptr / rowval are read); `flags` as for
+ * hs_factor (HS_CSC_ZERO_BASED, HS_CSC_INT32); node and DOF ids of the result use `index_base`. */
+typedef struct hs_ordering hs_ordering;
+int32_t hs_nd_create(int64_t n, const void* colptr, const void* rowval, int32_t flags, int32_t index_base, int64_t nmax,
+                     hs_ordering** out);
+int32_t hs_nd_elimtree(const hs_ordering* o, hs_elimtree* et_out);   /* views into `o` */
+int32_t hs_nd_free(hs_ordering* o);
+
 int32_t hs_symfact(const hs_elimtree* et, int32_t apply_postorder, hs_symbolic** out);
 int32_t hs_symbolic_tree(const hs_symbolic* s, hs_tree* tree_out);      /* views into `s` */
 int32_t hs_symbolic_perm(const hs_symbolic* s, const int64_t** perm, int64_t* n);
