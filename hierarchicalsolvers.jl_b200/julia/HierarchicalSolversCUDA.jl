@@ -17,7 +17,7 @@ using HierarchicalSolvers
 import LinearAlgebra: ldiv!
 import HierarchicalSolvers: maxrank, isleaf, isbranch
 
-export CuFactorNode, cufactor
+export CuFactorNode, cufactor, noderanks, nested_dissection
 
 const libhsolve = get(ENV, "LIBHSOLVE_CUDA", "libhsolve_cuda")
 
@@ -134,6 +134,50 @@ function maxrank(F::CuFactorNode)             # src/factornode.jl:49-57
   r = Ref{Int64}(0)
   check(ccall((:hs_maxrank, libhsolve), Int32, (Ptr{Cvoid}, Ref{Int64}), F.handle, r))
   return Int(r[])
+end
+
+# rank(F.L), rank(F.R) of a compressed node (LowRankMatrix, src/factorization.jl:173,179); (0, 0) when L, R are dense
+function noderanks(F::CuFactorNode)
+  rl = Ref{Int64}(0); rr = Ref{Int64}(0)
+  check(ccall((:hs_node_rank, libhsolve), Int32, (Ptr{Cvoid}, Int64, Ref{Int64}, Ref{Int64}),
+              getfield(F, :handle), getfield(F, :node), rl, rr))
+  return Int(rl[]), Int(rr[])
+end
+
+# ---- elimination tree for a matrix that comes without one (the reference has no ordering code) ----------------
+struct HsElimTree
+  nnodes::Int64
+  fathers::Ptr{Int64}; lsons::Ptr{Int64}; rsons::Ptr{Int64}
+  inter_ptr::Ptr{Int64}; inter_idx::Ptr{Int64}; bound_ptr::Ptr{Int64}; bound_idx::Ptr{Int64}
+  index_base::Int32
+end
+
+"""
+    nested_dissection(A; nmax = 100) -> NestedDissection
+
+Recursive METIS bisection of the pattern of `A + A'`; returns what `parse_elimtree` (src/nesteddissection.jl:105-148)
+returns for the `elim_tree` of a problem file.
+"""
+function nested_dissection(A::SparseMatrixCSC{T,Int}; nmax::Int = 100) where T
+  h = Ref{Ptr{Cvoid}}(C_NULL)
+  GC.@preserve A check(ccall((:hs_nd_create, libhsolve), Int32,
+                             (Int64, Ptr{Int64}, Ptr{Int64}, Int32, Int32, Int64, Ref{Ptr{Cvoid}}),
+                             size(A, 1), A.colptr, A.rowval, Int32(0), Int32(1), nmax, h))
+  et = Ref{HsElimTree}()
+  check(ccall((:hs_nd_elimtree, libhsolve), Int32, (Ptr{Cvoid}, Ref{HsElimTree}), h[], et))
+  e = et[]; nn = Int(e.nnodes)
+  cp(p, m) = copy(unsafe_wrap(Array, p, m))
+  fathers, lsons, rsons = cp(e.fathers, nn), cp(e.lsons, nn), cp(e.rsons, nn)
+  ip, bp = cp(e.inter_ptr, nn + 1), cp(e.bound_ptr, nn + 1)
+  ii, bi = cp(e.inter_idx, ip[end]), cp(e.bound_idx, bp[end])
+  ccall((:hs_nd_free, libhsolve), Int32, (Ptr{Cvoid},), h[])
+  ninter, nbound = diff(ip), diff(bp)
+  inter = zeros(Int, max(maximum(ninter), 1), nn); bound = zeros(Int, max(maximum(nbound), 1), nn)
+  for k in 1:nn
+    inter[1:ninter[k], k] = ii[ip[k]+1:ip[k+1]]
+    bound[1:nbound[k], k] = bi[bp[k]+1:bp[k+1]]
+  end
+  return HierarchicalSolvers.parse_elimtree(fathers, lsons, rsons, ninter, inter, nbound, bound)
 end
 
 # ---- FactorNode fields, copied from the device on access (src/factornode.jl:8-22) ----------------------------
