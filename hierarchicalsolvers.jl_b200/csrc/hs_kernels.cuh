@@ -213,7 +213,9 @@ __global__ void __launch_bounds__(128) k_laswp(const Front* __restrict__ fronts,
 // ------------------------------------------------------------------------------------------------
 // Schur / trailing update on the FP64 tensor cores:  C -= A·B  with A = L panel, B = U row panel of the same front.
 // DMMA m8n8k4 (the native FP64 MMA shape on sm_100a: `DMMA.8x8x4`); complex = 4 real DMMAs on interleaved operands.
-// 128×128 (f64) / 128×64 (c64) CTA tile, 8 warps, K in chunks staged by a 4-deep cp.async pipeline.
+// 128×64 (f64) / 64×64 (c64) CTA tile, 4 warps, two CTAs per SM, K in chunks staged by a 4-deep cp.async pipeline,
+// the C tile read-modify-written through shared memory.  GEN = true (GemmDesc) turns the same kernel into a free-standing
+// batched product C ∓= A·B for the compressed path (hs_compress.cu).
 //
 // Two-level blocking: inside an outer block [J0, BE) of pivot columns (BE = min(J0+NB, ni)) the inner panels of
 // width W update only the L-shaped region they must (mode 0); the big trailing block [BE,n)² is updated once per
