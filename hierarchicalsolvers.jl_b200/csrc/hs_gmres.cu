@@ -151,12 +151,16 @@ void gmres_impl(hs_ctx* ctx, hs_fac* f, long long n, const long long* rptr, cons
     fprintf(stderr, "[gmres] %-24s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - tg0).count());
     tg0 = t1;
   };
-  T *V = nullptr, *w = nullptr, *z = nullptr, *x = nullptr, *bdev = nullptr;
+  T *V = nullptr, *w = nullptr, *z = nullptr, *x = nullptr, *bdev = nullptr, *Zk = nullptr;
   cplx *part = nullptr, *dres = nullptr;
   // one grow-only workspace per context: cudaMalloc/cudaFree of the ~1 GB Krylov basis per call would dominate
   auto up = [](size_t b) { return (b + 255) / 256 * 256; };
   const size_t szv = up((size_t)n * sizeof(T));
-  const size_t need = szv * (restart + 1) + 4 * szv + up(RED_BLOCKS * sizeof(cplx)) + 256;
+  // The solution update x += Pr⁻¹·(V·y) equals Σ y_j·z_j with z_j = Pr⁻¹·v_j, which the Arnoldi step already computed:
+  // the first ZK of them are kept, so a solve that converges within ZK iterations of a cycle (a direct-solver
+  // preconditioner needs one) skips the second preconditioner application of IterativeSolvers' update.
+  const int64_t ZK = std::min<int64_t>(restart, 4);
+  const size_t need = szv * (restart + 1) + (4 + ZK) * szv + up(RED_BLOCKS * sizeof(cplx)) + 256;
   if (ctx->gm_bytes < need) {
     cudaFree(ctx->gm_buf);
     ctx->gm_buf = nullptr; ctx->gm_bytes = 0;
@@ -170,6 +174,7 @@ void gmres_impl(hs_ctx* ctx, hs_fac* f, long long n, const long long* rptr, cons
     z = (T*)p; p += szv;
     x = (T*)p; p += szv;
     bdev = (T*)p; p += szv;
+    Zk = (T*)p; p += szv * ZK;
     part = (cplx*)p; p += up(RED_BLOCKS * sizeof(cplx));
     dres = (cplx*)p;
   }
@@ -218,8 +223,9 @@ void gmres_impl(hs_ctx* ctx, hs_fac* f, long long n, const long long* rptr, cons
     while (k < restart && it < maxiter && resid > tol) {
       T* vk = V + (size_t)k * n;
       T* vk1 = V + (size_t)(k + 1) * n;
-      precond(vk, z);
-      matvec(z, vk1);
+      T* zk = k < ZK ? (T*)((char*)Zk + (size_t)k * szv) : z;
+      precond(vk, zk);
+      matvec(zk, vk1);
       for (int64_t j = 0; j <= k; ++j) {  // modified Gram-Schmidt
         const T* vj = V + (size_t)j * n;
         const zc h = dot(vj, vk1);
@@ -254,10 +260,14 @@ void gmres_impl(hs_ctx* ctx, hs_fac* f, long long n, const long long* rptr, cons
       for (int64_t j = i + 1; j < k; ++j) s -= Hm(i, j) * y[j];
       y[i] = s / Hm(i, i);
     }
-    CUDA_OK(cudaMemsetAsync(w, 0, (size_t)n * sizeof(T), st));
-    for (int64_t j = 0; j < k; ++j) axpy(y[j], V + (size_t)j * n, w, 0);
-    precond(w, z);
-    axpy(zc(1.0), z, x, 0);
+    if (k <= ZK) {
+      for (int64_t j = 0; j < k; ++j) axpy(y[j], (const T*)((const char*)Zk + (size_t)j * szv), x, 0);
+    } else {
+      CUDA_OK(cudaMemsetAsync(w, 0, (size_t)n * sizeof(T), st));
+      for (int64_t j = 0; j < k; ++j) axpy(y[j], V + (size_t)j * n, w, 0);
+      precond(w, z);
+      axpy(zc(1.0), z, x, 0);
+    }
     if (it < maxiter && resid > tol) {  // restart: r = b − A x
       matvec(x, w);
       axpy(zc(-1.0), bdev, w, 0);

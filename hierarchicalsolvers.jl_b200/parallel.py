@@ -451,8 +451,11 @@ def gmres_replicated(A_t, b, precond, reltol=1e-9, restart=30, maxiter=30):
         cs = np.zeros(restart, dtype=H.dtype); sn = np.zeros(restart, dtype=H.dtype)
         g = np.zeros(restart + 1, dtype=H.dtype); g[0] = beta
         k = 0
+        Z = []   # Pr⁻¹·v_j of the first iterations: x += Pr⁻¹·(V·y) = Σ y_j·z_j saves the second application
         while k < restart and it < maxiter and resid > tol:
             z = precond(V[k].clone())
+            if k < 4:
+                Z.append(z)
             w = torch.mv(A_t, z)
             for j in range(k + 1):
                 h = torch.vdot(V[j], w)
@@ -477,10 +480,14 @@ def gmres_replicated(A_t, b, precond, reltol=1e-9, restart=30, maxiter=30):
             resid = abs(g[k + 1]); res.append(float(resid))
             k += 1; it += 1
         y = np.linalg.solve(np.triu(H[:k, :k]), g[:k]) if k else np.zeros(0)
-        upd = torch.zeros_like(b)
-        for j in range(k):
-            upd = upd + complex(y[j]) * V[j] if cplx else upd + float(np.real(y[j])) * V[j]
-        x = x + precond(upd)
+        if k <= len(Z):
+            for j in range(k):
+                x = x + (complex(y[j]) if cplx else float(np.real(y[j]))) * Z[j]
+        else:
+            upd = torch.zeros_like(b)
+            for j in range(k):
+                upd = upd + complex(y[j]) * V[j] if cplx else upd + float(np.real(y[j])) * V[j]
+            x = x + precond(upd)
         if it < maxiter and resid > tol:
             r = b - torch.mv(A_t, x)
             beta = float(torch.linalg.vector_norm(r)); resid = beta
