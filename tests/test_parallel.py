@@ -70,9 +70,9 @@ def test_partition_tree_invariants(hs, nparts):
         assert len(set(lv[part.cut])) == 1
 
 
-@pytest.mark.parametrize("world,mode", [(2, "tree"), (4, "tree"), (3, "tree"), (4, "replicated")])
+@pytest.mark.parametrize("world,mode", [(2, "tree"), (4, "tree"), (3, "tree"), (4, "replicated"), (8, "tree")])
 def test_gloo_distributed_matches_direct_solve(world, mode):
-    outs = _run_ranks("gloo", world, 33, "poisson", mode)
+    outs = _run_ranks("gloo", world, 65 if world > 4 else 33, "poisson", mode)
     assert all("same=True" in o for _, o in outs)
 
 
