@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(256, 1) k_panel(const Front* __restrict__ fron
       if (gb > 0.0) {  // an exactly singular column is recorded and skipped, as LAPACK getf2 does
         // No per-row predicates here: frozen pivot rows are never searched or stored again, so letting the update
         // run over their registers is harmless, and rows beyond the front hold zeros.
-        const T inv = hs_recip(urow[j]);
+        const T inv = hs_recip_pivot(urow[j]);
         T l[RPT];
 #pragma unroll
         for (int i = 0; i < RPT; ++i) l[i] = hs_mul(colp[tr + TR * i], inv);

@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(TR* TC, MINB) k_front_small(const Front* __res
       __syncthreads();
       // (d) elimination from registers
       if (ok) {
-        const T inv = hs_recip(s_col[par][p]);
+        const T inv = hs_recip_pivot(s_col[par][p]);
         T l[RPT];
 #pragma unroll
         for (int i = 0; i < RPT; ++i) {
