@@ -69,14 +69,14 @@ __global__ void __launch_bounds__(128) k_trtri_diag(const Front* __restrict__ fr
   } else {
     const int j = tid - 64;  // column j of U⁻¹:  x_ij = −(Σ_{i<k≤j} U_ik·x_kj)/U_ii
     const bool act = j < db;
-    if (act) X[j * LDS + j] = hs_recip(S[j * LDS + j]);
+    if (act) X[j * LDS + j] = hs_recip_pivot(S[j * LDS + j]);
     for (int i = db - 2; i >= 0; --i) {
       T sacc = hs_zero<T>();
       for (int k = i + 1; k < db; ++k) {
         const T g = S[k * LDS + i];
         if (act && k <= j && i < j) sacc = hs_fma(sacc, g, X[j * LDS + k]);
       }
-      const T dinv = hs_recip(S[i * LDS + i]);
+      const T dinv = hs_recip_pivot(S[i * LDS + i]);
       if (act && i < j) X[j * LDS + i] = hs_sub(hs_zero<T>(), hs_mul(sacc, dinv));
     }
   }
