@@ -855,6 +855,8 @@ static int32_t factor_impl(hs_ctx* ctx, hs_dtype dtype, int64_t n, const int64_t
     CUDA_OK(cudaStreamSynchronize(st));
     ms_up = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   };
+  // device-resident inputs may still be in flight on the caller's stream; the copies below run on another one
+  if (on_device) CUDA_OK(cudaStreamSynchronize(ctx->stream));
   std::exception_ptr up_err;
   std::thread up_thread([&] { try { upload(); } catch (...) { up_err = std::current_exception(); } });
   try { build_plan(f.get(), tree); } catch (...) { up_thread.join(); throw; }
