@@ -62,7 +62,9 @@ __global__ void __launch_bounds__(256) k_id_init(const IdRun* __restrict__ runs,
 // one step k of every unfinished run: pick the column with the largest remaining norm, produce row k of R for all
 // columns and downdate the norms.  Every CTA of a run repeats the (cheap) pivot search so that no grid-wide barrier
 // is needed; the column norms are double-buffered by the parity of k.
-template <typename T>
+// STAGE: the pivot column (and its R entries) is staged in shared memory; for fronts too tall for that it is read
+// through L2 instead.
+template <typename T, bool STAGE>
 __global__ void __launch_bounds__(256) k_id_step(const IdRun* __restrict__ runs, const T* __restrict__ pool, T* __restrict__ ws,
                                                   double* __restrict__ state, int* __restrict__ ints, int k, double atol,
                                                   double rtol) {
@@ -76,8 +78,8 @@ __global__ void __launch_bounds__(256) k_id_step(const IdRun* __restrict__ runs,
     return;
   }
   extern __shared__ __align__(16) unsigned char smem_id[];
-  T* colp = reinterpret_cast<T*>(smem_id);
-  T* rp = colp + R.m;
+  T* scol = reinterpret_cast<T*>(smem_id);
+  T* srp = scol + (STAGE ? R.m : 0);
   __shared__ double s_v[8];
   __shared__ int s_i[8];
   __shared__ double s_red[8];
@@ -104,8 +106,10 @@ __global__ void __launch_bounds__(256) k_id_step(const IdRun* __restrict__ runs,
   const T* Mp = pool + R.moff + (long long)p * R.ld;
   const T* Rp = ws + R.rws + (long long)p * R.ldr;
   double part = 0.0;
-  for (int i = tid; i < R.m; i += 256) { const T v = Mp[i]; colp[i] = v; part += abs2(v); }
-  for (int l = tid; l < k; l += 256) { const T v = Rp[l]; rp[l] = v; part -= abs2(v); }
+  for (int i = tid; i < R.m; i += 256) { const T v = Mp[i]; if (STAGE) scol[i] = v; part += abs2(v); }
+  for (int l = tid; l < k; l += 256) { const T v = Rp[l]; if (STAGE) srp[l] = v; part -= abs2(v); }
+  const T* colp = STAGE ? scol : Mp;
+  const T* rp = STAGE ? srp : Rp;
   part = wsum(part);
   if (lane == 0) s_red[warp] = part;
   __syncthreads();
@@ -351,8 +355,10 @@ template <typename T> void prepare_impl(hs_fac* f, CompLevel& C) {
     max_m = std::max(max_m, std::max(cf.ni, cf.nb));
     max_rcap = std::max(max_rcap, cf.rcap);
   }
-  const size_t smem = (size_t)(max_m + max_rcap) * sizeof(T);
-  if (smem > 200 * 1024) throw hs_error(HS_ESIZE, "compressed front too large for the pivoted-QR kernel");
+  size_t smem = (size_t)(max_m + max_rcap) * sizeof(T);
+  static const bool no_stage = getenv("HS_ID_NOSTAGE") != nullptr;
+  const bool stage = smem <= 200 * 1024 && !no_stage;  // taller fronts read the pivot column through L2
+  if (!stage) smem = 0;
   CUDA_OK(cudaMemsetAsync(f->d_cint, 0, sizeof(int), st));
   {
     dim3 g(nruns, std::min((max_ncol + 7) / 8, 64));
@@ -366,7 +372,8 @@ template <typename T> void prepare_impl(hs_fac* f, CompLevel& C) {
   while (done < nruns && k <= max_rcap) {
     const int ke = std::min(k + 32, max_rcap + 1);
     for (; k < ke; ++k) {
-      k_id_step<T><<<dim3(nruns, ny), 256, smem, st>>>(d_runs, pool, ws, f->d_cstate, f->d_cint, k, atol, rtol);
+      if (stage) k_id_step<T, true><<<dim3(nruns, ny), 256, smem, st>>>(d_runs, pool, ws, f->d_cstate, f->d_cint, k, atol, rtol);
+      else k_id_step<T, false><<<dim3(nruns, ny), 256, 0, st>>>(d_runs, pool, ws, f->d_cstate, f->d_cint, k, atol, rtol);
       ++f->stats.launches_factor;
     }
     CUDA_OK(cudaGetLastError());
@@ -554,8 +561,8 @@ template <typename T> void solve_impl_c(hs_fac* f, const CompLevel& C, int64_t n
 void hs_comp_setup() {
   CUDA_OK(cudaFuncSetAttribute(k_gemm<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes<double>()));
   CUDA_OK(cudaFuncSetAttribute(k_gemm<cplx, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes<cplx>()));
-  CUDA_OK(cudaFuncSetAttribute(k_id_step<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  CUDA_OK(cudaFuncSetAttribute(k_id_step<cplx>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CUDA_OK(cudaFuncSetAttribute(k_id_step<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CUDA_OK(cudaFuncSetAttribute(k_id_step<cplx, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CUDA_OK(cudaFuncSetAttribute(k_lr_fwd<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   CUDA_OK(cudaFuncSetAttribute(k_lr_fwd<cplx>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
 }
