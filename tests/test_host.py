@@ -95,6 +95,45 @@ def test_golden_fixture(hs, orc):
     assert np.allclose(F.S, g["root_S"]) and np.allclose(orc.nodes_postorder(F)[0].L, g["leaf0_L"], atol=1e-14)
 
 
+def _golden_compressed(hs):
+    import scipy.sparse as sp
+    g = np.load(os.path.join(ROOT, "tests", "golden", "helmholtz2d_33x33_compressed.npz"))
+    prob = hs.grid_problem((33, 33), "helmholtz", nmax=40)
+    A = sp.csc_matrix(prob.A).copy()
+    A.sort_indices()
+    A.data = g["scale"].copy()          # stored in CSC order with sorted row indices
+    opts = dict(swlevel=int(g["swlevel"]), swsize=int(g["swsize"]), atol=float(g["atol"]), rtol=float(g["rtol"]))
+    return g, prob, A, opts
+
+
+def test_golden_fixture_compressed(hs, orc):
+    """tests/golden/helmholtz2d_33x33_compressed.npz: the oracle's compressed branch reproduces its committed output."""
+    import hs_oracle_hss as oh
+    g, prob, A, opts = _golden_compressed(hs)
+    Ao, ndo, ndo_loc, perm = orc.prepare(A, prob.elim_tree)
+    assert np.array_equal(perm, g["perm"])
+    F = orc.factor(Ao, ndo, ndo_loc, **opts)
+    assert np.array_equal(np.asarray(oh.node_ranks(F)), g["ranks"]) and g["ranks"].max() > 0
+    assert np.allclose(orc.ldiv(F, prob.b), g["x"], rtol=0, atol=1e-12)
+    assert np.allclose(F.L_dense(), g["root_L"], atol=1e-12)
+
+
+@pytest.mark.gpu
+def test_gpu_matches_golden_compressed(hs):
+    """The CUDA path against the committed fixture (no oracle at run time)."""
+    g, prob, A, opts = _golden_compressed(hs)
+    Ap, nd, nd_loc, perm = hs.prepare(A, prob.elim_tree)
+    assert np.array_equal(perm, g["perm"])
+    F = hs.factor(Ap, nd, nd_loc, **opts)
+    assert np.array_equal(np.asarray([F.node(k).ranks() for k in range(len(g["ranks"]))]), g["ranks"])
+    x = hs.ldiv(F, prob.b)
+    assert np.linalg.norm(x - g["x"]) / np.linalg.norm(g["x"]) < 1e-8
+    assert np.linalg.norm(F.L - g["root_L"]) / np.linalg.norm(g["root_L"]) < 1e-8
+    xs, ch = hs.gmres(Ap, prob.b, Pr=F, reltol=1e-9, restart=30, maxiter=30, log=True)
+    assert ch.isconverged == bool(g["converged"]) and ch.iters == len(g["resnorm"])
+    assert np.allclose(ch.resnorm, g["resnorm"], rtol=1e-5, atol=1e-12 * np.linalg.norm(prob.b))
+
+
 def test_solver_options(hs):
     o = hs.SolverOptions()
     assert (o.swlevel, o.swsize, o.atol, o.rtol, o.c_tol, o.leafsize, o.kest, o.stepsize, o.verbose) == \
