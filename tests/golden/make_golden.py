@@ -35,7 +35,10 @@ opts = dict(swlevel=-1, swsize=8, atol=1e-4, rtol=1e-4)
 F = orc.factor(Ao, nd, nd_loc, **opts)
 x = orc.ldiv(F, prob.b)
 _, res, conv = orc.gmres(Ao, prob.b, Pr=lambda v: orc.ldiv(F, v), reltol=1e-9, restart=30, maxiter=30)
+ranks = np.asarray(oh.node_ranks(F))
+kc = int(np.nonzero(ranks.max(axis=1) > 0)[0][-1])          # the highest compressed node (post-order id)
+nodec = orc.nodes_postorder(F)[kc]
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "helmholtz2d_33x33_compressed.npz"), scale=A.data, perm=perm,
-                    ranks=np.asarray(oh.node_ranks(F)), x=x, resnorm=np.asarray(res), converged=conv,
-                    root_L=F.L_dense(), **{k: np.asarray(v) for k, v in opts.items()})
+                    ranks=ranks, x=x, resnorm=np.asarray(res), converged=conv, node=kc, node_L=nodec.L_dense(),
+                    node_R=nodec.R_dense(), **{k: np.asarray(v) for k, v in opts.items()})
 print("wrote helmholtz2d_33x33_compressed.npz  maxrank", orc.maxrank(F), "gmres", len(res))

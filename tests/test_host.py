@@ -115,7 +115,8 @@ def test_golden_fixture_compressed(hs, orc):
     F = orc.factor(Ao, ndo, ndo_loc, **opts)
     assert np.array_equal(np.asarray(oh.node_ranks(F)), g["ranks"]) and g["ranks"].max() > 0
     assert np.allclose(orc.ldiv(F, prob.b), g["x"], rtol=0, atol=1e-12)
-    assert np.allclose(F.L_dense(), g["root_L"], atol=1e-12)
+    nodec = orc.nodes_postorder(F)[int(g["node"])]
+    assert np.allclose(nodec.L_dense(), g["node_L"], atol=1e-12) and np.allclose(nodec.R_dense(), g["node_R"], atol=1e-12)
 
 
 @pytest.mark.gpu
@@ -128,7 +129,9 @@ def test_gpu_matches_golden_compressed(hs):
     assert np.array_equal(np.asarray([F.node(k).ranks() for k in range(len(g["ranks"]))]), g["ranks"])
     x = hs.ldiv(F, prob.b)
     assert np.linalg.norm(x - g["x"]) / np.linalg.norm(g["x"]) < 1e-8
-    assert np.linalg.norm(F.L - g["root_L"]) / np.linalg.norm(g["root_L"]) < 1e-8
+    nk = F.node(int(g["node"]))
+    assert np.linalg.norm(nk.L - g["node_L"]) / np.linalg.norm(g["node_L"]) < 1e-8
+    assert np.linalg.norm(nk.R - g["node_R"]) / np.linalg.norm(g["node_R"]) < 1e-8
     xs, ch = hs.gmres(Ap, prob.b, Pr=F, reltol=1e-9, restart=30, maxiter=30, log=True)
     assert ch.isconverged == bool(g["converged"]) and ch.iters == len(g["resnorm"])
     assert np.allclose(ch.resnorm, g["resnorm"], rtol=1e-5, atol=1e-12 * np.linalg.norm(prob.b))
