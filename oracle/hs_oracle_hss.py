@@ -81,39 +81,71 @@ def _rgauss_transform(D, Aib: BlockMatrix, atol, rtol) -> LowRankMatrix:
     return R
 
 
-def _factor_branch_compressed(A, Fl, Fr, nd, nd_loc, atol, rtol) -> FactorNode:
-    """factorization.jl:78-112 with the Schur operator of :228-249 evaluated densely (module docstring)."""
+def _S(F):
+    """Dense view of a child's Schur complement (an ``HssMatrix`` in ``hss`` mode)."""
+    return F.S.dense() if hasattr(F.S, "dense") else F.S
+
+
+def _to_hss(S, n1, leafsize, atol, rtol):
+    """``compress(S[perm,perm], cl, cl)`` / ``randcompress_adaptive(Smap, cl, cl)`` with
+    ``cl = bisection_cluster((n1, n); leafsize)`` (factorization.jl:56-57,109-110): the first split separates what the
+    parent eliminates from what it passes up.  The randomized construction of the reference and this direct one
+    approximate the same operator to the same tolerance; they do not produce identical generators."""
+    import hs_hss
+    cl = hs_hss.bisection_cluster((n1, S.shape[0]), leafsize)
+    return hs_hss.compress(S, cl, cl, atol, rtol)
+
+
+def _factor_branch_compressed(A, Fl, Fr, nd, nd_loc, atol, rtol, hss=False, leafsize=32) -> FactorNode:
+    """factorization.jl:78-112 with the Schur operator of :228-249 evaluated densely (module docstring).  ``hss=True``
+    stores its HSS approximation (oracle/hs_hss.py) like the reference; parents then assemble from the approximated
+    blocks, which is what the reference's HSS-children methods (:126-140, blockmatrix.jl:121-130) do in HSS arithmetic."""
     int1 = nd.left.bnd[nd_loc.left.int - 1]
     bnd1 = nd.left.bnd[nd_loc.left.bnd - 1]
     int2 = nd.right.bnd[nd_loc.right.int - 1]
     bnd2 = nd.right.bnd[nd_loc.right.bnd - 1]
-    Aii, Aib, Abi, Abb = _assemble_blocks(A, Fl.S, Fr.S, int1, int2, bnd1, bnd2)
+    Aii, Aib, Abi, Abb = _assemble_blocks(A, _S(Fl), _S(Fr), int1, int2, bnd1, bnd2)
     D = blockfactor(Aii)                                   # :94
     L = _lgauss_transform(D, Abi, 0.5 * atol, 0.5 * rtol)  # :99
     R = _rgauss_transform(D, Aib, 0.5 * atol, 0.5 * rtol)  # :100
     U = Abi.dense() @ R.U                                  # :230  U = Abi*R
     S = Abb.dense() - U @ R.V.conj().T                     # :242,:248
     perm = np.concatenate([nd_loc.int, nd_loc.bnd]) - 1    # :107
-    return FactorNode(D, S[np.ix_(perm, perm)], L, R, nd.int, nd.bnd, nd_loc.int, nd_loc.bnd, Fl, Fr)
+    Sp = S[np.ix_(perm, perm)]
+    if hss and len(perm):
+        Sp = _to_hss(Sp, len(nd_loc.int), leafsize, atol, rtol)   # :109-110
+    return FactorNode(D, Sp, L, R, nd.int, nd.bnd, nd_loc.int, nd_loc.bnd, Fl, Fr)
 
 
-def factor(A, nd, nd_loc, swlevel=5, swsize=1, atol=1e-6, rtol=1e-6, **_unused) -> FactorNode:
-    """factorization.jl:5-11 — options as ``SolverOptions`` (HierarchicalSolvers.jl:30-40 defaults)."""
+def factor(A, nd, nd_loc, swlevel=5, swsize=1, atol=1e-6, rtol=1e-6, leafsize=32, hss=False, **_unused) -> FactorNode:
+    """factorization.jl:5-11 — options as ``SolverOptions`` (HierarchicalSolvers.jl:30-40 defaults).  ``hss=False`` (what
+    the CUDA library implements this round) keeps every Schur complement dense; ``hss=True`` stores the HSS
+    approximation of compressed nodes' Schur complements as the reference does."""
     A = sp.csr_matrix(A)
     sw = max(base.depth(nd) + swlevel, 0) if swlevel < 0 else swlevel   # :8
-    return _factor(A, nd, nd_loc, 1, sw, swsize, atol, rtol)
+    return _factor(A, nd, nd_loc, 1, sw, swsize, atol, rtol, hss, leafsize)
 
 
-def _factor(A, nd, nd_loc, level, swlevel, swsize, atol, rtol) -> FactorNode:
+def _factor(A, nd, nd_loc, level, swlevel, swsize, atol, rtol, hss=False, leafsize=32) -> FactorNode:
     """factorization.jl:14-27."""
     compression_flag = level <= swlevel and len(nd.bnd) >= swsize   # :15
     if isleaf(nd):
-        return _factor_leaf(A, nd, nd_loc)     # :30-42 and :45-59 coincide while S stays dense
+        F = _factor_leaf(A, nd, nd_loc)        # :30-42; the compressed leaf (:45-59) differs only in the storage of S
+        if compression_flag and hss and F.S.shape[0]:
+            F.S = _to_hss(F.S, len(nd_loc.int), leafsize, atol, rtol)   # :56-57
+        return F
     elif isbranch(nd):
-        Fl = _factor(A, nd.left, nd_loc.left, level + 1, swlevel, swsize, atol, rtol)
-        Fr = _factor(A, nd.right, nd_loc.right, level + 1, swlevel, swsize, atol, rtol)
+        Fl = _factor(A, nd.left, nd_loc.left, level + 1, swlevel, swsize, atol, rtol, hss, leafsize)
+        Fr = _factor(A, nd.right, nd_loc.right, level + 1, swlevel, swsize, atol, rtol, hss, leafsize)
         if compression_flag:
-            return _factor_branch_compressed(A, Fl, Fr, nd, nd_loc, atol, rtol)
+            return _factor_branch_compressed(A, Fl, Fr, nd, nd_loc, atol, rtol, hss, leafsize)
+        if hss and (hasattr(Fl.S, "dense") or hasattr(Fr.S, "dense")):
+            # an uncompressed node above compressed children (always the root, factorization.jl:15 with |bnd| = 0)
+            class _V:      # children viewed through their dense Schur blocks
+                def __init__(self, F): self.S = _S(F)
+            F = base._factor_branch(A, _V(Fl), _V(Fr), nd, nd_loc)
+            F.left, F.right = Fl, Fr
+            return F
         return base._factor_branch(A, Fl, Fr, nd, nd_loc)
     raise RuntimeError("Expected nested dissection to be a binary tree. Found a node with only one child.")
 

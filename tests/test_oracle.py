@@ -132,3 +132,78 @@ def test_oracle_pqrfact_truncation_rule():
     assert np.allclose(Q.T @ Q, np.eye(Q.shape[1]), atol=1e-12)
     Q0, R0 = oh.pqrfact(np.zeros((5, 4)), atol=1e-3, rtol=1e-3)
     assert Q0.shape == (5, 0) and R0.shape == (0, 4)
+
+
+# ---- HSS matrices (oracle/hs_hss.py): restatement of the un-vendored HssMatrices.jl entry points ---------------------
+def _kernel_matrix(n=240, seed=0, cplx=False):
+    rng = np.random.default_rng(seed)
+    x = np.sort(rng.random(n))
+    d = abs(x[:, None] - x[None, :])
+    A = 1.0 / (1.0 + 50.0 * d) + 2.0 * np.eye(n)
+    return A + 1j * np.exp(-d) if cplx else A
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("tol", [1e-2, 1e-6, 1e-10])
+def test_hss_compress_accuracy_and_algebra(orc, tol, cplx):
+    import hs_hss as H
+    A = _kernel_matrix(cplx=cplx)
+    n = A.shape[0]
+    cl = H.bisection_cluster(n, leafsize=32)
+    h = H.compress(A, cl, cl, atol=tol, rtol=tol)
+    F = H.full(h)
+    # every block row / column was cut at |R[k,k]| ≤ max(atol, rtol·|R[1,1]|): the error stays within a modest multiple
+    assert np.linalg.norm(F - A, 2) <= 20 * tol * max(1.0, np.linalg.norm(A, 2))
+    assert 0 < H.hssrank(h) < 32
+    X = np.random.default_rng(1).standard_normal((n, 3))
+    assert np.allclose(H.matmul(h, X), F @ X, atol=1e-12)              # O(n·r) product = product with full(h)
+    assert np.allclose(F @ H.solve(h, X), X, atol=1e-10)               # `\\` is exact for the represented matrix
+    U, V = H.generators(h.A11)                                          # nested, orthonormal bases
+    assert np.allclose(U.conj().T @ U, np.eye(U.shape[1]), atol=1e-10)
+    assert np.allclose(V.conj().T @ V, np.eye(V.shape[1]), atol=1e-10)
+    U2, V2 = H.generators(h.A22)
+    assert np.allclose(U @ h.B12 @ V2.conj().T, F[:h.A11.rows, h.A11.cols:], atol=1e-12)
+    rc, cc = H.cluster(h)
+    assert H.compatible(rc, cl) and H.compatible(cc, cl)
+    if tol == 1e-6:
+        looser = H.compress(A, cl, cl, atol=1e-2, rtol=1e-2)
+        assert H.hssrank(looser) < H.hssrank(h)
+
+
+def test_hss_cluster_first_split_and_pruning(orc):
+    import hs_hss as H
+    cl = H.bisection_cluster((70, 240), leafsize=40)                    # factorization.jl:56,109
+    assert (cl.left.size, cl.right.size) == (70, 170)
+    assert all(leaf <= 40 for leaf in _leaf_sizes(cl))
+    A = _kernel_matrix()
+    h = H.compress(A, cl, cl, 1e-8, 1e-8)
+    assert h.A11.shape == (70, 70) and h.A22.shape == (170, 170)        # S.A11 = what the parent eliminates
+    d0 = H.depth(H.cluster(h)[0])
+    hp = H.prune_leaves(h)
+    assert H.depth(H.cluster(hp)[0]) == d0 - 1
+    assert np.allclose(H.full(hp), H.full(H.compress(A, cl, cl, 1e-8, 1e-8)), atol=1e-12)
+
+
+def _leaf_sizes(cl):
+    return [cl.size] if cl.isleaf() else _leaf_sizes(cl.left) + _leaf_sizes(cl.right)
+
+
+@pytest.mark.parametrize("kind", ["poisson", "helmholtz"])
+def test_oracle_factor_with_hss_schur_complements(hs, orc, kind):
+    """``hss=True``: compressed nodes store the HSS approximation of their Schur complement like the reference
+    (factorization.jl:110); maxrank then also sees ``hssrank(S)`` and the preconditioner stays of the same quality."""
+    import hs_hss as H
+    prob = hs.grid_problem((65, 65), kind, nmax=40)
+    Ap, nd, nd_loc, _ = orc.prepare(prob.A, prob.elim_tree)
+    opts = dict(swlevel=-2, swsize=16, atol=1e-4, rtol=1e-4)
+    Fd = orc.factor(Ap, nd, nd_loc, **opts)
+    Fh = orc.factor(Ap, nd, nd_loc, hss=True, leafsize=16, **opts)
+    nh = [n for n in orc.nodes_postorder(Fh) if isinstance(n.S, H.HssMatrix)]
+    assert nh and all(n.S.A11.rows == len(n.int_loc) for n in nh if not n.S.leaf and 0 < len(n.int_loc) < n.S.rows)
+    assert orc.maxrank(Fh) >= max(n.S.rank for n in nh)
+    xd, xh = orc.ldiv(Fd, prob.b), orc.ldiv(Fh, prob.b)
+    rd = np.linalg.norm(Ap @ xd - prob.b) / np.linalg.norm(prob.b)
+    rh = np.linalg.norm(Ap @ xh - prob.b) / np.linalg.norm(prob.b)
+    assert rh < 50 * max(rd, 1e-4)
+    _, res, conv = orc.gmres(Ap, prob.b, Pr=lambda v: orc.ldiv(Fh, v), reltol=1e-9, restart=30, maxiter=30)
+    assert conv and len(res) <= 8
