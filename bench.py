@@ -457,7 +457,7 @@ def main():
         return
     line = {"metric": METRIC, "value": ms_step * 1e-3, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": False,
-            "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "c64" if cx else "f64",
+            "scaling": "strong", "vs_baseline": None, "dtype": "c64" if cx else "f64",
             "data": "synthetic", "config": config,
             "factor_ms": fac_ms_mean, "solve_ms": ms_step - fac_ms_mean, "gmres_iters": gm_iters, "residual": resid,
             "factor_tflops": flops / (fac_ms_mean * 1e-3) / 1e12, "factor_flops": flops,
