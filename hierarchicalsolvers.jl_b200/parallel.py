@@ -63,6 +63,7 @@ def _slice_tree(nd: NestedDissection, loc: NDLoc, nodes: np.ndarray, as_leaf: se
     out.analyzed = True
     out.depth = nd.depth
 
+    contiguous = len(nodes) > 0 and int(nodes[-1]) - int(nodes[0]) + 1 == len(nodes)
     leaf_mask = np.isin(nodes, np.fromiter(as_leaf, dtype=np.int64, count=len(as_leaf))) if as_leaf else np.zeros(len(nodes), bool)
 
     def remap(child):
@@ -77,6 +78,9 @@ def _slice_tree(nd: NestedDissection, loc: NDLoc, nodes: np.ndarray, as_leaf: se
     def ragged(ptr, idx, drop=()):
         # vectorised gather of the ragged rows `nodes` (no Python loop: the trees have 10^5 nodes)
         ptr = np.asarray(ptr, dtype=np.int64)
+        if contiguous and not drop:   # a subtree is a contiguous post-order range: plain slices
+            lo, hi = int(nodes[0]), int(nodes[-1]) + 1
+            return ptr[lo:hi + 1] - ptr[lo], np.asarray(idx[ptr[lo]:ptr[hi]], dtype=np.int64)
         lens = (ptr[1:] - ptr[:-1])[nodes].copy()
         if drop:
             lens[leaf_mask] = 0
