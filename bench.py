@@ -207,8 +207,7 @@ def run_distributed(args, hs, torch, world, rank, local_rank, Ap, nd, nd_loc, b,
     t0 = time.perf_counter()
     DF = DistributedFactor(Ap, nd, nd_loc, engine=eng, swlevel=0)
     t_first = time.perf_counter() - t0
-    A_t = torch.sparse_csr_tensor(torch.from_numpy(Ap.tocsr().indptr.astype(np.int64)), torch.from_numpy(Ap.tocsr().indices.astype(np.int64)),
-                                  torch.from_numpy(np.ascontiguousarray(Ap.tocsr().data)).to(tdt), size=Ap.shape).to("cuda")
+    A_t = eng.matvec(DF.h_sub)   # v -> A·v with the matrix this rank's subtree factorization holds in HBM (hs_spmv)
     b_dev = eng.to_device(b)
     out = {}
 
@@ -257,7 +256,7 @@ def run_distributed(args, hs, torch, world, rank, local_rank, Ap, nd, nd_loc, b,
         t0 = time.perf_counter()
         DF2 = DistributedFactor(Ap, nd, nd_loc, engine=eng, swlevel=0)
         bh = eng.to_device(b)
-        x2, _, _ = gmres_replicated(A_t, bh, DF2.ldiv_device, 1e-9, 30, 30)
+        x2, _, _ = gmres_replicated(eng.matvec(DF2.h_sub), bh, DF2.ldiv_device, 1e-9, 30, 30)
         _ = x2.cpu()
         torch.cuda.synchronize()
         te = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)

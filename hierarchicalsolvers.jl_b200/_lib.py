@@ -84,6 +84,7 @@ PROTOTYPES = [
     ("hs_node_rank", C.c_int32, [C.c_void_p, C.c_int64, i64p, i64p]),
     ("hs_stats", C.c_int32, [C.c_void_p, C.POINTER(hs_stats_t)]),
     ("hs_resolved_swlevel", C.c_int32, [C.c_void_p, i64p]),
+    ("hs_spmv", C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p]),
     ("hs_matrix_device", C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), i64p]),
     ("hs_gmres", C.c_int32, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                              C.c_void_p, C.c_void_p, C.c_double, C.c_int64, C.c_int64, C.POINTER(C.c_double), i64p,

@@ -332,6 +332,29 @@ void gmres_entry(hs_ctx* ctx, long long n, const int64_t* colptr, const int64_t*
 
 }  // namespace
 
+// y = A·x on the device with the matrix the factorization holds (CSR image built on first use, as hs_gmres does)
+template <typename T> static void spmv_impl(hs_fac* f, const void* x, void* y) {
+  if (!f->d_csr_ptr) {
+    T* cv = nullptr;
+    build_csr<T>(f, f->d_colptr, f->d_rowval, (const T*)f->d_nzval, f->nnz, &f->d_csr_ptr, &f->d_csr_col, &cv);
+    f->d_csr_val = cv;
+  }
+  const unsigned gb = (unsigned)((f->n + 255) / 256);
+  k_spmv_csr<T><<<gb, 256, 0, f->ctx->stream>>>(f->n, f->d_csr_ptr, f->d_csr_col, (const T*)f->d_csr_val, (const T*)x, (T*)y);
+  CUDA_OK(cudaGetLastError());
+  ++f->ctx->launches;
+}
+
+extern "C" int32_t hs_spmv(hs_fac* f, const void* x, void* y) {
+  HS_TRY_BEGIN
+  if (!f || !x || !y) return hs_fail(HS_EARG, "hs_spmv: null argument");
+  if (x == y) return hs_fail(HS_EARG, "hs_spmv: x and y must not alias");
+  CUDA_OK(cudaSetDevice(f->ctx->device));
+  if (f->dtype == HS_F64) spmv_impl<double>(f, x, y); else spmv_impl<cplx>(f, x, y);
+  return HS_OK;
+  HS_TRY_END
+}
+
 extern "C" int32_t hs_gmres(hs_ctx* ctx, hs_dtype dtype, int64_t n, const int64_t* colptr, const int64_t* rowval,
                             const void* nzval, int32_t index_base, hs_fac* fac, const void* b, void* x, double reltol,
                             int64_t restart, int64_t maxiter, double* resnorm, int64_t* niter, int32_t* converged,

@@ -242,6 +242,14 @@ class CudaEngine:
     def numeric(self, h):
         _lib.check(_lib.lib.hs_refactor(h, None, 0))
 
+    def matvec(self, h):
+        """``v -> A·v`` on the device with the matrix factorization ``h`` holds (``hs_spmv``)."""
+        def mv(v):
+            out = self.torch.empty_like(v)
+            _lib.check(_lib.lib.hs_spmv(h, C.c_void_p(v.data_ptr()), C.c_void_p(out.data_ptr())))
+            return out
+        return mv
+
     def to_device(self, b):
         return self.torch.from_numpy(np.ascontiguousarray(b, dtype=self.np_dtype)).to(f"cuda:{self.device}")
 
@@ -439,9 +447,10 @@ class DistributedFactor:
 
 def gmres_replicated(A_t, b, precond, reltol=1e-9, restart=30, maxiter=30):
     """Right-preconditioned restarted GMRES (test/rungmres.jl:47 semantics) on device tensors, run identically on every
-    rank: ``A_t`` is a torch sparse CSR matrix, ``precond(v)`` overwrites ``v`` with Pr⁻¹·v (``DistributedFactor.ldiv_device``).
-    Returns ``(x, resnorms, converged)``."""
+    rank: ``A_t`` is a torch sparse CSR matrix or a callable ``v -> A·v`` (``CudaEngine.matvec``), ``precond(v)`` overwrites
+    ``v`` with Pr⁻¹·v (``DistributedFactor.ldiv_device``).  Returns ``(x, resnorms, converged)``."""
     import torch
+    mv = A_t if callable(A_t) else (lambda v: torch.mv(A_t, v))
     n = b.shape[0]
     x = torch.zeros_like(b)
     r = b.clone()
@@ -460,7 +469,7 @@ def gmres_replicated(A_t, b, precond, reltol=1e-9, restart=30, maxiter=30):
             z = precond(V[k].clone())
             if k < 4:
                 Z.append(z)
-            w = torch.mv(A_t, z)
+            w = mv(z)
             for j in range(k + 1):
                 h = torch.vdot(V[j], w)
                 H[j, k] = h.item()
@@ -493,6 +502,6 @@ def gmres_replicated(A_t, b, precond, reltol=1e-9, restart=30, maxiter=30):
                 upd = upd + complex(y[j]) * V[j] if cplx else upd + float(np.real(y[j])) * V[j]
             x = x + precond(upd)
         if it < maxiter and resid > tol:
-            r = b - torch.mv(A_t, x)
+            r = b - mv(x)
             beta = float(torch.linalg.vector_norm(r)); resid = beta
     return x, res, bool(resid <= tol)

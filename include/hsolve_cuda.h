@@ -205,6 +205,9 @@ int32_t hs_resolved_swlevel(hs_fac* fac, int64_t* swlevel);  /* factorization.jl
 /* Device-resident copy of the matrix a factorization holds (0-based int64 colptr / rowval, nzval of the factorization's
  * dtype): lets further hs_factor / hs_analyze calls on the same matrix (the upper fronts of the subtree-per-GPU mapping)
  * pass HS_ON_DEVICE | HS_CSC_ZERO_BASED instead of uploading the CSC arrays again.  Valid until hs_factor_free(fac). */
+/* y = A·x on the device (x, y device vectors of the factorization's dtype, asynchronous on the context's stream) with the
+ * matrix `fac` holds — the mat-vec of a Krylov loop driven from the host side (replicated GMRES of the multi-GPU path). */
+int32_t hs_spmv(hs_fac* fac, const void* x, void* y);
 int32_t hs_matrix_device(hs_fac* fac, const int64_t** colptr, const int64_t** rowval, const void** nzval, int64_t* nnz);
 
 /* ---- GMRES with the factorization as right preconditioner (test/rungmres.jl:47-48) ---------------

@@ -278,3 +278,24 @@ def test_gmres_edge_cases(hs):
     assert h.iters == 12 and len(h.resnorm) == 12
     x, h = hs.gmres(Ap, np.zeros_like(prob.b), Pr=F, log=True)        # zero right-hand side converges immediately
     assert h.iters == 0 and np.all(x == 0)
+
+
+@pytest.mark.parametrize("kind", ["poisson", "helmholtz"])
+def test_spmv_with_the_resident_matrix(hs, kind):
+    """hs_spmv: y = A·x with the matrix a factorization holds (the mat-vec of the host-driven replicated GMRES)."""
+    import ctypes as C
+    import torch
+    prob = hs.grid_problem((33, 31), kind, nmax=40)
+    Ap, nd, nd_loc, _ = hs.prepare(prob.A, prob.elim_tree)
+    F = hs.factor(Ap, nd, nd_loc, swlevel=0)
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(Ap.shape[0]) + (1j * rng.standard_normal(Ap.shape[0]) if kind == "helmholtz" else 0)
+    xd = torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    yd = torch.empty_like(xd)
+    torch.cuda.synchronize()
+    hs._lib.check(hs._lib.lib.hs_spmv(F._hd.h, C.c_void_p(xd.data_ptr()), C.c_void_p(yd.data_ptr())))
+    hs.ldiv(F, prob.b)   # a synchronising call on the library's stream
+    torch.cuda.synchronize()
+    assert rel(yd.cpu().numpy(), Ap @ x) < 1e-13
+    with pytest.raises(hs.ArgumentError):
+        hs._lib.check(hs._lib.lib.hs_spmv(F._hd.h, C.c_void_p(xd.data_ptr()), C.c_void_p(xd.data_ptr())))
