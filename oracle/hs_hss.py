@@ -246,3 +246,93 @@ def prune_leaves(h: HssMatrix) -> HssMatrix:
         return out
     h.A11, h.A22 = prune_leaves(h.A11), prune_leaves(h.A22)
     return h
+
+
+# ------------------------------------------------------------------------------------------------
+# randomized construction from products and entries only (Martinsson 2011; `randcompress_adaptive`)
+# ------------------------------------------------------------------------------------------------
+def _row_id(S: np.ndarray, atol: float, rtol: float):
+    """Row interpolative decomposition ``S ≈ X·S[skel]`` with ``X[skel] = I`` from a column-pivoted QR of ``Sᴴ``,
+    truncated by the rule of ``pqrfact``.  Returns ``(X, skel)``."""
+    import scipy.linalg as sla
+    m = S.shape[0]
+    if m == 0 or S.shape[1] == 0:
+        return np.zeros((m, 0), dtype=S.dtype), np.zeros(0, dtype=np.int64)
+    _, R, p = sla.qr(S.conj().T, mode="economic", pivoting=True)
+    d = np.abs(np.diag(R))
+    ptol = max(atol, rtol * d[0]) if len(d) else 0.0
+    below = np.nonzero(d <= ptol)[0]
+    r = int(below[0]) if len(below) else len(d)
+    X = np.zeros((m, r), dtype=S.dtype)
+    if r:
+        X[p[:r]] = np.eye(r, dtype=S.dtype)
+        if r < m:
+            T = sla.solve_triangular(R[:r, :r], R[:r, r:])          # S[p[r:]]ᴴ ≈ S[p[:r]]ᴴ·T
+            X[p[r:]] = T.conj().T
+    return X, np.asarray(p[:r], dtype=np.int64)
+
+
+def randcompress_adaptive(mul, mulc, getidx, rcl: ClusterTree, ccl: ClusterTree, kest: int = 10, stepsize: int = 10,
+                          atol: float = 1e-9, rtol: float = 1e-9, rng=None, sketches=None, max_rounds: int = 12) -> HssMatrix:
+    """HSS form of an operator given only by ``mul(X) = A·X``, ``mulc(X) = Aᴴ·X`` and ``getidx(I, J) = A[I, J]`` (0-based
+    index vectors) — the ``LinearMap`` the reference builds for the Schur complement (factorization.jl:228-235) and hands
+    to ``randcompress_adaptive(Smap, cl, cl; kest, atol, rtol)`` (:110).  Gaussian test matrices with ``kest`` columns
+    (plus 10 of oversampling), interpolative decompositions per node, couplings ``B12/B21`` read at skeleton×skeleton
+    index sets; when a detected rank saturates the sample count, ``stepsize`` more columns are drawn and the
+    construction is repeated.  ``sketches = (Ω, Ψ)`` fixes the test matrices (parity runs); otherwise ``rng``."""
+    m, n = rcl.size, ccl.size
+    if not compatible_shape(rcl, ccl):
+        raise ValueError("DimensionMismatch: row and column cluster trees differ in shape")
+    rng = rng or np.random.default_rng(0)
+    k = int(kest) + 10
+    for _ in range(max_rounds):
+        if sketches is not None and sketches[0].shape[1] >= k:
+            Om, Ps = sketches[0][:, :k], sketches[1][:, :k]
+        else:
+            Om, Ps = rng.standard_normal((n, k)), rng.standard_normal((m, k))
+        Sr, Sc = mul(Om), mulc(Ps)
+        saturated = [False]
+
+        def rec(rc, cc, root):
+            h = HssMatrix()
+            I, J = np.arange(rc.lo, rc.hi), np.arange(cc.lo, cc.hi)
+            h.rows, h.cols = len(I), len(J)
+            if rc.isleaf():
+                h.leaf = True
+                h.D = np.asarray(getidx(I, J))
+                if root:
+                    return h, None
+                Sr_loc = Sr[I] - h.D @ Om[J]
+                Sc_loc = Sc[J] - h.D.conj().T @ Ps[I]
+                h.U, sr = _row_id(Sr_loc, atol, rtol)
+                h.V, sc = _row_id(Sc_loc, atol, rtol)
+                if max(len(sr), len(sc)) >= k - 10:
+                    saturated[0] = True
+                st = dict(Iskel=I[sr], Jskel=J[sc], Sr=Sr_loc[sr], Sc=Sc_loc[sc], Om=h.V.conj().T @ Om[J], Ps=h.U.conj().T @ Ps[I])
+                return h, st
+            h.leaf = False
+            h.A11, s1 = rec(rc.left, cc.left, False)
+            h.A22, s2 = rec(rc.right, cc.right, False)
+            h.B12 = np.asarray(getidx(s1["Iskel"], s2["Jskel"]))
+            h.B21 = np.asarray(getidx(s2["Iskel"], s1["Jskel"]))
+            if root:
+                return h, None
+            Sr_t = np.vstack([s1["Sr"] - h.B12 @ s2["Om"], s2["Sr"] - h.B21 @ s1["Om"]])
+            Sc_t = np.vstack([s1["Sc"] - h.B21.conj().T @ s2["Ps"], s2["Sc"] - h.B12.conj().T @ s1["Ps"]])
+            R, sr = _row_id(Sr_t, atol, rtol)
+            W, sc = _row_id(Sc_t, atol, rtol)
+            if max(len(sr), len(sc)) >= k - 10:
+                saturated[0] = True
+            r1, w1 = len(s1["Iskel"]), len(s1["Jskel"])
+            h.R1, h.R2, h.W1, h.W2 = R[:r1], R[r1:], W[:w1], W[w1:]
+            Isk = np.concatenate([s1["Iskel"], s2["Iskel"]])[sr]
+            Jsk = np.concatenate([s1["Jskel"], s2["Jskel"]])[sc]
+            st = dict(Iskel=Isk, Jskel=Jsk, Sr=Sr_t[sr], Sc=Sc_t[sc],
+                      Om=W.conj().T @ np.vstack([s1["Om"], s2["Om"]]), Ps=R.conj().T @ np.vstack([s1["Ps"], s2["Ps"]]))
+            return h, st
+
+        h, _ = rec(rcl, ccl, True)
+        if not saturated[0] or k >= min(m, n) + 10:
+            return h
+        k += int(stepsize)
+    return h

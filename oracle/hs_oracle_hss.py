@@ -6,7 +6,8 @@ CUDA library implements in this round:
 * the Gauss transforms ``L ≈ Abi·Aii⁻¹`` and ``R ≈ Aii⁻¹·Aib`` are low-rank, from a truncated column-pivoted QR of
   the dense coupling blocks (dense-children methods, factorization.jl:171-182) — followed line by line;
 * the Schur complement operator ``S = Abb − (Abi·R.U)·R.Vᴴ`` (factorization.jl:228-249) is *evaluated densely and
-  kept dense*.  The reference hands that operator to ``HssMatrices.randcompress_adaptive`` (factorization.jl:110,
+  kept dense* by default (``hss=False``, the form the CUDA library implements; ``hss=True`` / ``hss="rand"`` store the
+  HSS approximation through oracle/hs_hss.py — the second by the reference's matrix-free randomized route).  The reference hands that operator to ``HssMatrices.randcompress_adaptive`` (factorization.jl:110,
   third party, source absent) and stores the HSS approximation; here the HSS tolerance is taken to zero.  Because
   every ``S`` stays dense, the HSS-children methods (``_assemble_blocks`` :126-140, ``_equilibrate_clusters``
   :143-168, all-HSS ``blockfactor`` blockmatrix.jl:121-130, HSS Gauss transforms :184-209) are never reached.
@@ -96,7 +97,32 @@ def _to_hss(S, n1, leafsize, atol, rtol):
     return hs_hss.compress(S, cl, cl, atol, rtol)
 
 
-def _factor_branch_compressed(A, Fl, Fr, nd, nd_loc, atol, rtol, hss=False, leafsize=32) -> FactorNode:
+def _schur_complement(Abb, Abi, R: "LowRankMatrix", perm):
+    """factorization.jl:228-249: the Schur complement ``S[perm,perm]`` as products and entry evaluation only.
+    Returns ``(Smul, Smulc, Sidx)``; index arguments of ``Sidx`` are 0-based vectors."""
+    iperm = np.argsort(perm)
+    UU, UV = Abi @ R.U, R.V                                  # :230  U = Abi*R  (LowRankMatrix)
+
+    def Smul(x):                                             # :239-244  _sample_schur!
+        z = x[iperm]
+        y = np.empty((len(perm), x.shape[1]), dtype=np.result_type(Abb, x))
+        y[iperm] = Abb @ z - UU @ (UV.conj().T @ z)
+        return y
+
+    def Smulc(x):                                            # :233  the same with Abb', U'
+        z = x[iperm]
+        y = np.empty((len(perm), x.shape[1]), dtype=np.result_type(Abb, x))
+        y[iperm] = Abb.conj().T @ z - UV @ (UU.conj().T @ z)
+        return y
+
+    def Sidx(i, j):                                          # :246-249  _getindex_schur
+        ii, jj = perm[i], perm[j]
+        return Abb[np.ix_(ii, jj)] - UU[ii] @ UV[jj].conj().T
+
+    return Smul, Smulc, Sidx
+
+
+def _factor_branch_compressed(A, Fl, Fr, nd, nd_loc, atol, rtol, hss=False, leafsize=32, kest=-1, stepsize=10) -> FactorNode:
     """factorization.jl:78-112 with the Schur operator of :228-249 evaluated densely (module docstring).  ``hss=True``
     stores its HSS approximation (oracle/hs_hss.py) like the reference; parents then assemble from the approximated
     blocks, which is what the reference's HSS-children methods (:126-140, blockmatrix.jl:121-130) do in HSS arithmetic."""
@@ -112,21 +138,32 @@ def _factor_branch_compressed(A, Fl, Fr, nd, nd_loc, atol, rtol, hss=False, leaf
     S = Abb.dense() - U @ R.V.conj().T                     # :242,:248
     perm = np.concatenate([nd_loc.int, nd_loc.bnd]) - 1    # :107
     Sp = S[np.ix_(perm, perm)]
-    if hss and len(perm):
-        Sp = _to_hss(Sp, len(nd_loc.int), leafsize, atol, rtol)   # :109-110
+    if hss == "rand" and len(perm):
+        # the reference's own route (:102-110): matrix-free operator + randomized adaptive HSS construction
+        import hs_hss
+        if kest < 0:
+            kest = int(np.ceil(0.5 * L.rank))                                             # :102-104
+        Smul, Smulc, Sidx = _schur_complement(Abb.dense(), Abi.dense(), R, perm)         # :108
+        cl = hs_hss.bisection_cluster((len(nd_loc.int), len(perm)), leafsize)             # :109
+        Sp = hs_hss.randcompress_adaptive(Smul, Smulc, Sidx, cl, cl, kest=kest, stepsize=stepsize, atol=atol, rtol=rtol,
+                                          rng=np.random.default_rng(len(perm)))           # :110
+    elif hss and len(perm):
+        Sp = _to_hss(Sp, len(nd_loc.int), leafsize, atol, rtol)   # :109-110 by the direct construction
     return FactorNode(D, Sp, L, R, nd.int, nd.bnd, nd_loc.int, nd_loc.bnd, Fl, Fr)
 
 
-def factor(A, nd, nd_loc, swlevel=5, swsize=1, atol=1e-6, rtol=1e-6, leafsize=32, hss=False, **_unused) -> FactorNode:
+def factor(A, nd, nd_loc, swlevel=5, swsize=1, atol=1e-6, rtol=1e-6, leafsize=32, kest=-1, stepsize=10, hss=False,
+           **_unused) -> FactorNode:
     """factorization.jl:5-11 — options as ``SolverOptions`` (HierarchicalSolvers.jl:30-40 defaults).  ``hss=False`` (what
     the CUDA library implements this round) keeps every Schur complement dense; ``hss=True`` stores the HSS
-    approximation of compressed nodes' Schur complements as the reference does."""
+    approximation of compressed nodes' Schur complements (direct construction), ``hss="rand"`` builds it the reference's
+    way: the matrix-free operator of :228-249 handed to the randomized adaptive construction with ``kest``/``stepsize``."""
     A = sp.csr_matrix(A)
     sw = max(base.depth(nd) + swlevel, 0) if swlevel < 0 else swlevel   # :8
-    return _factor(A, nd, nd_loc, 1, sw, swsize, atol, rtol, hss, leafsize)
+    return _factor(A, nd, nd_loc, 1, sw, swsize, atol, rtol, hss, leafsize, kest, stepsize)
 
 
-def _factor(A, nd, nd_loc, level, swlevel, swsize, atol, rtol, hss=False, leafsize=32) -> FactorNode:
+def _factor(A, nd, nd_loc, level, swlevel, swsize, atol, rtol, hss=False, leafsize=32, kest=-1, stepsize=10) -> FactorNode:
     """factorization.jl:14-27."""
     compression_flag = level <= swlevel and len(nd.bnd) >= swsize   # :15
     if isleaf(nd):
@@ -135,10 +172,10 @@ def _factor(A, nd, nd_loc, level, swlevel, swsize, atol, rtol, hss=False, leafsi
             F.S = _to_hss(F.S, len(nd_loc.int), leafsize, atol, rtol)   # :56-57
         return F
     elif isbranch(nd):
-        Fl = _factor(A, nd.left, nd_loc.left, level + 1, swlevel, swsize, atol, rtol, hss, leafsize)
-        Fr = _factor(A, nd.right, nd_loc.right, level + 1, swlevel, swsize, atol, rtol, hss, leafsize)
+        Fl = _factor(A, nd.left, nd_loc.left, level + 1, swlevel, swsize, atol, rtol, hss, leafsize, kest, stepsize)
+        Fr = _factor(A, nd.right, nd_loc.right, level + 1, swlevel, swsize, atol, rtol, hss, leafsize, kest, stepsize)
         if compression_flag:
-            return _factor_branch_compressed(A, Fl, Fr, nd, nd_loc, atol, rtol, hss, leafsize)
+            return _factor_branch_compressed(A, Fl, Fr, nd, nd_loc, atol, rtol, hss, leafsize, kest, stepsize)
         if hss and (hasattr(Fl.S, "dense") or hasattr(Fr.S, "dense")):
             # an uncompressed node above compressed children (always the root, factorization.jl:15 with |bnd| = 0)
             class _V:      # children viewed through their dense Schur blocks

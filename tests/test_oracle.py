@@ -207,3 +207,57 @@ def test_oracle_factor_with_hss_schur_complements(hs, orc, kind):
     assert rh < 50 * max(rd, 1e-4)
     _, res, conv = orc.gmres(Ap, prob.b, Pr=lambda v: orc.ldiv(Fh, v), reltol=1e-9, restart=30, maxiter=30)
     assert conv and len(res) <= 8
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_hss_randomized_construction(orc, cplx):
+    """``randcompress_adaptive``: products + entries only, starts from a rank estimate that is too small and adapts."""
+    import hs_hss as H
+    A = _kernel_matrix(cplx=cplx)
+    n = A.shape[0]
+    cl = H.bisection_cluster((80, n), leafsize=32)
+    calls = {"mul": 0, "idx": 0}
+
+    def mul(X):
+        calls["mul"] += 1
+        return A @ X
+
+    def idx(I, J):
+        calls["idx"] += 1
+        return A[np.ix_(I, J)]
+
+    for tol in (1e-3, 1e-7):
+        h = H.randcompress_adaptive(mul, lambda X: A.conj().T @ X, idx, cl, cl, kest=3, stepsize=8, atol=tol, rtol=tol,
+                                    rng=np.random.default_rng(5))
+        hd = H.compress(A, cl, cl, tol, tol)
+        assert np.linalg.norm(H.full(h) - A, 2) <= 50 * tol * np.linalg.norm(A, 2)
+        assert abs(H.hssrank(h) - H.hssrank(hd)) <= 4 and H.hssrank(h) > 3         # grew past the initial estimate
+        assert h.A11.shape == (80, 80)
+    assert calls["mul"] >= 2 and calls["idx"] > 0
+    # fixed sketches make the construction reproducible (parity runs hand the same Ω, Ψ to both sides)
+    Om, Ps = np.random.default_rng(9).standard_normal((n, 60)), np.random.default_rng(10).standard_normal((n, 60))
+    h1 = H.randcompress_adaptive(mul, lambda X: A.conj().T @ X, idx, cl, cl, kest=40, atol=1e-6, rtol=1e-6, sketches=(Om, Ps))
+    h2 = H.randcompress_adaptive(mul, lambda X: A.conj().T @ X, idx, cl, cl, kest=40, atol=1e-6, rtol=1e-6, sketches=(Om, Ps))
+    assert np.array_equal(H.full(h1), H.full(h2))
+
+
+def test_oracle_schur_operator_and_randomized_hss_mode(hs, orc):
+    """The LinearMap of factorization.jl:228-249 (products, adjoint products, entries of S[perm,perm]) and the
+    reference's route through it: ``hss="rand"``."""
+    import hs_oracle_hss as oh
+    rng = np.random.default_rng(0)
+    nb, ni, r = 30, 20, 5
+    Abb, Abi = rng.standard_normal((nb, nb)), rng.standard_normal((nb, ni))
+    R = oh.LowRankMatrix(rng.standard_normal((ni, r)), rng.standard_normal((nb, r)))
+    perm = rng.permutation(nb)
+    S = (Abb - Abi @ R.U @ R.V.T)[np.ix_(perm, perm)]
+    mul, mulc, idx = oh._schur_complement(Abb, Abi, R, perm)
+    X = rng.standard_normal((nb, 3))
+    assert np.allclose(mul(X), S @ X) and np.allclose(mulc(X), S.T @ X)
+    assert np.allclose(idx(np.arange(4), np.arange(3, 9)), S[:4, 3:9])
+    prob = hs.grid_problem((65, 65), "poisson", nmax=40)
+    Ap, nd, nd_loc, _ = orc.prepare(prob.A, prob.elim_tree)
+    F = orc.factor(Ap, nd, nd_loc, swlevel=-2, swsize=16, atol=1e-4, rtol=1e-4, hss="rand", leafsize=16)
+    assert orc.maxrank(F) > 0
+    _, res, conv = orc.gmres(Ap, prob.b, Pr=lambda v: orc.ldiv(F, v), reltol=1e-9, restart=30, maxiter=30)
+    assert conv and len(res) <= 8
