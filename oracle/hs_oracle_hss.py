@@ -122,6 +122,68 @@ def _schur_complement(Abb, Abi, R: "LowRankMatrix", perm):
     return Smul, Smulc, Sidx
 
 
+def _equilibrate_clusters(S1, S2):
+    """factorization.jl:143-168: prune HSS leaf levels of ``S1.A11`` / ``S2.A11`` until their cluster trees are compatible
+    (the all-HSS ``blockfactor`` needs matching block structure).  Returns the (possibly pruned) pair."""
+    import hs_hss as H
+    r1, r2 = H.cluster(S1.A11)[0], H.cluster(S2.A11)[0]
+    guard = 0
+    while not H.compatible(r1, r2) and guard < 64:
+        d1, d2 = H.depth(r1), H.depth(r2)
+        if d1 >= d2 and not S1.A11.leaf:
+            S1.A11 = H.prune_leaves(S1.A11)
+        if d2 >= d1 and not S2.A11.leaf:
+            S2.A11 = H.prune_leaves(S2.A11)
+        r1, r2 = H.cluster(S1.A11)[0], H.cluster(S2.A11)[0]
+        guard += 1
+        if S1.A11.leaf and S2.A11.leaf:
+            break     # sizes differ: nothing left to prune (the reference's `compatible` also compares sizes)
+    return S1, S2
+
+
+def _hss_children_blocks(A, S1, S2, int1, int2, bnd1, bnd2):
+    """``_assemble_blocks`` for HSS children (factorization.jl:126-140): diagonal blocks from ``S.A11`` / ``S.A22``, the
+    children's off-diagonal blocks as low-rank pairs read off the generators, sparse couplings from ``A``."""
+    import hs_hss as H
+    Ui1, Vi1 = H.generators(S1.A11); Ui1 = Ui1 @ S1.B12          # :129
+    Ui2, Vi2 = H.generators(S2.A11); Ui2 = Ui2 @ S2.B12          # :130
+    Ub1, Vb1 = H.generators(S1.A22); Ub1 = Ub1 @ S1.B21          # :131
+    Ub2, Vb2 = H.generators(S2.A22); Ub2 = Ub2 @ S2.B21          # :132
+    sub = base._sub
+    Aii = BlockMatrix(H.full(S1.A11), sub(A, int1, int2), sub(A, int2, int1), H.full(S2.A11))             # :135
+    lr = dict(ib1=LowRankMatrix(Ui1, Vb1), ib2=LowRankMatrix(Ui2, Vb2), bi1=LowRankMatrix(Ub1, Vi1), bi2=LowRankMatrix(Ub2, Vi2))
+    Aib = BlockMatrix(lr["ib1"].dense(), sub(A, int1, bnd2), sub(A, int2, bnd1), lr["ib2"].dense())      # :136
+    Abi = BlockMatrix(lr["bi1"].dense(), sub(A, bnd1, int2), sub(A, bnd2, int1), lr["bi2"].dense())      # :137
+    Abb = BlockMatrix(H.full(S1.A22), sub(A, bnd1, bnd2), sub(A, bnd2, bnd1), H.full(S2.A22))             # :138
+    return Aii, Aib, Abi, Abb, lr
+
+
+def _blkdiag(X, Y):
+    out = np.zeros((X.shape[0] + Y.shape[0], X.shape[1] + Y.shape[1]), dtype=np.result_type(X, Y))
+    out[:X.shape[0], :X.shape[1]] = X
+    out[X.shape[0]:, X.shape[1]:] = Y
+    return out
+
+
+def _gauss_transforms_hss_children(D, Aib, Abi, lr, atol, rtol):
+    """factorization.jl:184-209: the children's low-rank blocks are concatenated without recompression (``_recompress!``
+    is dead code, :251-259), the sparse anti-diagonal couplings are compressed by ``pqrfact(…; sketch=:randn)`` — emulated
+    by the unsketched ``pqrfact`` — and appended; note the extra ``0.5×`` of the right transform (:202)."""
+    L = LowRankMatrix(_blkdiag(lr["bi1"].U, lr["bi2"].U), _blkdiag(lr["bi1"].V, lr["bi2"].V))          # :185
+    X = np.block([[np.zeros_like(Abi.A11), Abi.A12], [Abi.A21, np.zeros_like(Abi.A22)]])
+    if np.count_nonzero(Abi.A12) + np.count_nonzero(Abi.A21) > 0:                                      # :186
+        Q, Rp = pqrfact(X, atol, rtol)                                                                  # :189
+        L.U, L.V = np.hstack([L.U, Q]), np.hstack([L.V, Rp.conj().T])
+    L.V = blockrdiv_inplace(L.V.conj().T, D).conj().T if L.rank else L.V                                # :193
+    R = LowRankMatrix(_blkdiag(lr["ib1"].U, lr["ib2"].U), _blkdiag(lr["ib1"].V, lr["ib2"].V))          # :198
+    X = np.block([[np.zeros_like(Aib.A11), Aib.A12], [Aib.A21, np.zeros_like(Aib.A22)]])
+    if np.count_nonzero(Aib.A12) + np.count_nonzero(Aib.A21) > 0:                                      # :199
+        Q, Rp = pqrfact(X, 0.5 * atol, 0.5 * rtol)                                                      # :202
+        R.U, R.V = np.hstack([R.U, Q]), np.hstack([R.V, Rp.conj().T])
+    R.U = blockldiv_inplace(D, R.U) if R.rank else R.U                                                  # :206
+    return L, R
+
+
 def _factor_branch_compressed(A, Fl, Fr, nd, nd_loc, atol, rtol, hss=False, leafsize=32, kest=-1, stepsize=10) -> FactorNode:
     """factorization.jl:78-112 with the Schur operator of :228-249 evaluated densely (module docstring).  ``hss=True``
     stores its HSS approximation (oracle/hs_hss.py) like the reference; parents then assemble from the approximated
@@ -130,10 +192,19 @@ def _factor_branch_compressed(A, Fl, Fr, nd, nd_loc, atol, rtol, hss=False, leaf
     bnd1 = nd.left.bnd[nd_loc.left.bnd - 1]
     int2 = nd.right.bnd[nd_loc.right.int - 1]
     bnd2 = nd.right.bnd[nd_loc.right.bnd - 1]
-    Aii, Aib, Abi, Abb = _assemble_blocks(A, _S(Fl), _S(Fr), int1, int2, bnd1, bnd2)
-    D = blockfactor(Aii)                                   # :94
-    L = _lgauss_transform(D, Abi, 0.5 * atol, 0.5 * rtol)  # :99
-    R = _rgauss_transform(D, Aib, 0.5 * atol, 0.5 * rtol)  # :100
+    def _split(S):   # an HSS Schur complement whose first split separates the parent's int from its bnd
+        return hasattr(S, "dense") and not S.leaf
+    if hss and _split(Fl.S) and _split(Fr.S) and Fl.S.A11.rows == len(int1) and Fr.S.A11.rows == len(int2):
+        # both children are HSS: the HSS methods by dispatch (:86-91, :126-140, :184-209)
+        S1, S2 = _equilibrate_clusters(Fl.S, Fr.S)                                                  # :86-90
+        Aii, Aib, Abi, Abb, lr = _hss_children_blocks(A, S1, S2, int1, int2, bnd1, bnd2)
+        D = blockfactor(Aii)          # :94 (all-HSS method blockmatrix.jl:121-130, its recompress! tolerance → 0)
+        L, R = _gauss_transforms_hss_children(D, Aib, Abi, lr, 0.5 * atol, 0.5 * rtol)             # :99-100
+    else:
+        Aii, Aib, Abi, Abb = _assemble_blocks(A, _S(Fl), _S(Fr), int1, int2, bnd1, bnd2)
+        D = blockfactor(Aii)                                   # :94
+        L = _lgauss_transform(D, Abi, 0.5 * atol, 0.5 * rtol)  # :99
+        R = _rgauss_transform(D, Aib, 0.5 * atol, 0.5 * rtol)  # :100
     U = Abi.dense() @ R.U                                  # :230  U = Abi*R
     S = Abb.dense() - U @ R.V.conj().T                     # :242,:248
     perm = np.concatenate([nd_loc.int, nd_loc.bnd]) - 1    # :107

@@ -261,3 +261,34 @@ def test_oracle_schur_operator_and_randomized_hss_mode(hs, orc):
     assert orc.maxrank(F) > 0
     _, res, conv = orc.gmres(Ap, prob.b, Pr=lambda v: orc.ldiv(F, v), reltol=1e-9, restart=30, maxiter=30)
     assert conv and len(res) <= 8
+
+
+def test_oracle_hss_children_methods(hs, orc):
+    """Nodes whose two children carry HSS Schur complements go through the HSS methods by dispatch
+    (factorization.jl:86-91,126-140,184-209): diagonal blocks from S.A11 / S.A22, low-rank blocks read off the
+    generators and concatenated, sparse couplings appended."""
+    import hs_oracle_hss as oh
+    calls = []
+    orig = oh._gauss_transforms_hss_children
+
+    def spy(D, Aib, Abi, lr, atol, rtol):
+        L, R = orig(D, Aib, Abi, lr, atol, rtol)
+        calls.append((L.rank, R.rank, lr["bi1"].rank + lr["bi2"].rank))
+        # the transforms reproduce Abi·D⁻¹ and D⁻¹·Aib of the assembled (already approximated) blocks to the tolerance
+        Dd = orc.FactorNode(D, None, None, None, None, None, None, None).D_dense()
+        assert np.linalg.norm(L.dense() @ Dd - Abi.dense()) <= 10 * max(atol, rtol * np.linalg.norm(Abi.dense(), 2))
+        assert np.linalg.norm(Dd @ R.dense() - Aib.dense()) <= 10 * max(atol, rtol * np.linalg.norm(Aib.dense(), 2))
+        return L, R
+
+    oh._gauss_transforms_hss_children = spy
+    try:
+        prob = hs.grid_problem((65, 65), "helmholtz", nmax=40)
+        Ap, nd, nd_loc, _ = orc.prepare(prob.A, prob.elim_tree)
+        F = orc.factor(Ap, nd, nd_loc, swlevel=-2, swsize=16, atol=1e-5, rtol=1e-5, hss=True, leafsize=16)
+    finally:
+        oh._gauss_transforms_hss_children = orig
+    assert len(calls) > 10 and all(rl >= base for rl, _, base in calls)      # concatenation never drops below the children's ranks
+    x = orc.ldiv(F, prob.b)
+    assert np.linalg.norm(Ap @ x - prob.b) / np.linalg.norm(prob.b) < 1e-2
+    _, res, conv = orc.gmres(Ap, prob.b, Pr=lambda v: orc.ldiv(F, v), reltol=1e-9, restart=30, maxiter=30)
+    assert conv and len(res) <= 6
