@@ -113,3 +113,20 @@ def test_gpu_factor_on_metis_tree_matches_oracle(hs, orc, unsym, cplx):
     assert hs.maxrank(Fc) > 0 and abs(hs.maxrank(Fc) - orc.maxrank(Foc)) <= 1
     xc, xoc = hs.ldiv(Fc, b), orc.ldiv(Foc, b)
     assert np.linalg.norm(xc - xoc) / np.linalg.norm(xoc) < 1e-4
+
+
+@pytest.mark.parametrize("seed,unsym", [(11, False), (12, True), (13, False)])
+def test_symbolic_phase_on_metis_trees_matches_oracle(hs, orc, seed, unsym):
+    """The C++ symbolic phase (hs_symfact) against the oracle's ``symfact!`` / ``postorder`` / ``permuted!`` on the
+    irregular trees METIS produces (unbalanced subtrees, leaves at different depths)."""
+    A, _ = _mesh_matrix(900 + 37 * seed, seed=seed, unsym=unsym)
+    et = hs.nested_dissection(A, nmax=35)
+    Ap, nd, nd_loc, perm = hs.prepare(A, et)
+    Ao, ndo, ndo_loc, permo = orc.prepare(A, et)
+    assert np.array_equal(perm, permo) and abs(Ap - Ao).max() == 0
+    nodes, locs = orc._postorder_nodes(ndo), orc._postorder_nodes(ndo_loc)
+    assert len(nodes) == nd.nnodes and hs.depth(nd) == orc.depth(ndo)
+    for k, (a, l) in enumerate(zip(nodes, locs)):
+        v, vl = nd.node(k), nd_loc.node(k)
+        assert np.array_equal(v.int, a.int) and np.array_equal(v.bnd, a.bnd)
+        assert np.array_equal(vl.int, l.int) and np.array_equal(vl.bnd, l.bnd)
