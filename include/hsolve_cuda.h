@@ -41,7 +41,10 @@ enum {
 typedef enum { HS_F64 = 0, HS_C64 = 1 } hs_dtype;
 
 /* `SolverOptions` (HierarchicalSolvers.jl:30-40), same field names.  `swlevel` is passed as the user gave it;
- * negative values are resolved against the tree depth inside hs_factor as factorization.jl:8 does. */
+ * negative values are resolved against the tree depth inside hs_factor as factorization.jl:8 does.  A node with
+ * level ≤ swlevel and |bnd| ≥ swsize is compressed (factorization.jl:15): its L and R become low-rank, truncated at
+ * atol/2, rtol/2 (:99-100); its Schur complement is evaluated exactly and kept dense, so `leafsize`, `kest`, `stepsize`
+ * (parameters of the reference's HSS storage of S) and `c_tol` (ignored by the reference itself, :97) have no effect. */
 typedef struct {
   int64_t swlevel;
   int64_t swsize;
