@@ -336,3 +336,122 @@ def randcompress_adaptive(mul, mulc, getidx, rcl: ClusterTree, ccl: ClusterTree,
             return h
         k += int(stepsize)
     return h
+
+
+# ------------------------------------------------------------------------------------------------
+# sparse embedding: an HSS system as a larger sparse system whose elimination tree is the HSS tree
+# ------------------------------------------------------------------------------------------------
+def sparse_embedding(h: HssMatrix):
+    """Extended sparse system of an HSS matrix (Chandrasekaran, Dewilde, Gu, Lyons, Pals 2006) together with an
+    elimination tree in the reference's ``elim_tree`` schema, so that ``h \\ b`` can be computed by the multifrontal
+    factorization of this very repository: auxiliary unknowns ``g_τ = V_τᴴ·x_τ`` and ``f_τ`` (what reaches node τ from
+    outside, in the coordinates of ``U_τ``) for every non-root node τ,
+
+        leaf i        D_i·x_i + U_i·f_i = b_i                    V_iᴴ·x_i − g_i = 0
+        branch τ      f_c1 − B12·g_c2 − R1·f_τ = 0               f_c2 − B21·g_c1 − R2·f_τ = 0
+                      g_τ − W1ᴴ·g_c1 − W2ᴴ·g_c2 = 0              (R, W, f_τ, g_τ absent at the root)
+
+    Returns ``(A_ext, n, tree)``: ``A_ext`` (scipy CSC, the first ``n`` unknowns are ``x``), and ``tree`` = dict of
+    1-based arrays ``fathers, lsons, rsons, inter (list), bound (list)``.  Every leaf of the tree owns its ``x_i, g_i, f_i``
+    and — the schema has no unknowns of its own at branches — the ``g_τ, f_τ`` of the ancestors whose left-most leaf it is.
+    This is the round-2 route for pivot blocks kept in HSS form."""
+    import scipy.sparse as sp
+    if h.leaf:
+        raise ValueError("sparse_embedding: the HSS matrix is a single dense block")
+    nodes, kids, father = [], [], []
+
+    def number(node, fa):
+        k = len(nodes)
+        nodes.append(node); kids.append((-1, -1)); father.append(fa)
+        if not node.leaf:
+            a = number(node.A11, k)
+            b = number(node.A22, k)
+            kids[k] = (a, b)
+        return k
+
+    number(h, -1)
+    nn = len(nodes)
+    urank = [0] * nn          # columns of U_τ  = size of f_τ
+    vrank = [0] * nn          # columns of V_τ  = size of g_τ
+    for k, nd_ in enumerate(nodes):
+        if father[k] < 0:
+            continue
+        if nd_.leaf:
+            urank[k], vrank[k] = nd_.U.shape[1], nd_.V.shape[1]
+        else:
+            urank[k], vrank[k] = nd_.R1.shape[1], nd_.W1.shape[1]
+    # unknown numbering: x in leaf order, then (g_τ, f_τ) per non-root node
+    xoff, off = [0] * nn, 0
+    for k, nd_ in enumerate(nodes):
+        if nd_.leaf:
+            xoff[k] = off
+            off += nd_.rows
+    n = off
+    goff, foff = [0] * nn, [0] * nn
+    for k in range(nn):
+        if father[k] < 0:
+            continue
+        goff[k] = off; off += vrank[k]
+        foff[k] = off; off += urank[k]
+    ntot = off
+    rows, cols, vals = [], [], []
+
+    def put(r0, c0, M):
+        M = np.asarray(M)
+        if M.size == 0:
+            return
+        rr, cc = np.meshgrid(np.arange(M.shape[0]) + r0, np.arange(M.shape[1]) + c0, indexing="ij")
+        rows.append(rr.ravel()); cols.append(cc.ravel()); vals.append(M.ravel())
+
+    for k, nd_ in enumerate(nodes):
+        if nd_.leaf:
+            put(xoff[k], xoff[k], nd_.D)
+            put(xoff[k], foff[k], nd_.U)
+            put(goff[k], xoff[k], nd_.V.conj().T)
+            put(goff[k], goff[k], -np.eye(vrank[k]))
+            continue
+        c1, c2 = kids[k]
+        put(foff[c1], foff[c1], np.eye(urank[c1]))
+        put(foff[c1], goff[c2], -nd_.B12)
+        put(foff[c2], foff[c2], np.eye(urank[c2]))
+        put(foff[c2], goff[c1], -nd_.B21)
+        if father[k] >= 0:
+            put(foff[c1], foff[k], -nd_.R1)
+            put(foff[c2], foff[k], -nd_.R2)
+            put(goff[k], goff[k], np.eye(vrank[k]))
+            put(goff[k], goff[c1], -nd_.W1.conj().T)
+            put(goff[k], goff[c2], -nd_.W2.conj().T)
+    dt = np.result_type(*[v.dtype for v in vals])
+    A = sp.coo_matrix((np.concatenate(vals).astype(dt), (np.concatenate(rows), np.concatenate(cols))), shape=(ntot, ntot)).tocsc()
+    # vertex sets: every non-root node's (g, f) lives in its left-most leaf
+    leafset = {k: list(range(xoff[k], xoff[k] + nodes[k].rows)) for k in range(nn) if nodes[k].leaf}
+    for k in range(nn):
+        if father[k] < 0:
+            continue
+        j = k
+        while not nodes[j].leaf:
+            j = kids[j][0]
+        leafset[j] += list(range(goff[k], goff[k] + vrank[k])) + list(range(foff[k], foff[k] + urank[k]))
+    P = sp.csr_matrix((abs(A) + abs(A).T) != 0)
+    owner = np.zeros(ntot, dtype=np.int64)       # leaf each unknown belongs to
+    for j, vs in leafset.items():
+        owner[vs] = j
+    # leaves below every node (as a set of leaf ids)
+    below = [None] * nn
+    for k in range(nn - 1, -1, -1):
+        below[k] = {k} if nodes[k].leaf else below[kids[k][0]] | below[kids[k][1]]
+    inter, bound = [None] * nn, [None] * nn
+    for k in range(nn - 1, -1, -1):
+        cand = sorted(leafset[k]) if nodes[k].leaf else sorted(bound[kids[k][0]] + bound[kids[k][1]])
+        inside = below[k]
+        ii, bb = [], []
+        for v in cand:
+            nb = P.indices[P.indptr[v]:P.indptr[v + 1]]
+            (bb if any(int(owner[u]) not in inside for u in nb) else ii).append(v)
+        inter[k], bound[k] = ii, bb
+    tree = dict(fathers=np.array([f + 1 if f >= 0 else -1 for f in father], dtype=np.int64),
+                lsons=np.array([a + 1 if a >= 0 else -1 for a, _ in kids], dtype=np.int64),
+                rsons=np.array([b + 1 if b >= 0 else -1 for _, b in kids], dtype=np.int64),
+                inter=[np.asarray(v, dtype=np.int64) + 1 for v in inter],
+                bound=[np.asarray(v, dtype=np.int64) + 1 for v in bound])
+    return A, n, tree

@@ -176,3 +176,20 @@ def test_compressed_root_with_boundary(hs, orc, kind):
         assert np.linalg.norm(Xg - Xo) / np.linalg.norm(Xo) < 1e-7, name
     B = rng.standard_normal((Ap.shape[0], 2)).astype(Fo.S.dtype)
     assert np.linalg.norm(hs.ldiv(F, B) - orc.ldiv(Fo, B)) / np.linalg.norm(B) < 1e-7
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_hss_solve_through_the_multifrontal_kernels(hs, orc, cplx):
+    """Round-2 groundwork: an HSS matrix (oracle/hs_hss.py) embedded as a sparse system whose elimination tree is the
+    HSS tree is factored and solved by the CUDA multifrontal path as it is — O(n·r²) instead of O(n³) for the block."""
+    import hs_hss as H
+    from test_oracle import _embedding_problem
+    h, Aext, nx, et, b, bext = _embedding_problem(hs, H, cplx, n=1200, leafsize=64, tol=1e-9)
+    Ap, nd, nd_loc, perm = hs.prepare(Aext, et)
+    F = hs.factor(Ap, nd, nd_loc, swlevel=0)
+    xp = hs.ldiv(F, bext[perm - 1])
+    x = np.empty_like(xp)
+    x[perm - 1] = xp
+    xh = H.solve(h, b)
+    assert np.linalg.norm(x[:nx] - xh) / np.linalg.norm(xh) < 1e-10
+    assert F.stats()["max_ni"] + F.stats()["max_nb"] < nx // 3

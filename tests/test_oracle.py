@@ -292,3 +292,44 @@ def test_oracle_hss_children_methods(hs, orc):
     assert np.linalg.norm(Ap @ x - prob.b) / np.linalg.norm(prob.b) < 1e-2
     _, res, conv = orc.gmres(Ap, prob.b, Pr=lambda v: orc.ldiv(F, v), reltol=1e-9, restart=30, maxiter=30)
     assert conv and len(res) <= 6
+
+
+def _embedding_problem(hs, H, cplx, n=400, leafsize=40, tol=1e-8):
+    A = _kernel_matrix(n=n, cplx=cplx)
+    cl = H.bisection_cluster(n, leafsize=leafsize)
+    h = H.compress(A, cl, cl, tol, tol)
+    Aext, nx, tree = H.sparse_embedding(h)
+    iptr = np.concatenate([[0], np.cumsum([len(v) for v in tree["inter"]])]).astype(np.int64)
+    bptr = np.concatenate([[0], np.cumsum([len(v) for v in tree["bound"]])]).astype(np.int64)
+    et = hs.ElimTree(tree["fathers"], tree["lsons"], tree["rsons"], iptr, np.concatenate(tree["inter"]), bptr,
+                     np.concatenate(list(tree["bound"]) + [np.zeros(0, np.int64)]))
+    rng = np.random.default_rng(2)
+    b = rng.standard_normal(n) + (1j * rng.standard_normal(n) if cplx else 0)
+    bext = np.zeros(Aext.shape[0], dtype=Aext.dtype)
+    bext[:nx] = b
+    return h, Aext, nx, et, b, bext
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_hss_sparse_embedding_solved_by_the_multifrontal_oracle(hs, orc, cplx):
+    """An HSS system as a sparse system whose elimination tree is the HSS tree (oracle/hs_hss.py::sparse_embedding):
+    SuperLU on the extended matrix and the multifrontal oracle on the HSS tree both reproduce ``h \\ b`` — fronts of size
+    leafsize + O(rank) instead of n.  This is the round-2 route for pivot blocks kept in HSS form."""
+    import hs_hss as H
+    h, Aext, nx, et, b, bext = _embedding_problem(hs, H, cplx)
+    xh = H.solve(h, b)
+    xe = spla.splu(sp_csc(Aext)).solve(bext)
+    assert np.linalg.norm(xe[:nx] - xh) / np.linalg.norm(xh) < 1e-12
+    assert Aext.nnz < 0.3 * nx * nx
+    Ap, nd, nd_loc, perm = orc.prepare(Aext, et)
+    F = orc.factor(Ap, nd, nd_loc)
+    xo = orc.ldiv(F, bext[perm - 1])
+    x = np.empty_like(xo)
+    x[perm - 1] = xo
+    assert np.linalg.norm(x[:nx] - xh) / np.linalg.norm(xh) < 1e-12
+    assert max(len(v.int) + len(v.bnd) for v in orc.nodes_postorder(F)) < nx // 3
+
+
+def sp_csc(A):
+    import scipy.sparse as sp
+    return sp.csc_matrix(A)
