@@ -14,6 +14,7 @@ HS_OK, HS_EARG, HS_EDIM, HS_ETREE, HS_ESINGULAR, HS_ECUDA, HS_ENOMEM, HS_ENOTIMP
 HS_F64, HS_C64 = 0, 1
 HS_ON_DEVICE, HS_CSC_ZERO_BASED, HS_CSC_INT32 = 1, 2, 4
 HS_GET_D, HS_GET_S, HS_GET_L, HS_GET_R, HS_GET_FRONT, HS_GET_PIV = range(6)
+HS_HSS_D, HS_HSS_U, HS_HSS_V, HS_HSS_B12, HS_HSS_B21, HS_HSS_R, HS_HSS_W = range(7)
 
 i64p = C.POINTER(C.c_int64)
 
@@ -21,7 +22,10 @@ i64p = C.POINTER(C.c_int64)
 class hs_opts(C.Structure):
     _fields_ = [("swlevel", C.c_int64), ("swsize", C.c_int64), ("atol", C.c_double), ("rtol", C.c_double),
                 ("c_tol", C.c_double), ("leafsize", C.c_int64), ("kest", C.c_int64), ("stepsize", C.c_int64),
-                ("verbose", C.c_int32), ("subtree", C.c_int32)]
+                ("verbose", C.c_int32), ("subtree", C.c_int32),
+                # extension: HSS storage of the Schur complements + the host-supplied sketch matrices (hsolve_cuda.h)
+                ("hss", C.c_int32), ("pad0", C.c_int32), ("sketch_omega", C.c_void_p), ("sketch_psi", C.c_void_p),
+                ("sketch_rows", C.c_int64), ("sketch_cols", C.c_int64), ("sketch_seed", C.c_uint64)]
 
 
 class hs_elimtree(C.Structure):
@@ -45,7 +49,9 @@ class hs_stats_t(C.Structure):
                 ("launches_solve", C.c_int64), ("singular_front", C.c_int64), ("singular_col", C.c_int64),
                 ("maxrank", C.c_int64), ("gemm_flops", C.c_double), ("gemm_launches", C.c_int64),
                 ("panel_launches", C.c_int64), ("ms_extend_add", C.c_double), ("ms_small", C.c_double), ("ms_solve_prep", C.c_double),
-                ("ms_compress", C.c_double), ("lowrank_bytes", C.c_double)]
+                ("ms_compress", C.c_double), ("lowrank_bytes", C.c_double),
+                ("ms_hss", C.c_double), ("hss_bytes", C.c_double), ("hss_maxrank", C.c_int64), ("hss_rounds", C.c_int64),
+                ("hss_nodes", C.c_int64), ("sketch_flops", C.c_double)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -86,6 +92,9 @@ PROTOTYPES = [
     ("hs_resolved_swlevel", C.c_int32, [C.c_void_p, i64p]),
     ("hs_spmv", C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p]),
     ("hs_matrix_device", C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), i64p]),
+    ("hs_matrix_checksum", C.c_int32, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    ("hs_hss_info", C.c_int32, [C.c_void_p, C.c_int64, i64p, i64p]),
+    ("hs_hss_get", C.c_int32, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, i64p]),
     ("hs_gmres", C.c_int32, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                              C.c_void_p, C.c_void_p, C.c_double, C.c_int64, C.c_int64, C.POINTER(C.c_double), i64p,
                              C.POINTER(C.c_int32), C.c_int32]),

@@ -72,6 +72,7 @@ extern "C" int32_t hs_create(hs_ctx** out, int32_t device) {
   hs_panel_setup_c64();
   hs_solve_setup();
   hs_comp_setup();
+  hs_hss_setup();
   c->max_cluster = getenv("HS_MAX_CLUSTER") ? atoi(getenv("HS_MAX_CLUSTER")) : 16;
   if (getenv("HS_OUTER_BLOCK")) c->outer_block = std::max(1, atoi(getenv("HS_OUTER_BLOCK")));
   CUDA_OK(cudaFuncSetAttribute(k_gemm<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes<double>()));
@@ -297,6 +298,7 @@ template <typename T> static void numeric(hs_fac* f) {
   hs_stats_t& s = f->stats;
   s.ms_assemble = s.ms_panel = s.ms_trsm = s.ms_gemm = s.ms_solve_prep = s.ms_small = s.ms_extend_add = s.ms_compress = 0;
   s.maxrank = 0;
+  s.ms_hss = 0; s.hss_bytes = 0; s.hss_maxrank = 0; s.hss_rounds = 0; s.hss_nodes = 0; s.sketch_flops = 0;
   s.launches_factor = 0;
   s.gemm_launches = s.panel_launches = 0;
   s.gemm_flops = 0;
@@ -345,8 +347,16 @@ template <typename T> static void numeric(hs_fac* f) {
         hs_comp_prepare(f, C);
       }
       factor_level<T>(f, FL);
-      PhaseTimer t(f, &s.ms_compress);
-      hs_comp_schur(f, C);
+      {
+        PhaseTimer t(f, &s.ms_compress);
+        hs_comp_schur(f, C);
+      }
+      // HSS storage of the Schur complements (`randcompress_adaptive`, factorization.jl:102-110): matrix-free sketches,
+      // interpolative decompositions per HSS level, then the represented matrix goes back into the dense slots
+      if (!f->hss.empty()) {
+        PhaseTimer t(f, &s.ms_hss);
+        hs_hss_build(f, C);
+      }
     }
   }
   s.lowrank_bytes = 0;
@@ -541,8 +551,7 @@ static void build_plan(hs_fac* f, const hs_tree* t) {
   // L and R in the reference too (:45-59) and S stays dense here, so only branches change.
   f->swlevel_resolved = f->opts.swlevel < 0 ? std::max<int64_t>(f->depth + f->opts.swlevel, 0) : f->opts.swlevel;
   std::vector<char> cflag(nn, 0);
-  if (!f->opts.subtree)
-    for (int64_t k = 0; k < nn; ++k)
+  for (int64_t k = 0; k < nn; ++k)   // subtree mode included: the root's dense slot is persistent, so its S can be exported
       cflag[k] = f->left[k] >= 0 && f->level[k] <= f->swlevel_resolved && f->node_nb[k] >= f->opts.swsize &&
                  f->node_ni[k] > 0 && f->node_nb[k] > 0;
   // front order: deepest level first; inside a level the dense fronts before the compressed ones, each group by ni
@@ -779,6 +788,7 @@ static void build_plan(hs_fac* f, const hs_tree* t) {
   CUDA_OK(cudaStreamSynchronize(st));  // host vectors go out of scope
   clk.tick("upload tables");
   hs_comp_plan(f);
+  hs_hss_plan(f);
 }
 
 __global__ void k_widen_index(long long* dst, const int* src, long long n, long long base) {
@@ -934,24 +944,41 @@ extern "C" int32_t hs_schur_import(hs_fac* f, int64_t node, const void* src, int
   HS_TRY_END
 }
 
+template <typename T> static void sweep_impl(hs_fac* f, int64_t nrhs, void* xv, int which) {
+  cudaStream_t st = f->ctx->stream;
+  if (nrhs > f->rhs_cap) {
+    cudaFree(f->d_x); cudaFree(f->d_work);
+    f->d_x = f->d_work = nullptr;
+    CUDA_OK(cudaMalloc(&f->d_x, (size_t)f->xld * nrhs * sizeof(T)));
+    CUDA_OK(cudaMalloc(&f->d_work, std::max<size_t>((size_t)f->max_level_idx * nrhs, 1) * sizeof(T)));
+    f->rhs_cap = nrhs;
+  }
+  f->stats.launches_solve = 0;
+  if (!f->nvirt) {
+    hs_solve_run(f, nrhs, xv, which);
+  } else {
+    // compressed fronts: the border rows of the thin fronts live in virtual slots behind the n entries of x, so the
+    // sweep runs on the internal buffer (leading dimension n + nvirt).  The slots carry nothing from the forward to
+    // the backward half (k_lr_bwd rewrites them), so the two halves may be separate calls.
+    T* x = (T*)f->d_x;
+    CUDA_OK(cudaMemcpy2DAsync(x, (size_t)f->xld * sizeof(T), xv, (size_t)f->n * sizeof(T), (size_t)f->n * sizeof(T), nrhs,
+                              cudaMemcpyDeviceToDevice, st));
+    CUDA_OK(cudaMemset2DAsync(x + f->n, (size_t)f->xld * sizeof(T), 0, (size_t)f->nvirt * sizeof(T), nrhs, st));
+    hs_solve_run(f, nrhs, x, which);
+    CUDA_OK(cudaMemcpy2DAsync(xv, (size_t)f->n * sizeof(T), x, (size_t)f->xld * sizeof(T), (size_t)f->n * sizeof(T), nrhs,
+                              cudaMemcpyDeviceToDevice, st));
+  }
+  f->ctx->launches += f->stats.launches_solve;
+  CUDA_OK(cudaStreamSynchronize(st));
+}
+
 extern "C" int32_t hs_solve_sweep(hs_fac* f, int64_t nrhs, void* x, int64_t ldx, int32_t which) {
   HS_TRY_BEGIN
   if (!f || !x) return hs_fail(HS_EARG, "hs_solve_sweep: null argument");
   if (nrhs <= 0 || !(which & 3)) return HS_OK;
   if (ldx != f->n) return hs_fail(HS_EDIM, "hs_solve_sweep: ldx must equal n");
-  if (f->nvirt) return hs_fail(HS_ENOTIMPL, "hs_solve_sweep: not available for factorizations with compressed fronts");
   CUDA_OK(cudaSetDevice(f->ctx->device));
-  if (nrhs > f->rhs_cap) {
-    cudaFree(f->d_x); cudaFree(f->d_work);
-    f->d_x = f->d_work = nullptr;
-    CUDA_OK(cudaMalloc(&f->d_x, (size_t)f->n * nrhs * f->esz));
-    CUDA_OK(cudaMalloc(&f->d_work, std::max<size_t>((size_t)f->max_level_idx * nrhs, 1) * f->esz));
-    f->rhs_cap = nrhs;
-  }
-  f->stats.launches_solve = 0;
-  hs_solve_run(f, nrhs, x, which);
-  f->ctx->launches += f->stats.launches_solve;
-  CUDA_OK(cudaStreamSynchronize(f->ctx->stream));
+  if (f->dtype == HS_F64) sweep_impl<double>(f, nrhs, x, which); else sweep_impl<cplx>(f, nrhs, x, which);
   return HS_OK;
   HS_TRY_END
 }
@@ -960,9 +987,13 @@ extern "C" int32_t hs_refactor(hs_fac* f, const void* nzval, int32_t on_device) 
   HS_TRY_BEGIN
   if (!f) return hs_fail(HS_EARG, "hs_refactor: null argument");
   CUDA_OK(cudaSetDevice(f->ctx->device));
-  if (nzval && nzval != f->d_nzval)
+  if (nzval && nzval != f->d_nzval) {
     CUDA_OK(cudaMemcpyAsync(f->d_nzval, nzval, (size_t)f->nnz * f->esz, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
                             f->ctx->stream));
+    // the CSR image hs_gmres / hs_spmv build on first use holds the OLD values: mark it stale (its values are gathered
+    // again on next use) so that the operator of the Krylov loop and the preconditioner keep describing the same matrix
+    f->csr_stale = true;
+  }
   if (f->dtype == HS_F64) numeric<double>(f); else numeric<cplx>(f);
   if (f->stats.singular_col >= 0) return hs_fail(HS_ESINGULAR, "hs_refactor: exactly singular pivot block");
   return HS_OK;
@@ -1030,6 +1061,13 @@ template <typename T> static void node_get_compressed(hs_fac* f, int64_t node, c
   const int fi = cf.fi, ni = cf.ni, nb = cf.nb;
   cudaStream_t st = f->ctx->stream;
   T* o = (T*)out;
+  if (which == HS_GET_S && cf.hss >= 0) {
+    // F.S is an HssMatrix (factorization.jl:110-111): the dense matrix it represents, S[perm,perm] order
+    const HssFront& H = f->hss[cf.hss];
+    if (dims) { dims[0] = H.m; dims[1] = H.m; }
+    if (out) hs_hss_dense(f, cf.hss, out);
+    return;
+  }
   if (which == HS_GET_S && f->transient_schur && f->node2front[node] != f->root_front)
     throw hs_error(HS_EARG, "hs_node_get: the dense Schur block of a compressed front is transient (its slot is reused two levels up); "
                             "set HS_KEEP_SCHUR=1 before hs_factor to keep it");
@@ -1255,6 +1293,81 @@ extern "C" int32_t hs_node_rank(hs_fac* f, int64_t node, int64_t* rank_l, int64_
   for (const CompFront& cf : f->comp)
     if (cf.fi == fi) { *rank_l = cf.r1; *rank_r = cf.r2; }
   return HS_OK;
+}
+
+static const CompFront* comp_of(hs_fac* f, int64_t node) {
+  const int fi = f->node2front[node];
+  for (const CompFront& cf : f->comp)
+    if (cf.fi == fi) return &cf;
+  return nullptr;
+}
+
+extern "C" int32_t hs_hss_info(hs_fac* f, int64_t node, int64_t* nhss, int64_t* info) {
+  HS_TRY_BEGIN
+  if (!f || !nhss) return hs_fail(HS_EARG, "hs_hss_info: null argument");
+  if (node < 0 || node >= f->nnodes) return hs_fail(HS_EARG, "hs_hss_info: node out of range");
+  *nhss = 0;
+  const CompFront* cf = comp_of(f, node);
+  if (!cf || cf->hss < 0) return HS_OK;
+  const HssFront& H = f->hss[cf->hss];
+  *nhss = (int64_t)H.tree.size();
+  if (info)
+    for (size_t t = 0; t < H.tree.size(); ++t) {
+      const HssTreeNode& tn = H.tree[t];
+      int64_t* o = info + 8 * t;
+      o[0] = tn.lo; o[1] = tn.hi; o[2] = tn.left; o[3] = tn.right; o[4] = H.st[t].r0; o[5] = H.st[t].r1; o[6] = tn.parent; o[7] = tn.left < 0;
+    }
+  return HS_OK;
+  HS_TRY_END
+}
+
+extern "C" int32_t hs_hss_get(hs_fac* f, int64_t node, int64_t hnode, hs_hss_which which, void* out, int64_t* dims) {
+  HS_TRY_BEGIN
+  if (!f || !dims) return hs_fail(HS_EARG, "hs_hss_get: null argument");
+  if (node < 0 || node >= f->nnodes) return hs_fail(HS_EARG, "hs_hss_get: node out of range");
+  const CompFront* cf = comp_of(f, node);
+  if (!cf || cf->hss < 0) return hs_fail(HS_EARG, "hs_hss_get: the Schur complement of this node is not an HSS matrix");
+  const HssFront& H = f->hss[cf->hss];
+  if (hnode < 0 || hnode >= (int64_t)H.tree.size()) return hs_fail(HS_EARG, "hs_hss_get: HSS node out of range");
+  const HssTreeNode& tn = H.tree[hnode];
+  const HssStored& S = H.st[hnode];
+  const bool leaf = tn.left < 0;
+  const int m = tn.hi - tn.lo;
+  long long src = -1; int ld = 0, rows = 0, cols = 0; bool ct = false;   // ct: stored conjugate-transposed
+  int ra0 = 0, ra1 = 0, rb0 = 0, rb1 = 0;
+  if (!leaf) { ra0 = H.st[tn.left].r0; ra1 = H.st[tn.left].r1; rb0 = H.st[tn.right].r0; rb1 = H.st[tn.right].r1; }
+  switch (which) {
+    case HS_HSS_D: if (leaf) { src = S.D; ld = S.ldD; rows = cols = m; } break;
+    case HS_HSS_U: if (leaf) { src = S.U; ld = S.ldU; rows = m; cols = S.r0; } break;
+    case HS_HSS_V: if (leaf) { src = S.VH; ld = S.ldVH; rows = m; cols = S.r1; ct = true; } break;
+    case HS_HSS_B12: if (!leaf) { src = S.B12; ld = S.ldB12; rows = ra0; cols = rb1; } break;
+    case HS_HSS_B21: if (!leaf) { src = S.B21; ld = S.ldB21; rows = rb0; cols = ra1; } break;
+    case HS_HSS_R: if (!leaf && tn.parent >= 0) { src = S.R; ld = S.ldR; rows = ra0 + rb0; cols = S.r0; } break;
+    case HS_HSS_W: if (!leaf && tn.parent >= 0) { src = S.WH; ld = S.ldWH; rows = ra1 + rb1; cols = S.r1; ct = true; } break;
+    default: return hs_fail(HS_EARG, "hs_hss_get: unknown generator");
+  }
+  if (src < 0) return hs_fail(HS_EARG, "hs_hss_get: this HSS node has no such generator");
+  dims[0] = rows; dims[1] = cols;
+  if (!out || rows == 0 || cols == 0) return HS_OK;
+  CUDA_OK(cudaSetDevice(f->ctx->device));
+  const size_t esz = f->esz;
+  const int srows = ct ? cols : rows, scols = ct ? rows : cols;
+  std::vector<char> tmp((size_t)srows * scols * esz);
+  CUDA_OK(cudaMemcpy2D(tmp.data(), (size_t)srows * esz, (const char*)f->pool + src * (long long)esz, (size_t)ld * esz, (size_t)srows * esz, scols,
+                       cudaMemcpyDeviceToHost));
+  if (!ct) { std::memcpy(out, tmp.data(), tmp.size()); return HS_OK; }
+  const int nw = (int)(esz / 8);
+  const double* in = (const double*)tmp.data();
+  double* o = (double*)out;
+  for (int j = 0; j < cols; ++j)
+    for (int i = 0; i < rows; ++i) {   // out[i, j] = conj(stored[j, i])
+      const double* e = in + ((size_t)i * srows + j) * nw;
+      double* d = o + ((size_t)j * rows + i) * nw;
+      d[0] = e[0];
+      if (nw == 2) d[1] = -e[1];
+    }
+  return HS_OK;
+  HS_TRY_END
 }
 
 extern "C" int32_t hs_stats(hs_fac* f, hs_stats_t* out) {

@@ -496,6 +496,7 @@ template <typename T> void schur_impl(hs_fac* f, CompLevel& C) {
   const int gs = (int)gd.size();
   for (int c = C.c0; c < C.c1; ++c) {
     const CompFront& cf = f->comp[c];
+    if (cf.hss >= 0) continue;   // HSS Schur complement: the operator stays matrix-free (Abb, Z, Ri), see hs_hss.cu
     const Front& fd = f->fronts[cf.fi];
     GemmDesc d{};
     d.a = wbase + f->runs[2 * c + 1].rws; d.lda = even_up(cf.nb);           // Z
@@ -531,7 +532,7 @@ template <typename T> void schur_impl(hs_fac* f, CompLevel& C) {
     CUDA_OK(cudaMemsetAsync(ws + f->runs[2 * c + 1].rws, 0, (size_t)even_up(cf.nb) * std::max(cf.r2, 1) * sizeof(T), st));
   }
   gen_gemm<T>(f, dg + gz, nc, max_nb, max_r2);
-  gen_gemm<T>(f, dg + gs, nc, max_nb, max_nb);
+  gen_gemm<T>(f, dg + gs, (int)gd.size() - gs, max_nb, max_nb);
 }
 
 template <typename T> void solve_impl_c(hs_fac* f, const CompLevel& C, int64_t nrhs, T* x, bool fwd) {
@@ -602,6 +603,10 @@ void hs_comp_plan(hs_fac* f) {
   CUDA_OK(cudaMalloc((void**)&f->d_lr, f->comp.size() * sizeof(LrDesc)));
   CUDA_OK(cudaMemcpyAsync(f->d_runs, f->runs.data(), f->runs.size() * sizeof(IdRun), cudaMemcpyHostToDevice, st));
   CUDA_OK(cudaStreamSynchronize(st));
+}
+
+void hs_gen_gemm(hs_fac* f, const GemmDesc* d_items, int nitems, int maxM, int maxN) {
+  if (f->dtype == HS_F64) gen_gemm<double>(f, d_items, nitems, maxM, maxN); else gen_gemm<cplx>(f, d_items, nitems, maxM, maxN);
 }
 
 void hs_comp_prepare(hs_fac* f, CompLevel& C) {

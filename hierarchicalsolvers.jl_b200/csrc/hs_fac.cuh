@@ -85,6 +85,9 @@ struct CompFront {
   long long voff = 0;                   // first virtual slot (x index n + voff)
   long long qb = 0, vit = 0, ri = 0;    // element offsets from `pool` of Qb (nb×r1), Riᵀ (nb×r2), Ri (r2×nb)
   int qb_ld = 0, ri_ld = 0;
+  int hss = -1;      // index into hs_fac::hss when this front's Schur complement is stored as an HSS matrix
+  int rx1 = 0, rx2 = 0;  // HSS-children Gauss transforms: ranks of the sketched sparse couplings appended to L / R
+  int hchild = 0;    // 1: both children are HSS with the split at their int/bnd boundary → generator-concatenating transforms
 };
 struct IdRun {       // one truncated column-pivoted QR (pivoted Cholesky of the Gram matrix), device + host
   long long moff;    // pool offset of M(0,0);  M is m × ncol with leading dimension ld
@@ -110,6 +113,40 @@ struct CompLevel {
   int flevel = 0;         // index of the thin level in hs_fac::flevels
   void* side = nullptr;   // thin fronts + Qb + Ri of this level (sized once the ranks are known)
   size_t side_bytes = 0;
+  void* hss_store = nullptr;   // HSS generators of this level's Schur complements (grow-only across refactorizations)
+  size_t hss_store_bytes = 0;
+  void* xws = nullptr;         // workspace of the HSS-children Gauss transforms (copies of the sparse couplings)
+  size_t xws_bytes = 0;
+};
+
+// ---- HSS storage of the Schur complements (factorization.jl:102-110; HssMatrices.jl's HssMatrix) ----------------------
+struct HssTreeNode {       // cluster-tree node of one front, numbered in pre-order inside the front
+  int lo = 0, hi = 0;      // rows [lo, hi) of S[perm,perm]
+  int left = -1, right = -1, parent = -1;
+  int height = 0, isright = 0;
+};
+struct HssStored {         // generators of one HSS node inside the level's store; offsets are element offsets from `pool`
+  int r0 = 0, r1 = 0;      // rank of the row basis (U / [R1;R2]) and of the column basis (V / [W1;W2])
+  long long D = -1, U = -1, VH = -1;   // leaf: D m×m, U m×r0, Vᴴ r1×m
+  long long R = -1, WH = -1;           // non-root branch: R (r0a+r0b)×r0, Wᴴ r1×(r1a+r1b)
+  long long B12 = -1, B21 = -1;        // branch: B12 r0a×r1b, B21 r0b×r1a
+  int ldD = 0, ldU = 0, ldVH = 0, ldR = 0, ldWH = 0, ldB12 = 0, ldB21 = 0;
+};
+struct HssFront {
+  int comp = -1;           // index into hs_fac::comp
+  int m = 0, n1 = 0;       // rows of S[perm,perm] and the forced first split (factorization.jl:109)
+  std::vector<HssTreeNode> tree;
+  std::vector<HssStored> st;
+  std::vector<int> perm;   // [int_loc; bnd_loc], 0-based positions in the node's bnd
+  int perm_off = 0;        // offset of `perm` inside hs_fac::d_hperm
+  int k = 0, rounds = 0;   // sample count of the last round, adaptive rounds taken
+  bool done = false;
+  int hssrank = 0;
+  // what the parent's Gauss transforms take from this HSS matrix (:129-137), element offsets from `pool` into the store:
+  // ta = Û(A11)·B12 (n1×rb1), tb = Û(A22)·B21 ((m−n1)×ra1), vha = V̂(A11)ᴴ (ra1×n1), vhb = V̂(A22)ᴴ (rb1×(m−n1))
+  long long ta = -1, tb = -1, vha = -1, vhb = -1;
+  int ld_ta = 0, ld_tb = 0, ld_vha = 0, ld_vhb = 0;
+  int ra1 = 0, rb1 = 0;
 };
 
 struct hs_fac {
@@ -129,6 +166,10 @@ struct hs_fac {
   std::vector<Level> flevels; // factor / solve levels: per assembly level its dense fronts, then its thin fronts
   std::vector<CompFront> comp;
   std::vector<CompLevel> clevels;
+  std::vector<HssFront> hss;   // HSS Schur complements (opts.hss); CompFront::hss indexes it
+  void* d_sk = nullptr;        // sketch matrices Ω, Ψ on the device (sk_rows × sk_cols each, Ψ behind Ω)
+  long long sk_rows = 0, sk_cols = 0;
+  int* d_hperm = nullptr;      // perm of every HSS front, concatenated
   int nfr = 0;                // number of dense front descriptors; thin descriptors follow at nfr + fi
   bool transient_schur = true; // dense slots of compressed fronts are recycled two levels up
   long long nvirt = 0;        // virtual slots appended to the solution vector
@@ -155,8 +196,9 @@ struct hs_fac {
   void* d_nzval = nullptr;
   void *d_x = nullptr, *d_work = nullptr;
   // CSR image of A for the GMRES mat-vec (built on first use)
-  long long *d_csr_ptr = nullptr, *d_csr_col = nullptr;
+  long long *d_csr_ptr = nullptr, *d_csr_col = nullptr, *d_csr_src = nullptr;  // d_csr_src: CSC position of every CSR entry
   void* d_csr_val = nullptr;
+  bool csr_stale = true;      // values of the CSR image are older than d_nzval (hs_refactor with new values)
   int64_t rhs_cap = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   hs_stats_t stats{};
@@ -164,9 +206,10 @@ struct hs_fac {
   ~hs_fac() {
     cudaFree(pool); cudaFree(d_fronts); cudaFree(d_gidx); cudaFree(d_ipiv); cudaFree(d_rperm); cudaFree(d_cmap);
     cudaFree(d_own); cudaFree(d_pos); cudaFree(d_info); cudaFree(d_colptr); cudaFree(d_rowval); cudaFree(d_nzval);
-    cudaFree(d_x); cudaFree(d_work); cudaFree(d_csr_ptr); cudaFree(d_csr_col); cudaFree(d_csr_val);
+    cudaFree(d_x); cudaFree(d_work); cudaFree(d_csr_ptr); cudaFree(d_csr_col); cudaFree(d_csr_val); cudaFree(d_csr_src);
     cudaFree(d_cws); cudaFree(d_cstate); cudaFree(d_cint); cudaFree(d_runs); cudaFree(d_lr); cudaFree(d_gd);
-    for (auto& c : clevels) cudaFree(c.side);
+    for (auto& c : clevels) { cudaFree(c.side); cudaFree(c.hss_store); cudaFree(c.xws); }
+    cudaFree(d_sk); cudaFree(d_hperm);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
   }
@@ -203,3 +246,11 @@ void hs_comp_plan(hs_fac* f);                        // workspaces + device desc
 void hs_comp_prepare(hs_fac* f, CompLevel& C);       // IDs of Abi / Aib, ranks, thin fronts (before their LU)
 void hs_comp_schur(hs_fac* f, CompLevel& C);         // S = Abb − (Abi·Aii⁻¹Qi)·Ri (after the thin LU)
 void hs_comp_solve(hs_fac* f, const CompLevel& C, int64_t nrhs, void* x, bool fwd);
+struct GemmDesc;
+void hs_gen_gemm(hs_fac* f, const GemmDesc* d_items, int nitems, int maxM, int maxN);  // batched C ∓= A·B on the DMMA kernel
+
+// hs_hss.cu
+void hs_hss_setup();
+void hs_hss_plan(hs_fac* f);                         // cluster trees of the compressed fronts, perm tables, sketch matrices
+void hs_hss_build(hs_fac* f, CompLevel& C);          // randomized adaptive HSS construction + expansion into the dense slots
+void hs_hss_dense(hs_fac* f, int hi, void* out_host);  // dense S[perm,perm] a stored HSS matrix represents (m×m, column-major)

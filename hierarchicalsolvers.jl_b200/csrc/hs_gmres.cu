@@ -84,55 +84,69 @@ __global__ void k_count_rows(long long nnz, const long long* __restrict__ rowval
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p < nnz) atomicAdd(&cnt[rowval[p]], 1ull);
 }
-template <typename T>
+// the CSR image keeps, per entry, the position of that entry in the CSC value array (`csrc`): new values of the same
+// pattern (hs_refactor) are then one gather away
 __global__ void k_fill_csr(long long n, const long long* __restrict__ colptr, const long long* __restrict__ rowval,
-                           const T* __restrict__ nzval, const long long* __restrict__ rptr, unsigned long long* __restrict__ fill,
-                           long long* __restrict__ ccol, T* __restrict__ cval) {
+                           const long long* __restrict__ rptr, unsigned long long* __restrict__ fill,
+                           long long* __restrict__ ccol, long long* __restrict__ csrc) {
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   for (long long p = colptr[j]; p < colptr[j + 1]; ++p) {
     const long long i = rowval[p];
     const long long q = rptr[i] + (long long)atomicAdd(&fill[i], 1ull);
     ccol[q] = j;
-    cval[q] = nzval[p];
+    csrc[q] = p;
   }
 }
 // rows were filled in a racy order: sort each row by column so the mat-vec is bitwise reproducible
-template <typename T>
-__global__ void k_sort_rows(long long n, const long long* __restrict__ rptr, long long* __restrict__ ccol, T* __restrict__ cval) {
+__global__ void k_sort_rows(long long n, const long long* __restrict__ rptr, long long* __restrict__ ccol, long long* __restrict__ csrc) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const long long a = rptr[i], b = rptr[i + 1];
   for (long long p = a + 1; p < b; ++p) {
     const long long c = ccol[p];
-    const T v = cval[p];
+    const long long v = csrc[p];
     long long q = p - 1;
-    while (q >= a && ccol[q] > c) { ccol[q + 1] = ccol[q]; cval[q + 1] = cval[q]; --q; }
+    while (q >= a && ccol[q] > c) { ccol[q + 1] = ccol[q]; csrc[q + 1] = csrc[q]; --q; }
     ccol[q + 1] = c;
-    cval[q + 1] = v;
+    csrc[q + 1] = v;
   }
 }
-
 template <typename T>
-void build_csr(hs_fac* f, const long long* d_colptr, const long long* d_rowval, const T* d_nzval, long long nnz,
-               long long** rptr_out, long long** ccol_out, T** cval_out) {
+__global__ void k_gather_vals(long long nnz, const long long* __restrict__ csrc, const T* __restrict__ nzval, T* __restrict__ cval) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < nnz) cval[q] = nzval[csrc[q]];
+}
+
+// CSR image of the matrix the factorization holds: pattern + source map built once, values gathered again whenever
+// hs_refactor installed new ones (f->csr_stale)
+template <typename T> void ensure_csr(hs_fac* f) {
   cudaStream_t st = f->ctx->stream;
-  const long long n = f->n;
-  long long* rptr = nullptr; long long* ccol = nullptr; T* cval = nullptr; unsigned long long* cnt = nullptr;
-  CUDA_OK(cudaMalloc((void**)&rptr, (size_t)(n + 1) * sizeof(long long)));
-  CUDA_OK(cudaMalloc((void**)&ccol, std::max<size_t>(nnz, 1) * sizeof(long long)));
-  CUDA_OK(cudaMalloc((void**)&cval, std::max<size_t>(nnz, 1) * sizeof(T)));
-  CUDA_OK(cudaMalloc((void**)&cnt, (size_t)(n + 1) * sizeof(unsigned long long)));
-  CUDA_OK(cudaMemsetAsync(cnt, 0, (size_t)(n + 1) * sizeof(unsigned long long), st));
-  if (nnz) k_count_rows<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(nnz, d_rowval, cnt);
-  thrust::exclusive_scan(thrust::cuda::par.on(st), (long long*)cnt, (long long*)cnt + n + 1, rptr);
-  CUDA_OK(cudaMemsetAsync(cnt, 0, (size_t)(n + 1) * sizeof(unsigned long long), st));
-  k_fill_csr<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, d_colptr, d_rowval, d_nzval, rptr, cnt, ccol, cval);
-  k_sort_rows<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, rptr, ccol, cval);
-  CUDA_OK(cudaGetLastError());
-  CUDA_OK(cudaStreamSynchronize(st));
-  cudaFree(cnt);
-  *rptr_out = rptr; *ccol_out = ccol; *cval_out = cval;
+  const long long n = f->n, nnz = f->nnz;
+  if (!f->d_csr_ptr) {
+    unsigned long long* cnt = nullptr;
+    CUDA_OK(cudaMalloc((void**)&f->d_csr_ptr, (size_t)(n + 1) * sizeof(long long)));
+    CUDA_OK(cudaMalloc((void**)&f->d_csr_col, std::max<size_t>(nnz, 1) * sizeof(long long)));
+    CUDA_OK(cudaMalloc((void**)&f->d_csr_src, std::max<size_t>(nnz, 1) * sizeof(long long)));
+    CUDA_OK(cudaMalloc(&f->d_csr_val, std::max<size_t>(nnz, 1) * sizeof(T)));
+    CUDA_OK(cudaMalloc((void**)&cnt, (size_t)(n + 1) * sizeof(unsigned long long)));
+    CUDA_OK(cudaMemsetAsync(cnt, 0, (size_t)(n + 1) * sizeof(unsigned long long), st));
+    if (nnz) k_count_rows<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(nnz, f->d_rowval, cnt);
+    thrust::exclusive_scan(thrust::cuda::par.on(st), (long long*)cnt, (long long*)cnt + n + 1, f->d_csr_ptr);
+    CUDA_OK(cudaMemsetAsync(cnt, 0, (size_t)(n + 1) * sizeof(unsigned long long), st));
+    k_fill_csr<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, f->d_colptr, f->d_rowval, f->d_csr_ptr, cnt, f->d_csr_col, f->d_csr_src);
+    k_sort_rows<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, f->d_csr_ptr, f->d_csr_col, f->d_csr_src);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(st));
+    cudaFree(cnt);
+    f->csr_stale = true;
+  }
+  if (f->csr_stale) {
+    if (nnz) k_gather_vals<T><<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(nnz, f->d_csr_src, (const T*)f->d_nzval, (T*)f->d_csr_val);
+    CUDA_OK(cudaGetLastError());
+    ++f->ctx->launches;
+    f->csr_stale = false;
+  }
 }
 
 using zc = std::complex<double>;
@@ -296,11 +310,7 @@ void gmres_entry(hs_ctx* ctx, long long n, const int64_t* colptr, const int64_t*
   struct Tmp { std::vector<void*> p; ~Tmp() { for (void* q : p) cudaFree(q); } } tmp;
   if (!colptr) {
     if (!f) throw hs_error(HS_EARG, "hs_gmres: no matrix given and no factorization to take it from");
-    if (!f->d_csr_ptr) {
-      T* cv = nullptr;
-      build_csr<T>(f, f->d_colptr, f->d_rowval, (const T*)f->d_nzval, f->nnz, &f->d_csr_ptr, &f->d_csr_col, &cv);
-      f->d_csr_val = cv;
-    }
+    ensure_csr<T>(f);
     rptr = f->d_csr_ptr; ccol = f->d_csr_col; cval = (T*)f->d_csr_val;
   } else {
     // host CSC → CSR on the host (A given explicitly, e.g. a matrix that differs from the factored one)
@@ -334,11 +344,7 @@ void gmres_entry(hs_ctx* ctx, long long n, const int64_t* colptr, const int64_t*
 
 // y = A·x on the device with the matrix the factorization holds (CSR image built on first use, as hs_gmres does)
 template <typename T> static void spmv_impl(hs_fac* f, const void* x, void* y) {
-  if (!f->d_csr_ptr) {
-    T* cv = nullptr;
-    build_csr<T>(f, f->d_colptr, f->d_rowval, (const T*)f->d_nzval, f->nnz, &f->d_csr_ptr, &f->d_csr_col, &cv);
-    f->d_csr_val = cv;
-  }
+  ensure_csr<T>(f);
   const unsigned gb = (unsigned)((f->n + 255) / 256);
   k_spmv_csr<T><<<gb, 256, 0, f->ctx->stream>>>(f->n, f->d_csr_ptr, f->d_csr_col, (const T*)f->d_csr_val, (const T*)x, (T*)y);
   CUDA_OK(cudaGetLastError());
@@ -351,6 +357,39 @@ extern "C" int32_t hs_spmv(hs_fac* f, const void* x, void* y) {
   if (x == y) return hs_fail(HS_EARG, "hs_spmv: x and y must not alias");
   CUDA_OK(cudaSetDevice(f->ctx->device));
   if (f->dtype == HS_F64) spmv_impl<double>(f, x, y); else spmv_impl<cplx>(f, x, y);
+  return HS_OK;
+  HS_TRY_END
+}
+
+// order-independent checksum of the bit patterns of the matrix values a factorization holds (wrapping sum and XOR of the
+// 64-bit words): lets a host binding decide cheaply whether a matrix it is handed is the one already resident in HBM
+__global__ void k_checksum(const unsigned long long* __restrict__ w, long long n, unsigned long long* __restrict__ out) {
+  unsigned long long s = 0, x = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const unsigned long long v = w[i];
+    s += v; x ^= v;
+  }
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); x ^= __shfl_xor_sync(0xffffffffu, x, o); }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(out, s); atomicXor(out + 1, x); }
+}
+
+extern "C" int32_t hs_matrix_checksum(hs_fac* f, uint64_t* sum_out, uint64_t* xor_out) {
+  HS_TRY_BEGIN
+  if (!f || !sum_out || !xor_out) return hs_fail(HS_EARG, "hs_matrix_checksum: null argument");
+  CUDA_OK(cudaSetDevice(f->ctx->device));
+  cudaStream_t st = f->ctx->stream;
+  unsigned long long* d = nullptr;
+  CUDA_OK(cudaMalloc((void**)&d, 2 * sizeof(unsigned long long)));
+  CUDA_OK(cudaMemsetAsync(d, 0, 2 * sizeof(unsigned long long), st));
+  const long long words = f->nnz * (long long)(f->esz / 8);
+  if (words) k_checksum<<<592, 256, 0, st>>>((const unsigned long long*)f->d_nzval, words, d);
+  unsigned long long h[2];
+  cudaError_t e = cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d);
+  CUDA_OK(e);
+  ++f->ctx->launches;
+  *sum_out = h[0]; *xor_out = h[1];
   return HS_OK;
   HS_TRY_END
 }

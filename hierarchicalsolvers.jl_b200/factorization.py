@@ -22,7 +22,11 @@ def factor(A, nd: NestedDissection, nd_loc: NDLoc, opts: SolverOptions = None, d
     chkopts(opts)                                 # :7
     if not sp.issparse(A):
         raise TypeError("factor expects a sparse matrix (SparseMatrixCSC)")
-    A = sp.csc_matrix(A)          # no copy when A already is CSC; duplicates are not allowed (as in SparseMatrixCSC)
+    A = sp.csc_matrix(A)          # no copy when A already is CSC
+    if not A.has_canonical_format:
+        # duplicate entries would overwrite each other in the device gather (SparseMatrixCSC cannot hold duplicates)
+        A = A.copy()
+        A.sum_duplicates()
     if A.shape[0] != A.shape[1]:
         raise _lib.DimensionMismatch(_lib.HS_EDIM, "A must be square")
     cx = np.iscomplexobj(A.data)
@@ -40,7 +44,7 @@ def factor(A, nd: NestedDissection, nd_loc: NDLoc, opts: SolverOptions = None, d
     from .parallel import _tree_struct
     tree, keep = _tree_struct(nd, nd_loc)
     ctx = _lib.default_context(device)
-    copts = to_c(opts)
+    copts, _keep_sk = to_c(opts, dtype=dtype)
     h = C.c_void_p()
     rc = _lib.lib.hs_factor(ctx, _lib.HS_C64 if cx else _lib.HS_F64, n, colptr.ctypes.data_as(C.c_void_p),
                             rowval.ctypes.data_as(C.c_void_p), nzval.ctypes.data_as(C.c_void_p), C.byref(tree),
@@ -50,6 +54,7 @@ def factor(A, nd: NestedDissection, nd_loc: NDLoc, opts: SolverOptions = None, d
             _lib.lib.hs_factor_free(h)
         _lib.check(rc)
     hd = _Handle(h, ctx, dtype, n, nd, nd_loc)
-    # lets gmres() reuse the device-resident copy when it is handed the very same matrix values
-    hd.A_key = (A.data.__array_interface__["data"][0], A.data.shape[0], A.indices.__array_interface__["data"][0])
+    # strong references to the arrays that were uploaded: gmres() reuses the device-resident copy only for these very
+    # objects (identity, not addresses - a freed temporary's address can be recycled) with unchanged contents
+    hd.A_ref = (A.indptr, A.indices, A.data)
     return FactorNode(hd, nd.root)

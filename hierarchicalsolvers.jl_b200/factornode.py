@@ -103,6 +103,47 @@ class FactorNode:
         _lib.check(_lib.lib.hs_node_rank(self._hd.h, self._k, C.byref(rl), C.byref(rr)))
         return int(rl.value), int(rr.value)
 
+    def hss(self):
+        """``F.S`` as the reference stores it for a compressed node — an ``HssMatrix`` (factorization.jl:110-111) — or
+        ``None`` when ``S`` is dense.  Returns the HSS tree in pre-order as a list of dicts: ``lo, hi`` (rows of
+        ``S[perm,perm]``), ``left, right, parent`` (list positions, -1 = none), ``leaf`` and the generators of
+        HssMatrices.jl's type: leaves ``D, U, V``; branches ``B12, B21`` and (below the root) ``R1, R2, W1, W2``."""
+        n = C.c_int64()
+        _lib.check(_lib.lib.hs_hss_info(self._hd.h, self._k, C.byref(n), None))
+        if n.value == 0:
+            return None
+        info = np.zeros((n.value, 8), dtype=np.int64)
+        _lib.check(_lib.lib.hs_hss_info(self._hd.h, self._k, C.byref(n), info.ctypes.data_as(_lib.i64p)))
+
+        def get(t, which):
+            dims = (C.c_int64 * 2)()
+            _lib.check(_lib.lib.hs_hss_get(self._hd.h, self._k, t, which, None, dims))
+            out = np.zeros((int(dims[0]), int(dims[1])), dtype=self._hd.dtype, order="F")
+            if out.size:
+                _lib.check(_lib.lib.hs_hss_get(self._hd.h, self._k, t, which, out.ctypes.data_as(C.c_void_p), dims))
+            return out
+        nodes = []
+        for t in range(n.value):
+            lo, hi, left, right, r0, r1, parent, leaf = (int(v) for v in info[t])
+            d = dict(lo=lo, hi=hi, left=left, right=right, parent=parent, leaf=bool(leaf), rank_u=r0, rank_v=r1)
+            if leaf:
+                d.update(D=get(t, _lib.HS_HSS_D), U=get(t, _lib.HS_HSS_U), V=get(t, _lib.HS_HSS_V))
+            else:
+                d.update(B12=get(t, _lib.HS_HSS_B12), B21=get(t, _lib.HS_HSS_B21))
+                if parent >= 0:
+                    R, W = get(t, _lib.HS_HSS_R), get(t, _lib.HS_HSS_W)
+                    ra0, ra1 = int(info[left][4]), int(info[left][5])
+                    d.update(R1=R[:ra0], R2=R[ra0:], W1=W[:ra1], W2=W[ra1:])
+            nodes.append(d)
+        return nodes
+
+    def hssrank(self) -> int:
+        """``hssrank(F.S)`` (factornode.jl:53): largest off-diagonal generator rank; 0 when ``S`` is dense."""
+        nodes = self.hss()
+        if not nodes:
+            return 0
+        return max([max(*d["B12"].shape, *d["B21"].shape) for d in nodes if not d["leaf"]] + [0])
+
     def resolved_swlevel(self) -> int:
         v = C.c_int64()
         _lib.check(_lib.lib.hs_resolved_swlevel(self._hd.h, C.byref(v)))
@@ -112,8 +153,14 @@ class FactorNode:
         """Numeric re-factorization with new values on the same sparsity and tree."""
         import scipy.sparse as sp
         A = sp.csc_matrix(A)
+        if not A.has_canonical_format:
+            A = A.copy()
+            A.sum_duplicates()
+        if np.iscomplexobj(A.data) and self._hd.dtype == np.float64:
+            raise TypeError("refactor: complex values for a real factorization")
         nz = np.ascontiguousarray(A.data, dtype=self._hd.dtype)
         _lib.check(_lib.lib.hs_refactor(self._hd.h, nz.ctypes.data_as(C.c_void_p), 0))
+        self._hd.A_ref = (A.indptr, A.indices, A.data)     # what the device now holds
         return self
 
     def __repr__(self):
@@ -162,6 +209,9 @@ def ldiv(*args):
     B = np.asarray(B)
     if B.shape[0] != hd.n:
         raise _lib.DimensionMismatch(_lib.HS_EDIM, f"B has {B.shape[0]} rows, expected {hd.n}")
+    if np.iscomplexobj(B) and hd.dtype == np.float64:
+        # the reference has no ldiv! method for mismatched element types (MethodError); never drop the imaginary part
+        raise TypeError("ldiv: complex right-hand side for a real (Float64) factorization")
     vec = B.ndim == 1
     nrhs = 1 if vec else B.shape[1]
     Bf = np.asfortranarray(B.reshape(hd.n, nrhs), dtype=hd.dtype)

@@ -32,11 +32,16 @@ class ConvergenceHistory:
 
 
 def gmres(A, b, Pr: Optional[FactorNode] = None, reltol: float = 1e-9, restart: int = 30, maxiter: int = 30,
-          log: bool = False, device_resident: bool = True, device: int = 0):
+          log: bool = False, device_resident: bool = True, device: int = 0, A_is_factored: Optional[bool] = None):
     """Restarted GMRES(restart), x0 = 0, right preconditioner ``Pr`` (a ``FactorNode``), modified Gram-Schmidt.
 
     ``device_resident=True`` runs the whole iteration in HBM (``hs_gmres``); ``False`` drives the Arnoldi loop on
-    the host and calls ``ldiv!`` once per step the way IterativeSolvers does."""
+    the host and calls ``ldiv!`` once per step the way IterativeSolvers does.
+
+    ``A_is_factored``: ``True`` - ``A`` is the matrix ``Pr`` factored (the copy already resident in HBM is used, nothing
+    is uploaded); ``False`` - upload ``A``; ``None`` (default) - reuse the resident copy only if ``A``'s arrays are the
+    very objects handed to ``factor``/``refactor`` AND their contents still match the device copy (bitwise checksum),
+    otherwise upload."""
     A = sp.csc_matrix(A)
     n = A.shape[0]
     cx = np.iscomplexobj(A.data) or np.iscomplexobj(b) or (Pr is not None and Pr.dtype == np.complex128)
@@ -47,8 +52,15 @@ def gmres(A, b, Pr: Optional[FactorNode] = None, reltol: float = 1e-9, restart: 
         res = np.zeros(max(maxiter, 1), dtype=np.float64)
         nit, conv = C.c_int64(), C.c_int32()
         ctx = Pr._hd.ctx if Pr is not None else _lib.default_context(device)
-        key = (A.data.__array_interface__["data"][0], A.data.shape[0], A.indices.__array_interface__["data"][0])
-        same = Pr is not None and getattr(Pr._hd, "A_key", None) == key
+        same = bool(A_is_factored) and Pr is not None
+        if A_is_factored is None and Pr is not None:
+            ref = getattr(Pr._hd, "A_ref", None)
+            if ref is not None and A.indptr is ref[0] and A.indices is ref[1] and A.data is ref[2] and A.data.dtype == dtype:
+                w = np.ascontiguousarray(A.data).view(np.uint64)
+                hsum, hxor = C.c_uint64(), C.c_uint64()
+                _lib.check(_lib.lib.hs_matrix_checksum(Pr._hd.h, C.byref(hsum), C.byref(hxor)))
+                same = (int(np.add.reduce(w, dtype=np.uint64)) == hsum.value
+                        and int(np.bitwise_xor.reduce(w)) == hxor.value)
         if same:   # the matrix the factorization already holds in HBM
             cp = rv = nzp = None
         else:

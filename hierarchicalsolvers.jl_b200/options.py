@@ -17,6 +17,13 @@ class SolverOptions:
     kest: int = -1          # rank estimate
     stepsize: int = 10      # rank increment of the adaptive sampler
     verbose: bool = False
+    # --- extensions of this library (not fields of the reference struct) ---
+    hss: bool = True        # compressed nodes store S as an HSS matrix (`randcompress_adaptive`, factorization.jl:102-110) like
+                            # the reference; False: S evaluated exactly and kept dense (HSS tolerance -> 0, the round-1 form)
+    sketches: object = None # (Omega, Psi): host-supplied Gaussian test matrices (rows >= largest compressed boundary, cols >= the
+                            # largest sample count); a node with m boundary rows and k samples uses Omega[:m, :k], Psi[:m, :k].
+                            # None: drawn on the device from a counter-based generator seeded with `sketch_seed`
+    sketch_seed: int = 123  # test/rungmres.jl:7 seeds Julia's global RNG with 123
 
     def copy(self, **kw) -> "SolverOptions":
         """``copy(opts; kw...)`` HierarchicalSolvers.jl:62-71."""
@@ -36,9 +43,33 @@ def chkopts(opts: SolverOptions) -> None:
     if not opts.rtol >= 0.0: bad("rtol")
     if not (0.0 < opts.c_tol <= 1.0): bad("c_tol")
     if not opts.leafsize >= 1: bad("leafsize")
+    if opts.verbose:
+        # c_tol is validated and then ignored by the reference itself (factorization.jl:97: tolerance hard-coded 0.5x)
+        print("hsolve: option c_tol has no effect (as in the reference, factorization.jl:97-100)")
+        if not opts.hss:
+            print("hsolve: hss=False - Schur complements stay dense: leafsize, kest, stepsize have no effect")
 
 
-def to_c(opts: SolverOptions, subtree: bool = False) -> _lib.hs_opts:
-    return _lib.hs_opts(int(opts.swlevel), int(opts.swsize), float(opts.atol), float(opts.rtol), float(opts.c_tol),
-                        int(opts.leafsize), int(opts.kest), int(opts.stepsize), int(bool(opts.verbose)),
-                        int(bool(subtree)))
+def to_c(opts: SolverOptions, subtree: bool = False, dtype=None):
+    """``(hs_opts, keepalive)``: the C struct and the host arrays it points to (sketch matrices in the factorization's
+    dtype, column-major)."""
+    import ctypes as C
+
+    import numpy as np
+    keep = []
+    om = ps = None
+    rows = cols = 0
+    if opts.sketches is not None:
+        Om, Ps = opts.sketches
+        dt = np.float64 if dtype is None else dtype
+        Om = np.asfortranarray(Om, dtype=dt)
+        Ps = np.asfortranarray(Ps, dtype=dt)
+        if Om.ndim != 2 or Om.shape != Ps.shape:
+            raise _lib.DimensionMismatch(_lib.HS_EDIM, "sketches must be two matrices of the same shape")
+        keep += [Om, Ps]
+        om, ps = Om.ctypes.data_as(C.c_void_p), Ps.ctypes.data_as(C.c_void_p)
+        rows, cols = Om.shape
+    o = _lib.hs_opts(int(opts.swlevel), int(opts.swsize), float(opts.atol), float(opts.rtol), float(opts.c_tol),
+                     int(opts.leafsize), int(opts.kest), int(opts.stepsize), int(bool(opts.verbose)),
+                     int(bool(subtree)), int(bool(opts.hss)), 0, om, ps, int(rows), int(cols), int(opts.sketch_seed))
+    return o, keep

@@ -45,6 +45,7 @@ class TreePartition:
     int_idx: List[np.ndarray]      # per rank: 1-based DOFs eliminated inside its subtree
     bnd_idx: List[np.ndarray]      # per rank: 1-based boundary DOFs of its subtree root
     work: np.ndarray               # estimated flops per node
+    top_nodes: np.ndarray = None   # global (post-order) id of every node of the top tree
 
 
 def _front_flops(nd: NestedDissection) -> np.ndarray:
@@ -139,7 +140,7 @@ def partition_tree(nd: NestedDissection, nd_loc: NDLoc, nparts: int) -> TreePart
         bnd_idx.append(nd.bnd_idx[nd.bnd_ptr[g]:nd.bnd_ptr[g + 1]].copy())
     top_nodes = np.array(sorted(set(np.nonzero(~in_sub)[0].tolist()) | set(cut)), dtype=np.int64)
     top_nd, top_loc, newid = _slice_tree(nd, nd_loc, top_nodes, set(cut))
-    return TreePartition(cut, sub_nd, sub_loc, top_nd, top_loc, [int(newid[g]) for g in cut], int_idx, bnd_idx, w)
+    return TreePartition(cut, sub_nd, sub_loc, top_nd, top_loc, [int(newid[g]) for g in cut], int_idx, bnd_idx, w, top_nodes)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -201,7 +202,7 @@ class CudaEngine:
     def _factor(self, A, nd, loc, opts, subtree, numeric):
         n, colptr, rowval, nz, flags = self._csc(A)
         tree, keep = _tree_struct(nd, loc)
-        copts = to_c(opts, subtree=subtree)
+        copts, _keep_sk = to_c(opts, subtree=subtree, dtype=self.np_dtype)
         h = C.c_void_p()
         fn = _lib.lib.hs_factor if numeric else _lib.lib.hs_analyze
         dev = getattr(self, "_dev_csc", None)
@@ -295,12 +296,28 @@ class DistributedFactor:
         self.eng = engine if engine is not None else CudaEngine()
         self.part = part = partition_tree(nd, nd_loc, self.world)
         self.n = A.shape[0]
+        # Compression (factorization.jl:8,15) is decided by the level in the WHOLE tree: resolve swlevel here and hand
+        # every partial tree the level budget that is left below its own root.
+        lev = np.zeros(nd.nnodes, dtype=np.int64)
+        lev[nd.nnodes - 1] = 1
+        for k in range(nd.nnodes - 1, -1, -1):          # post-order numbering: parents after children
+            for c in (int(nd.left[k]), int(nd.right[k])):
+                if c >= 0:
+                    lev[c] = lev[k] + 1
+        self._level = lev
+        sw = int(opts.swlevel)
+        self._sw = max(int(lev.max()) + sw, 0) if sw < 0 else sw
+
+        def _opts_below(global_level):
+            return opts.copy(swlevel=max(self._sw - (int(global_level) - 1), 0))
+        self._opts_below = _opts_below
+        self._top_global = part.top_nodes
         self.mode = top if self.world > 1 else "replicated"
         g = self.rank
         nbs = [len(b) for b in part.bnd_idx]
         self.schur_bytes = 0
         # 1. my subtree
-        self.h_sub = self.eng.factor_subtree(A, part.sub_nd[g], part.sub_loc[g], opts)
+        self.h_sub = self.eng.factor_subtree(A, part.sub_nd[g], part.sub_loc[g], _opts_below(lev[part.cut[g]]))
         if self.mode == "replicated":
             # 2. exchange the subtree-root Schur complements (concatenation — boundaries are disjoint)
             self.pad = pad = max(max(nbs), 1)
@@ -309,7 +326,7 @@ class DistributedFactor:
             dist.all_gather(self.schur, mine, group=group)
             self.schur_bytes = int(sum(nb * nb for nb in nbs) * mine.element_size())
             # 3. the fronts above the cut, redundantly on every rank
-            self.h_top = self.eng.analyze_top(A, part.top_nd, part.top_loc, opts)
+            self.h_top = self.eng.analyze_top(A, part.top_nd, part.top_loc, _opts_below(1))
             for r in range(self.world):
                 if nbs[r]:
                     self.eng.import_schur(self.h_top, part.top_leaf[r], self.schur[r], pad)
@@ -361,7 +378,8 @@ class DistributedFactor:
                 dist.recv(self.S[c2], src=src, group=self.group)
                 self.schur_bytes += int(st["nb2"] ** 2 * self.S[c2].element_size())
             if first:
-                st["h"] = eng.analyze_top(A, st["nd"], st["loc"], self.opts, subtree=not st["root"])
+                st["h"] = eng.analyze_top(A, st["nd"], st["loc"], self._opts_below(self._level[self._top_global[st["t"]]]),
+                                          subtree=not st["root"])
                 if st["nb1"]:
                     eng.import_schur(st["h"], 0, self.S[c1], max(st["nb1"], 1))
                 if st["nb2"]:

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define HS_VERSION 100
+#define HS_VERSION 200
 
 /* status codes — the Julia shim maps them to the exception the reference would raise */
 enum {
@@ -40,11 +40,22 @@ enum {
 
 typedef enum { HS_F64 = 0, HS_C64 = 1 } hs_dtype;
 
-/* `SolverOptions` (HierarchicalSolvers.jl:30-40), same field names.  `swlevel` is passed as the user gave it;
- * negative values are resolved against the tree depth inside hs_factor as factorization.jl:8 does.  A node with
- * level ≤ swlevel and |bnd| ≥ swsize is compressed (factorization.jl:15): its L and R become low-rank, truncated at
- * atol/2, rtol/2 (:99-100); its Schur complement is evaluated exactly and kept dense, so `leafsize`, `kest`, `stepsize`
- * (parameters of the reference's HSS storage of S) and `c_tol` (ignored by the reference itself, :97) have no effect. */
+/* `SolverOptions` (HierarchicalSolvers.jl:30-40), same field names, followed by this library's extensions.
+ * `swlevel` is passed as the user gave it; negative values are resolved against the tree depth inside hs_factor as
+ * factorization.jl:8 does.  A node with level ≤ swlevel and |bnd| ≥ swsize is compressed (factorization.jl:15):
+ *   - its L and R become low-rank, truncated at atol/2, rtol/2 (:99-100, :171-209);
+ *   - with `hss` != 0 (the reference's behaviour) its Schur complement S[perm,perm] is stored as an HSS matrix built by
+ *     the adaptive randomized construction (`randcompress_adaptive`, :102-110) from the matrix-free operator of :228-249:
+ *     cluster tree = bisection down to `leafsize` with the first split forced at |int_loc| (:109), `kest` + 10 Gaussian
+ *     samples (kest < 0: ceil(rank(L)/2), :102-104), `stepsize` more whenever a detected rank saturates the sample
+ *     count, truncation at atol, rtol.  Parents then assemble from the HSS-approximated blocks and take their low-rank
+ *     Gauss transforms from the children's generators (:126-140, :184-209);
+ *   - with `hss` == 0 S is evaluated exactly and kept dense (the limit of a zero HSS tolerance); `leafsize`, `kest`,
+ *     `stepsize` then have no effect.
+ * `c_tol` is validated and ignored, as in the reference (:97).
+ * Accuracy floor: the low-rank Gauss transforms truncate through a pivoted Cholesky factorization of a Gram matrix, which
+ * resolves singular values down to about 1e-7·‖block‖; atol/rtol below that (including 0) drive the ranks to
+ * min(ni, nb) without a gain in accuracy.  The HSS construction uses Householder QR with column pivoting (no such floor). */
 typedef struct {
   int64_t swlevel;
   int64_t swsize;
@@ -57,6 +68,17 @@ typedef struct {
   int32_t verbose;
   int32_t subtree;    /* extension for subtree-per-GPU runs: 1 = the tree is a subtree of a larger one — its root keeps a
                          non-empty boundary whose Schur block is exported (hs_schur_export) instead of being solved */
+  int32_t hss;        /* extension: 1 = HSS storage of compressed nodes' Schur complements (see above), 0 = dense */
+  int32_t pad0;
+  /* Host-supplied Gaussian test matrices of the randomized HSS construction (the parity anchor: the reference draws them
+   * from Julia's global RNG, test/rungmres.jl:7).  Column-major sketch_rows × sketch_cols, element type of the
+   * factorization; a compressed node whose S has m rows and needs k samples uses Ω[0:m, 0:k] and Ψ[0:m, 0:k] (S·Ω and
+   * Sᴴ·Ψ).  sketch_rows must cover the largest compressed boundary and sketch_cols the largest sample count reached
+   * (HS_EARG otherwise).  NULL: both are drawn on the device from a counter-based generator seeded with sketch_seed. */
+  const void* sketch_omega;
+  const void* sketch_psi;
+  int64_t sketch_rows, sketch_cols;
+  uint64_t sketch_seed;
 } hs_opts;
 
 /* Serialized elimination tree, the ragged form of the `.mat` schema that parse_elimtree consumes
@@ -118,6 +140,12 @@ typedef struct {
   double ms_compress;      /* compressed fronts: pivoted QR of A_bi / A_ib, thin fronts, Schur complement      */
   double lowrank_bytes;    /* device bytes of the thin fronts + low-rank factors of compressed fronts (their dense
                               slots are transient and counted once, as two arenas, in front_bytes)            */
+  double ms_hss;           /* randomized HSS construction of the Schur complements (sketches, IDs, couplings, expansion) */
+  double hss_bytes;        /* device bytes of the stored HSS generators                                          */
+  int64_t hss_maxrank;     /* max over compressed nodes of hssrank(S) (factornode.jl:53)                          */
+  int64_t hss_rounds;      /* adaptive rounds taken in total (1 per compressed level when no rank saturated)      */
+  int64_t hss_nodes;       /* HSS tree nodes over all compressed fronts                                           */
+  double sketch_flops;     /* flops of the sketch GEMMs S·Ω, Sᴴ·Ψ (matrix-free: Abb·X − Z·(Ri·X))                 */
 } hs_stats_t;
 
 typedef enum { HS_GET_D = 0, HS_GET_S = 1, HS_GET_L = 2, HS_GET_R = 3, HS_GET_FRONT = 4, HS_GET_PIV = 5 } hs_which;
@@ -199,10 +227,19 @@ int32_t hs_solve(hs_fac* fac, int64_t nrhs, const void* B, int64_t ldb, void* X,
  * (D = the pivot block A_ii, L = A_bi·A_ii⁻¹, R = A_ii⁻¹·A_ib, S = Schur complement permuted by
  * [int_loc; bnd_loc]); HS_GET_FRONT returns the raw partially factored front, HS_GET_PIV its pivots (int64). */
 int32_t hs_node_get(hs_fac* fac, int64_t node, hs_which which, void* out, int64_t* dims);
-int32_t hs_maxrank(hs_fac* fac, int64_t* rank);              /* factornode.jl:49-57 */
+int32_t hs_maxrank(hs_fac* fac, int64_t* rank);              /* factornode.jl:49-57: max over nodes of hssrank(S), rank(L), rank(R) */
 /* rank(F.L), rank(F.R) of one node (LowRankMatrix, factorization.jl:173,179); 0, 0 for an uncompressed node whose
  * L and R are dense.  For a compressed node hs_node_get returns the dense products L = U·Vᴴ, R = U·Vᴴ. */
 int32_t hs_node_rank(hs_fac* fac, int64_t node, int64_t* rank_l, int64_t* rank_r);
+/* HSS form of a compressed node's Schur complement (`F.S::HssMatrix`, factorization.jl:110-111; fields of
+ * HssMatrices.jl's HssMatrix: leaf D, U, V; branch B12, B21, R1/R2 stacked as R, W1/W2 stacked as W).  HSS tree nodes of
+ * one front are numbered in pre-order (0 = root, then the whole A11 subtree, then A22).
+ *   hs_hss_info(fac, node, &nhss, info): nhss = number of HSS tree nodes (0: S is dense); info (may be NULL, else
+ *     8·nhss int64): per HSS node {lo, hi, left, right, rank_u, rank_v, parent, is_leaf}; rows [lo, hi) of S[perm,perm].
+ *   hs_hss_get(fac, node, hnode, which, out, dims): one generator, column-major; out == NULL queries dims. */
+typedef enum { HS_HSS_D = 0, HS_HSS_U = 1, HS_HSS_V = 2, HS_HSS_B12 = 3, HS_HSS_B21 = 4, HS_HSS_R = 5, HS_HSS_W = 6 } hs_hss_which;
+int32_t hs_hss_info(hs_fac* fac, int64_t node, int64_t* nhss, int64_t* info);
+int32_t hs_hss_get(hs_fac* fac, int64_t node, int64_t hnode, hs_hss_which which, void* out, int64_t* dims);
 int32_t hs_stats(hs_fac* fac, hs_stats_t* out);
 int32_t hs_resolved_swlevel(hs_fac* fac, int64_t* swlevel);  /* factorization.jl:8 */
 /* Device-resident copy of the matrix a factorization holds (0-based int64 colptr / rowval, nzval of the factorization's
@@ -211,6 +248,9 @@ int32_t hs_resolved_swlevel(hs_fac* fac, int64_t* swlevel);  /* factorization.jl
 /* y = A·x on the device (x, y device vectors of the factorization's dtype, asynchronous on the context's stream) with the
  * matrix `fac` holds — the mat-vec of a Krylov loop driven from the host side (replicated GMRES of the multi-GPU path). */
 int32_t hs_spmv(hs_fac* fac, const void* x, void* y);
+/* wrapping sum and XOR of the 64-bit words of the matrix values held in HBM: lets a host binding check cheaply that a
+ * matrix it is handed still equals the resident copy before skipping the upload (hs_gmres with colptr == NULL) */
+int32_t hs_matrix_checksum(hs_fac* fac, uint64_t* sum_out, uint64_t* xor_out);
 int32_t hs_matrix_device(hs_fac* fac, const int64_t** colptr, const int64_t** rowval, const void** nzval, int64_t* nnz);
 
 /* ---- GMRES with the factorization as right preconditioner (test/rungmres.jl:47-48) ---------------

@@ -273,7 +273,8 @@ def _row_id(S: np.ndarray, atol: float, rtol: float):
 
 
 def randcompress_adaptive(mul, mulc, getidx, rcl: ClusterTree, ccl: ClusterTree, kest: int = 10, stepsize: int = 10,
-                          atol: float = 1e-9, rtol: float = 1e-9, rng=None, sketches=None, max_rounds: int = 12) -> HssMatrix:
+                          atol: float = 1e-9, rtol: float = 1e-9, rng=None, sketches=None, max_rounds: int = 12,
+                          strict_sketches: bool = False) -> HssMatrix:
     """HSS form of an operator given only by ``mul(X) = A·X``, ``mulc(X) = Aᴴ·X`` and ``getidx(I, J) = A[I, J]`` (0-based
     index vectors) — the ``LinearMap`` the reference builds for the Schur complement (factorization.jl:228-235) and hands
     to ``randcompress_adaptive(Smap, cl, cl; kest, atol, rtol)`` (:110).  Gaussian test matrices with ``kest`` columns
@@ -288,6 +289,8 @@ def randcompress_adaptive(mul, mulc, getidx, rcl: ClusterTree, ccl: ClusterTree,
     for _ in range(max_rounds):
         if sketches is not None and sketches[0].shape[1] >= k:
             Om, Ps = sketches[0][:, :k], sketches[1][:, :k]
+        elif strict_sketches:
+            raise ValueError(f"randcompress_adaptive: {k} sample columns needed, the supplied sketch matrices have {sketches[0].shape[1]}")
         else:
             Om, Ps = rng.standard_normal((n, k)), rng.standard_normal((m, k))
         Sr, Sc = mul(Om), mulc(Ps)

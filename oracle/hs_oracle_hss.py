@@ -184,7 +184,7 @@ def _gauss_transforms_hss_children(D, Aib, Abi, lr, atol, rtol):
     return L, R
 
 
-def _factor_branch_compressed(A, Fl, Fr, nd, nd_loc, atol, rtol, hss=False, leafsize=32, kest=-1, stepsize=10) -> FactorNode:
+def _factor_branch_compressed(A, Fl, Fr, nd, nd_loc, atol, rtol, hss=False, leafsize=32, kest=-1, stepsize=10, sketches=None) -> FactorNode:
     """factorization.jl:78-112 with the Schur operator of :228-249 evaluated densely (module docstring).  ``hss=True``
     stores its HSS approximation (oracle/hs_hss.py) like the reference; parents then assemble from the approximated
     blocks, which is what the reference's HSS-children methods (:126-140, blockmatrix.jl:121-130) do in HSS arithmetic."""
@@ -216,25 +216,32 @@ def _factor_branch_compressed(A, Fl, Fr, nd, nd_loc, atol, rtol, hss=False, leaf
             kest = int(np.ceil(0.5 * L.rank))                                             # :102-104
         Smul, Smulc, Sidx = _schur_complement(Abb.dense(), Abi.dense(), R, perm)         # :108
         cl = hs_hss.bisection_cluster((len(nd_loc.int), len(perm)), leafsize)             # :109
-        Sp = hs_hss.randcompress_adaptive(Smul, Smulc, Sidx, cl, cl, kest=kest, stepsize=stepsize, atol=atol, rtol=rtol,
-                                          rng=np.random.default_rng(len(perm)))           # :110
+        # `sketches = (Ω, Ψ)`: host-supplied Gaussian test matrices shared with the CUDA library (the parity anchor of
+        # SURVEY §8c): a node with m boundary rows and k samples uses Ω[:m, :k], Ψ[:m, :k]
+        sk = None if sketches is None else (sketches[0][:len(perm)], sketches[1][:len(perm)])
+        if cl.isleaf():
+            Sp = hs_hss.HssMatrix(); Sp.leaf = True; Sp.rows = Sp.cols = len(perm)
+            Sp.D = np.asarray(Sidx(np.arange(len(perm)), np.arange(len(perm))))            # a single dense block
+        else:
+            Sp = hs_hss.randcompress_adaptive(Smul, Smulc, Sidx, cl, cl, kest=kest, stepsize=stepsize, atol=atol, rtol=rtol,
+                                              rng=np.random.default_rng(len(perm)), sketches=sk, strict_sketches=sk is not None)  # :110
     elif hss and len(perm):
         Sp = _to_hss(Sp, len(nd_loc.int), leafsize, atol, rtol)   # :109-110 by the direct construction
     return FactorNode(D, Sp, L, R, nd.int, nd.bnd, nd_loc.int, nd_loc.bnd, Fl, Fr)
 
 
 def factor(A, nd, nd_loc, swlevel=5, swsize=1, atol=1e-6, rtol=1e-6, leafsize=32, kest=-1, stepsize=10, hss=False,
-           **_unused) -> FactorNode:
+           sketches=None, **_unused) -> FactorNode:
     """factorization.jl:5-11 — options as ``SolverOptions`` (HierarchicalSolvers.jl:30-40 defaults).  ``hss=False`` (what
     the CUDA library implements this round) keeps every Schur complement dense; ``hss=True`` stores the HSS
     approximation of compressed nodes' Schur complements (direct construction), ``hss="rand"`` builds it the reference's
     way: the matrix-free operator of :228-249 handed to the randomized adaptive construction with ``kest``/``stepsize``."""
     A = sp.csr_matrix(A)
     sw = max(base.depth(nd) + swlevel, 0) if swlevel < 0 else swlevel   # :8
-    return _factor(A, nd, nd_loc, 1, sw, swsize, atol, rtol, hss, leafsize, kest, stepsize)
+    return _factor(A, nd, nd_loc, 1, sw, swsize, atol, rtol, hss, leafsize, kest, stepsize, sketches)
 
 
-def _factor(A, nd, nd_loc, level, swlevel, swsize, atol, rtol, hss=False, leafsize=32, kest=-1, stepsize=10) -> FactorNode:
+def _factor(A, nd, nd_loc, level, swlevel, swsize, atol, rtol, hss=False, leafsize=32, kest=-1, stepsize=10, sketches=None) -> FactorNode:
     """factorization.jl:14-27."""
     compression_flag = level <= swlevel and len(nd.bnd) >= swsize   # :15
     if isleaf(nd):
@@ -243,10 +250,10 @@ def _factor(A, nd, nd_loc, level, swlevel, swsize, atol, rtol, hss=False, leafsi
             F.S = _to_hss(F.S, len(nd_loc.int), leafsize, atol, rtol)   # :56-57
         return F
     elif isbranch(nd):
-        Fl = _factor(A, nd.left, nd_loc.left, level + 1, swlevel, swsize, atol, rtol, hss, leafsize, kest, stepsize)
-        Fr = _factor(A, nd.right, nd_loc.right, level + 1, swlevel, swsize, atol, rtol, hss, leafsize, kest, stepsize)
+        Fl = _factor(A, nd.left, nd_loc.left, level + 1, swlevel, swsize, atol, rtol, hss, leafsize, kest, stepsize, sketches)
+        Fr = _factor(A, nd.right, nd_loc.right, level + 1, swlevel, swsize, atol, rtol, hss, leafsize, kest, stepsize, sketches)
         if compression_flag:
-            return _factor_branch_compressed(A, Fl, Fr, nd, nd_loc, atol, rtol, hss, leafsize, kest, stepsize)
+            return _factor_branch_compressed(A, Fl, Fr, nd, nd_loc, atol, rtol, hss, leafsize, kest, stepsize, sketches)
         if hss and (hasattr(Fl.S, "dense") or hasattr(Fr.S, "dense")):
             # an uncompressed node above compressed children (always the root, factorization.jl:15 with |bnd| = 0)
             class _V:      # children viewed through their dense Schur blocks

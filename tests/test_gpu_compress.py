@@ -31,6 +31,7 @@ def _both(hs, orc, prob, keep_schur=False, **opts):
     """Oracle and GPU factorizations of the same problem.  ``keep_schur``: keep the dense Schur blocks of compressed
     fronts (HS_KEEP_SCHUR=1) so that ``F.S`` of those nodes can be read back; by default their slots are transient."""
     import os
+    opts.setdefault("hss", False)   # this file pins the low-rank Gauss transforms with dense Schur complements; test_gpu_hss.py the HSS form
     Ap, nd, nd_loc, perm = orc.prepare(prob.A, prob.elim_tree)
     Fo = orc.factor(Ap, nd, nd_loc, **opts)
     hnd = hs.from_elimtree(prob.elim_tree)
@@ -125,13 +126,13 @@ def test_compression_options_semantics(hs, orc):
     import hs_oracle_hss as oh
     for sw, size in [(2, 1), (3, 40), (-3, 1), (50, 10 ** 6)]:
         Fo = orc.factor(Ap, nd, nd_loc, swlevel=sw, swsize=size, atol=1e-4, rtol=1e-4)
-        F = hs.factor(A, hnd, hloc, swlevel=sw, swsize=size, atol=1e-4, rtol=1e-4)
+        F = hs.factor(A, hnd, hloc, swlevel=sw, swsize=size, atol=1e-4, rtol=1e-4, hss=False)
         ro = oh.node_ranks(Fo)
         rg = [F.node(k).ranks() for k in range(len(ro))]
         assert [r != (0, 0) for r in rg] == [r != (0, 0) for r in ro]
         assert hs.maxrank(F) == orc.maxrank(Fo)
     # refactor keeps working on a compressed factorization
-    F = hs.factor(A, hnd, hloc, swlevel=3, swsize=1, atol=1e-6, rtol=1e-6)
+    F = hs.factor(A, hnd, hloc, swlevel=3, swsize=1, atol=1e-6, rtol=1e-6, hss=False)
     x1 = hs.ldiv(F, prob.b)
     F.refactor(A)
     assert np.allclose(hs.ldiv(F, prob.b), x1, rtol=1e-12, atol=0)

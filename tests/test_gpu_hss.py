@@ -1,0 +1,179 @@
+"""GPU: HSS storage of the Schur complements (`randcompress_adaptive` on the matrix-free Schur operator,
+factorization.jl:102-110,228-249) and the HSS-children methods (:126-140, :184-209) against the oracle's restatement
+(oracle/hs_oracle_hss.factor(..., hss="rand"), oracle/hs_hss.py) — with the SAME host-supplied Gaussian sketch matrices
+on both sides, the parity anchor BASELINE.json's north_star names.
+
+Tolerances.  Both sides run Householder QR with column pivoting on the same sample blocks; random samples have no tied
+column norms, so the pivot orders — hence skeleton index sets, ranks and every generator — must agree: ranks exactly,
+generators and the represented matrix to 1e-8 relative (the sample blocks themselves come from DMMA GEMMs vs LAPACK
+GEMMs: rounding-level differences amplified by the interpolation solves)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+pytestmark = pytest.mark.gpu
+
+
+def _perturbed(hs, shape, kind, nmax, seed=0):
+    prob = hs.grid_problem(shape, kind, nmax=nmax)
+    rng = np.random.default_rng(seed)
+    A = sp.csr_matrix(prob.A).copy()
+    A.data = A.data * (1.0 + 0.3 * rng.random(A.nnz))
+    prob.A = sp.csc_matrix(A)
+    return prob
+
+
+def _sketches(prob, cols=160, seed=11):
+    rng = np.random.default_rng(seed)
+    nbmax = int(prob.elim_tree.nbound().max())
+    return rng.standard_normal((nbmax, cols)), rng.standard_normal((nbmax, cols))
+
+
+def _both(hs, orc, prob, **opts):
+    Ap, nd, nd_loc, perm = orc.prepare(prob.A, prob.elim_tree)
+    Fo = orc.factor(Ap, nd, nd_loc, hss="rand", **opts)
+    A, hnd, hloc, _ = hs.prepare(prob.A, prob.elim_tree)
+    F = hs.factor(A, hnd, hloc, hss=True, **opts)
+    return Ap, Fo, F
+
+
+def _preorder(h):
+    out = [h]
+    if not h.leaf:
+        out += _preorder(h.A11) + _preorder(h.A22)
+    return out
+
+
+def _rel(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    nb = np.linalg.norm(b)
+    return np.linalg.norm(a - b) / nb if nb > 0 else np.linalg.norm(a)
+
+
+def _compare_hss(gnodes, ho, tol, tag):
+    onodes = _preorder(ho)
+    assert len(gnodes) == len(onodes), (tag, len(gnodes), len(onodes))
+    for t, (g, o) in enumerate(zip(gnodes, onodes)):
+        assert g["leaf"] == o.leaf and g["hi"] - g["lo"] == o.rows, (tag, t)
+        if o.leaf:
+            names = ("D", "U", "V")
+        else:
+            names = ("B12", "B21") + (("R1", "R2", "W1", "W2") if g["parent"] >= 0 else ())
+        for nme in names:
+            Xo = getattr(o, nme)
+            if Xo is None:
+                continue
+            assert g[nme].shape == Xo.shape, (tag, t, nme, g[nme].shape, Xo.shape)
+            if Xo.size:
+                e = _rel(g[nme], Xo)
+                assert e < tol, (tag, t, nme, e)
+
+
+CASES = [("poisson", (65, 65), 1e-6, 16, -1), ("helmholtz", (65, 65), 1e-6, 16, -1), ("poisson", (65, 65), 1e-3, 12, 4),
+         ("helmholtz", (49, 49), 1e-4, 32, 30), ("poisson", (12, 11, 10), 1e-4, 16, -1)]
+
+
+@pytest.mark.parametrize("kind,shape,tol,leafsize,kest", CASES)
+def test_hss_schur_complement_matches_oracle(hs, orc, kind, shape, tol, leafsize, kest):
+    """One compressed level (swlevel=2): children dense, `S` of the level-2 nodes stored as HSS by the randomized adaptive
+    construction; the root assembles from the HSS-approximated blocks."""
+    import hs_hss as H
+    prob = _perturbed(hs, shape, kind, nmax=40)
+    Om, Ps = _sketches(prob)
+    opts = dict(swlevel=2, swsize=16, atol=tol, rtol=tol, leafsize=leafsize, kest=kest, stepsize=7, sketches=(Om, Ps))
+    Ap, Fo, F = _both(hs, orc, prob, **opts)
+    onodes = orc.nodes_postorder(Fo)
+    nh = 0
+    for k, no in enumerate(onodes):
+        nk = F.node(k)
+        g = nk.hss()
+        if not isinstance(no.S, H.HssMatrix) or no.S.leaf:
+            assert g is None
+            continue
+        nh += 1
+        assert g is not None, f"node {k}: S should be an HSS matrix"
+        assert nk.ranks() == (no.L.rank, no.R.rank)
+        _compare_hss(g, no.S, 1e-8, f"node {k}")
+        assert nk.hssrank() == H.hssrank(no.S)
+        assert _rel(nk.S, no.S.dense()) < 1e-8                       # the matrix the HSS form represents
+    assert nh > 0
+    assert hs.maxrank(F) == orc.maxrank(Fo) > 0                      # factornode.jl:49-57 incl. hssrank(S)
+    # nodes above (the root) assemble from the approximated blocks
+    root_o = onodes[-1]
+    for name, Xo in (("D", root_o.D_dense()), ("L", root_o.L_dense()), ("R", root_o.R_dense())):
+        if Xo.size:
+            assert _rel(getattr(F, name), Xo) < 1e-8, name
+    b = prob.b
+    xo, xg = orc.ldiv(Fo, b), hs.ldiv(F, b)
+    assert _rel(xg, xo) < 1e-8
+    _, reso, convo = orc.gmres(Ap, b, Pr=lambda v: orc.ldiv(Fo, v), reltol=1e-9, restart=30, maxiter=30)
+    xs, ch = hs.gmres(sp.csc_matrix(Ap), b, Pr=F, reltol=1e-9, restart=30, maxiter=30, log=True)
+    assert ch.isconverged == convo and ch.iters == len(reso)        # north_star: the iteration count must match
+    assert np.allclose(np.asarray(ch.resnorm), np.asarray(reso), rtol=1e-6, atol=1e-12 * np.linalg.norm(b))
+    st = F.stats()
+    assert st["hss_nodes"] > 0 and st["sketch_flops"] > 0 and st["hss_maxrank"] > 0
+
+
+def test_hss_adaptive_rounds_and_option_semantics(hs, orc):
+    """kest / stepsize / leafsize are live: a small kest forces extra adaptive rounds (same ranks as the oracle's loop),
+    leafsize changes the cluster tree, too few supplied sketch columns is an ArgumentError."""
+    import hs_hss as H
+    prob = _perturbed(hs, (65, 65), "poisson", nmax=40)
+    Om, Ps = _sketches(prob, cols=200)
+    base = dict(swlevel=2, swsize=16, atol=1e-6, rtol=1e-6, sketches=(Om, Ps))
+    Ap, Fo, F = _both(hs, orc, prob, leafsize=16, kest=2, stepsize=5, **base)
+    assert F.stats()["hss_rounds"] > 1
+    for k, no in enumerate(orc.nodes_postorder(Fo)):
+        if isinstance(no.S, H.HssMatrix) and not no.S.leaf:
+            _compare_hss(F.node(k).hss(), no.S, 1e-8, f"node {k}")
+    assert hs.maxrank(F) == orc.maxrank(Fo)
+    _, _, F8 = _both(hs, orc, prob, leafsize=8, kest=20, stepsize=10, **base)
+    k2 = next(k for k in range(F._hd.nd.nnodes) if F.node(k).hss() is not None)
+    assert len(F8.node(k2).hss()) > len(F.node(k2).hss())
+    A, hnd, hloc, _ = hs.prepare(prob.A, prob.elim_tree)
+    with pytest.raises(hs.ArgumentError):
+        hs.factor(A, hnd, hloc, hss=True, leafsize=16, kest=40, swlevel=2, swsize=16, sketches=(Om[:, :20], Ps[:, :20]))
+    # no sketches supplied: the device generator draws them; same seed => same factorization, and it still preconditions
+    F1 = hs.factor(A, hnd, hloc, hss=True, leafsize=16, swlevel=2, swsize=16, atol=1e-6, rtol=1e-6, sketch_seed=5)
+    F2 = hs.factor(A, hnd, hloc, hss=True, leafsize=16, swlevel=2, swsize=16, atol=1e-6, rtol=1e-6, sketch_seed=5)
+    x1, x2 = hs.ldiv(F1, prob.b), hs.ldiv(F2, prob.b)
+    assert np.array_equal(x1, x2)
+    assert np.linalg.norm(A @ x1 - prob.b) / np.linalg.norm(prob.b) < 1e-4
+    x1b = hs.ldiv(F1.refactor(A), prob.b)
+    assert np.allclose(x1b, x1, rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("kind,shape,tol", [("poisson", (65, 65), 1e-6), ("helmholtz", (65, 65), 1e-5), ("poisson", (129, 129), 1e-2)])
+def test_hss_children_methods_match_oracle(hs, orc, kind, shape, tol):
+    """Several compressed levels (swlevel=-2 as test/rungmres.jl:39): parents of HSS children take the HSS methods —
+    `_assemble_blocks` from the generators (:126-140), generator-concatenating Gauss transforms plus the sketched sparse
+    couplings (:184-209, incl. the extra 0.5x of :202) — so rank(L), rank(R) are sums of the children's HSS ranks."""
+    import hs_hss as H
+    import hs_oracle_hss as oh
+    prob = _perturbed(hs, shape, kind, nmax=40 if shape[0] < 100 else 100)
+    Om, Ps = _sketches(prob, cols=220)
+    opts = dict(swlevel=-2, swsize=16 if shape[0] < 100 else 64, atol=tol, rtol=tol, leafsize=16 if shape[0] < 100 else 32,
+                kest=-1, stepsize=10, sketches=(Om, Ps))
+    Ap, Fo, F = _both(hs, orc, prob, **opts)
+    onodes = orc.nodes_postorder(Fo)
+    ranks_o = oh.node_ranks(Fo)
+    nchild = 0
+    for k, (no, ro) in enumerate(zip(onodes, ranks_o)):
+        nk = F.node(k)
+        assert nk.ranks() == ro, f"node {k}: ranks {nk.ranks()} vs oracle {ro}"
+        if isinstance(no.S, H.HssMatrix) and not no.S.leaf:
+            assert nk.hssrank() == H.hssrank(no.S), k
+            assert _rel(nk.S, no.S.dense()) < 1e-7, k
+        if ro != (0, 0) and no.left is not None and isinstance(no.left.S, H.HssMatrix) and isinstance(no.right.S, H.HssMatrix):
+            nchild += 1
+            for name, Xo in (("D", no.D_dense()), ("L", no.L_dense()), ("R", no.R_dense())):
+                assert _rel(getattr(nk, name), Xo) < 1e-7, (k, name)
+    assert nchild > 0
+    assert hs.maxrank(F) == orc.maxrank(Fo) > 0
+    b = prob.b
+    assert _rel(hs.ldiv(F, b), orc.ldiv(Fo, b)) < 1e-7
+    _, reso, convo = orc.gmres(Ap, b, Pr=lambda v: orc.ldiv(Fo, v), reltol=1e-9, restart=30, maxiter=30)
+    xs, ch = hs.gmres(sp.csc_matrix(Ap), b, Pr=F, reltol=1e-9, restart=30, maxiter=30, log=True)
+    assert ch.isconverged == convo and ch.iters == len(reso)
+    assert np.allclose(np.asarray(ch.resnorm), np.asarray(reso), rtol=1e-5, atol=1e-12 * np.linalg.norm(b))
