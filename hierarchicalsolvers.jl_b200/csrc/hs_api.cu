@@ -554,6 +554,15 @@ static void build_plan(hs_fac* f, const hs_tree* t) {
   for (int64_t k = 0; k < nn; ++k)   // subtree mode included: the root's dense slot is persistent, so its S can be exported
       cflag[k] = f->left[k] >= 0 && f->level[k] <= f->swlevel_resolved && f->node_nb[k] >= f->opts.swsize &&
                  f->node_ni[k] > 0 && f->node_nb[k] > 0;
+  // which compressed nodes will hold an HSS Schur complement (cluster root not a single leaf, hs_hss.cu) and which of them
+  // have the first cluster split forced at the int/bnd boundary (0 < |int_loc| < |perm|, factorization.jl:109): a
+  // compressed node whose two children both do takes the HSS-children methods (:86-91 by dispatch)
+  std::vector<char> hss_forced(nn, 0);
+  if (f->opts.hss)
+    for (int64_t k = 0; k < nn; ++k) {
+      const int64_t n1 = nloc(f->iloc_ptr, k), m = n1 + nloc(f->bloc_ptr, k);
+      hss_forced[k] = cflag[k] && n1 > 0 && n1 < m;
+    }
   // front order: deepest level first; inside a level the dense fronts before the compressed ones, each group by ni
   // descending (active panels form a prefix)
   std::vector<int64_t> order(nn);
@@ -642,7 +651,7 @@ static void build_plan(hs_fac* f, const hs_tree* t) {
   {
     size_t cap = (size_t)ioff + (pseudo ? f->node_nb[root] : 0);
     for (int64_t k = 0; k < nn; ++k)
-      if (cflag[k]) cap += (size_t)f->node_ni[k] + std::min(f->node_ni[k], f->node_nb[k]);  // thin descriptors
+      if (cflag[k]) cap += 2 * ((size_t)f->node_ni[k] + f->node_nb[k]);  // thin descriptors (border ≤ ni + nb rows)
     gidx.reserve(cap); cmap.reserve(cap);
     gidx.set_size(ioff); cmap.set_size(ioff);
   }
@@ -707,6 +716,7 @@ static void build_plan(hs_fac* f, const hs_tree* t) {
   f->fronts.resize(2 * (size_t)nfr, Front{});
   f->flevels.clear(); f->comp.clear(); f->clevels.clear();
   f->nvirt = 0;
+  std::vector<int> front2comp(nfr, -1);
   for (size_t li = 0; li < f->levels.size(); ++li) {
     const Level& L = f->levels[li];
     if (L.fm > L.f0 || L.f1 == L.f0) {
@@ -730,15 +740,23 @@ static void build_plan(hs_fac* f, const hs_tree* t) {
       for (int i = L.fm; i < L.f1; ++i) {
         const Front& fd = f->fronts[i];
         CompFront cf; cf.fi = i; cf.ni = fd.ni; cf.nb = fd.n - fd.ni; cf.rcap = std::min(cf.ni, cf.nb);
-        cf.voff = f->nvirt; f->nvirt += cf.rcap;
+        {
+          const int64_t k = order[i], l = f->left[k], r = f->right[k];
+          cf.hchild = l >= 0 && hss_forced[l] && hss_forced[r];
+          if (cf.hchild) { cf.cl = front2comp[f->node2front[l]]; cf.cr = front2comp[f->node2front[r]]; }
+          cf.ni_l = fd.ni_l; cf.nb_l = fd.nb_l;
+          front2comp[i] = (int)f->comp.size();
+        }
+        cf.vcap = cf.hchild ? cf.ni + cf.nb : cf.rcap;
+        cf.voff = f->nvirt; f->nvirt += cf.vcap;
         f->comp.push_back(cf);
         Front& th = f->fronts[nfr + i];
         th = fd;
         th.ioff = ioff; th.parent = -1; th.ni_l = -1; th.nb_l = 0; th.flags = 0;
         th.n = fd.ni; th.ld = (fd.ni + 1) & ~1;  // set per factorization once the ranks are known
         for (int q = 0; q < fd.ni; ++q) gidx.push_back(gidx[fd.ioff + q]);
-        for (int q = 0; q < cf.rcap; ++q) gidx.push_back((int)(f->n + cf.voff + q));
-        ioff += fd.ni + cf.rcap;
+        for (int q = 0; q < cf.vcap; ++q) gidx.push_back((int)(f->n + cf.voff + q));
+        ioff += fd.ni + cf.vcap;
         Tl.ni_sorted.push_back(fd.ni);
         Tl.max_ni = std::max(Tl.max_ni, fd.ni);
       }
@@ -757,7 +775,7 @@ static void build_plan(hs_fac* f, const hs_tree* t) {
   for (auto& L : f->flevels) f->max_level_idx = std::max(f->max_level_idx, L.ioff1 - L.ioff0 + 0);
   for (auto& C : f->clevels) {  // the border of a thin front may grow to rcap rows
     long long span = 0;
-    for (int c = C.c0; c < C.c1; ++c) span += f->comp[c].ni + f->comp[c].rcap;
+    for (int c = C.c0; c < C.c1; ++c) span += f->comp[c].ni + f->comp[c].vcap;
     f->max_level_idx = std::max(f->max_level_idx, span);
   }
   const double cx = f->dtype == HS_C64 ? 4.0 : 1.0;
@@ -1333,20 +1351,21 @@ extern "C" int32_t hs_hss_get(hs_fac* f, int64_t node, int64_t hnode, hs_hss_whi
   const HssStored& S = H.st[hnode];
   const bool leaf = tn.left < 0;
   const int m = tn.hi - tn.lo;
-  long long src = -1; int ld = 0, rows = 0, cols = 0; bool ct = false;   // ct: stored conjugate-transposed
+  long long src = 0; int ld = 0, rows = 0, cols = 0; bool ct = false, have = false;   // ct: stored conjugate-transposed
   int ra0 = 0, ra1 = 0, rb0 = 0, rb1 = 0;
   if (!leaf) { ra0 = H.st[tn.left].r0; ra1 = H.st[tn.left].r1; rb0 = H.st[tn.right].r0; rb1 = H.st[tn.right].r1; }
   switch (which) {
-    case HS_HSS_D: if (leaf) { src = S.D; ld = S.ldD; rows = cols = m; } break;
-    case HS_HSS_U: if (leaf) { src = S.U; ld = S.ldU; rows = m; cols = S.r0; } break;
-    case HS_HSS_V: if (leaf) { src = S.VH; ld = S.ldVH; rows = m; cols = S.r1; ct = true; } break;
-    case HS_HSS_B12: if (!leaf) { src = S.B12; ld = S.ldB12; rows = ra0; cols = rb1; } break;
-    case HS_HSS_B21: if (!leaf) { src = S.B21; ld = S.ldB21; rows = rb0; cols = ra1; } break;
-    case HS_HSS_R: if (!leaf && tn.parent >= 0) { src = S.R; ld = S.ldR; rows = ra0 + rb0; cols = S.r0; } break;
-    case HS_HSS_W: if (!leaf && tn.parent >= 0) { src = S.WH; ld = S.ldWH; rows = ra1 + rb1; cols = S.r1; ct = true; } break;
+    case HS_HSS_D: if (leaf) { have = true; src = S.D; ld = S.ldD; rows = cols = m; } break;
+    case HS_HSS_U: if (leaf) { have = true; src = S.U; ld = S.ldU; rows = m; cols = S.r0; } break;
+    case HS_HSS_V: if (leaf) { have = true; src = S.VH; ld = S.ldVH; rows = m; cols = S.r1; ct = true; } break;
+    case HS_HSS_B12: if (!leaf) { have = true; src = S.B12; ld = S.ldB12; rows = ra0; cols = rb1; } break;
+    case HS_HSS_B21: if (!leaf) { have = true; src = S.B21; ld = S.ldB21; rows = rb0; cols = ra1; } break;
+    case HS_HSS_R: if (!leaf && tn.parent >= 0) { have = true; src = S.R; ld = S.ldR; rows = ra0 + rb0; cols = S.r0; } break;
+    case HS_HSS_W: if (!leaf && tn.parent >= 0) { have = true; src = S.WH; ld = S.ldWH; rows = ra1 + rb1; cols = S.r1; ct = true; } break;
     default: return hs_fail(HS_EARG, "hs_hss_get: unknown generator");
   }
-  if (src < 0) return hs_fail(HS_EARG, "hs_hss_get: this HSS node has no such generator");
+  if (!have) return hs_fail(HS_EARG, "hs_hss_get: this HSS node has no such generator");
+  src += H.sbase;
   dims[0] = rows; dims[1] = cols;
   if (!out || rows == 0 || cols == 0) return HS_OK;
   CUDA_OK(cudaSetDevice(f->ctx->device));

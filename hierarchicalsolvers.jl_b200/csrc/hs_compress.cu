@@ -118,7 +118,8 @@ __global__ void __launch_bounds__(256) k_id_step(const IdRun* __restrict__ runs,
   for (int w = 0; w < 8; ++w) y += s_red[w];
   const double rkk = sqrt(fmax(y, 0.0));                       // |R[k,k]|, recomputed rather than downdated
   const double r11 = k == 0 ? rkk : state[R.st + 2ll * R.ncol];
-  const double ptol = fmax(atol, rtol * r11);
+  const double tscale = R.pad ? 0.5 : 1.0;   // the right transform's sketch of the sparse couplings halves once more (:202)
+  const double ptol = fmax(tscale * atol, tscale * rtol * r11);
   if (!(rkk > ptol)) {
     if (lead) { *rank = k; atomicAdd(ints, 1); }
     return;
@@ -185,13 +186,13 @@ __global__ void __launch_bounds__(128) k_form_q(const IdRun* __restrict__ runs, 
   const IdRun R = runs[blockIdx.x];
   const LrDesc D = lr[blockIdx.x >> 1];
   const int which = blockIdx.x & 1;
-  const int r = which ? D.r2 : D.r1;
+  const int r = which ? D.r2x : D.r1x;
   const int i = blockIdx.y * 128 + threadIdx.x;
   if (i >= R.m) return;
   T* Q;
   long long ldq;
-  if (!which) { Q = pool + D.qb; ldq = D.qb_ld; }
-  else { const Front th = fronts[D.thin]; Q = pool + th.off + (long long)D.ni * th.ld; ldq = th.ld; }
+  if (!which) { ldq = D.qb_ld; Q = pool + D.qb + (long long)D.off1 * ldq; }
+  else { const Front th = fronts[D.thin]; ldq = th.ld; Q = pool + th.off + (long long)(D.ni + D.off2) * ldq; }
   const int* piv = ints + R.ip;
   const T* M = pool + R.moff;
   for (int q = 0; q < r; ++q) {
@@ -219,15 +220,40 @@ __global__ void __launch_bounds__(256) k_build_thin(const LrDesc* __restrict__ l
       T* dst = pool + th.off + (long long)j * th.ld;
       for (int i = lane; i < D.ni; i += 32) dst[i] = src[i];
       const T* rb = ws + Rb.rws + (long long)j * Rb.ldr;
-      for (int l = lane; l < D.r1; l += 32) dst[D.ni + l] = rb[l];
+      for (int l = lane; l < D.r1x; l += 32) dst[D.ni + D.off1 + l] = rb[l];
     }
     if (j < D.nb) {
       const T* rr = ws + Ri.rws + (long long)j * Ri.ldr;
-      for (int l = lane; l < D.r2; l += 32) {
+      for (int l = lane; l < D.r2x; l += 32) {
         const T v = rr[l];
-        pool[D.ri + (long long)j * D.ri_ld + l] = v;
-        pool[D.vit + (long long)l * D.qb_ld + j] = v;
+        pool[D.ri + (long long)j * D.ri_ld + D.off2 + l] = v;
+        pool[D.vit + (long long)(D.off2 + l) * D.qb_ld + j] = v;
       }
+    }
+  }
+}
+
+// HSS-children fronts (factorization.jl:184-209): the pivoted QR runs on the sparse couplings alone — the anti-diagonal
+// blocks A[bnd1,int2], A[bnd2,int1] of Abi and A[int1,bnd2], A[int2,bnd1] of Aib — copied out of the assembled front
+template <typename T>
+__global__ void __launch_bounds__(256) k_copy_anti(const LrDesc* __restrict__ lr, const Front* __restrict__ fronts, T* pool) {
+  const LrDesc D = lr[blockIdx.x];
+  if (!D.hchild) return;
+  const Front fd = fronts[D.fi];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const T* F = pool + fd.off;
+  for (int j = blockIdx.y * 8 + warp; j < D.ni + D.nb; j += gridDim.y * 8) {
+    if (j < D.ni) {   // column j of X1 (nb × ni): rows of the other child only
+      T* dst = pool + D.x1 + (long long)j * D.ldx1;
+      const T* src = F + (long long)j * fd.ld + D.ni;
+      const bool cl = j < D.ni_l;
+      for (int r = lane; r < D.nb; r += 32) dst[r] = ((r < D.nb_l) != cl) ? src[r] : hs_zero<T>();
+    } else {          // column j − ni of X2 (ni × nb)
+      const int c = j - D.ni;
+      T* dst = pool + D.x2 + (long long)c * D.ldx2;
+      const T* src = F + (long long)(D.ni + c) * fd.ld;
+      const bool cl = c < D.nb_l;
+      for (int r = lane; r < D.ni; r += 32) dst[r] = ((r < D.ni_l) != cl) ? src[r] : hs_zero<T>();
     }
   }
 }
@@ -236,16 +262,15 @@ __global__ void __launch_bounds__(256) k_build_thin(const LrDesc* __restrict__ l
 // Y = L11⁻¹·P·Qi (border columns of the factored thin front) → workspace, ld = ldy
 template <typename T>
 __global__ void __launch_bounds__(256) k_copy_y(const LrDesc* __restrict__ lr, const IdRun* __restrict__ runs,
-                                                 const Front* __restrict__ fronts, const T* pool, T* __restrict__ ws) {
+                                                 const Front* __restrict__ fronts, T* pool, T* __restrict__ ws) {
   const int c = blockIdx.x;
   const LrDesc D = lr[c];
   const Front th = fronts[D.thin];
-  const long long dst0 = runs[2 * c].rws;
-  const int ldy = (D.ni + 1) & ~1;
+  const int ldy = max(2, (D.ni + 1) & ~1);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int q = blockIdx.y * 8 + warp; q < D.r2; q += gridDim.y * 8) {
     const T* src = pool + th.off + (long long)(D.ni + q) * th.ld;
-    T* dst = ws + dst0 + (long long)q * ldy;
+    T* dst = pool + D.y + (long long)q * ldy;
     for (int i = lane; i < D.ni; i += 32) dst[i] = src[i];
   }
 }
@@ -254,7 +279,7 @@ __global__ void __launch_bounds__(256) k_copy_y(const LrDesc* __restrict__ lr, c
 // diagonal block.  One warp per column of Y.
 template <typename T>
 __global__ void __launch_bounds__(128) k_diag_apply(const LrDesc* __restrict__ lr, const IdRun* __restrict__ runs,
-                                                     const Front* __restrict__ fronts, const T* pool, T* __restrict__ ws,
+                                                     const Front* __restrict__ fronts, T* pool, T* __restrict__ ws,
                                                      int b) {
   const int c = blockIdx.x;
   const LrDesc D = lr[c];
@@ -263,11 +288,11 @@ __global__ void __launch_bounds__(128) k_diag_apply(const LrDesc* __restrict__ l
   const int db = min(64, D.ni - b0);
   const Front th = fronts[D.thin];
   const T* U = pool + th.off + (long long)b0 * th.ld + b0;
-  const int ldy = (D.ni + 1) & ~1;
+  const int ldy = max(2, (D.ni + 1) & ~1);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   __shared__ T ys[4][64];
   for (int q = blockIdx.y * 4 + warp; q < D.r2; q += gridDim.y * 4) {
-    T* y = ws + runs[2 * c].rws + (long long)q * ldy + b0;
+    T* y = pool + D.y + (long long)q * ldy + b0;
     ys[warp][lane] = lane < db ? y[lane] : hs_zero<T>();
     ys[warp][lane + 32] = lane + 32 < db ? y[lane + 32] : hs_zero<T>();
     __syncwarp();
@@ -349,11 +374,29 @@ template <typename T> void prepare_impl(hs_fac* f, CompLevel& C) {
   const T* pool = (const T*)f->pool;
   T* ws = (T*)f->d_cws;
   int max_ncol = 0, max_m = 0, max_rcap = 0;
+  bool any_hchild = false;
   for (int c = C.c0; c < C.c1; ++c) {
     const CompFront& cf = f->comp[c];
     max_ncol = std::max(max_ncol, std::max(cf.ni, cf.nb));
     max_m = std::max(max_m, std::max(cf.ni, cf.nb));
     max_rcap = std::max(max_rcap, cf.rcap);
+    any_hchild = any_hchild || cf.hchild;
+  }
+  std::vector<LrDesc> lr(nc);
+  for (int c = C.c0; c < C.c1; ++c) {   // static part; ranks and buffer offsets follow once the pivoted QRs are done
+    const CompFront& cf = f->comp[c];
+    LrDesc& d = lr[c - C.c0];
+    d = LrDesc{};
+    d.fi = cf.fi; d.thin = f->nfr + cf.fi; d.ni = cf.ni; d.nb = cf.nb; d.voff = cf.voff;
+    d.hchild = cf.hchild; d.ni_l = cf.ni_l; d.nb_l = cf.nb_l; d.x1 = cf.x1; d.x2 = cf.x2; d.ldx1 = cf.ldx1; d.ldx2 = cf.ldx2;
+  }
+  if (any_hchild) {
+    // children in HSS form: their low-rank blocks are taken over as they are, only the sparse couplings are compressed
+    CUDA_OK(cudaMemcpyAsync(f->d_lr + C.c0, lr.data(), (size_t)nc * sizeof(LrDesc), cudaMemcpyHostToDevice, st));
+    dim3 g(nc, std::min((max_m * 2 + 7) / 8, 128));
+    k_copy_anti<T><<<g, 256, 0, st>>>(f->d_lr + C.c0, f->d_fronts, (T*)f->pool);
+    CUDA_OK(cudaGetLastError());
+    ++f->stats.launches_factor;
   }
   size_t smem = (size_t)(max_m + max_rcap) * sizeof(T);
   static const bool no_stage = getenv("HS_ID_NOSTAGE") != nullptr;
@@ -383,18 +426,29 @@ template <typename T> void prepare_impl(hs_fac* f, CompLevel& C) {
   std::vector<int> ranks(nruns);
   CUDA_OK(cudaMemcpyAsync(ranks.data(), f->d_cint + 1, (size_t)nruns * sizeof(int), cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaStreamSynchronize(st));
-  // side buffer: thin fronts, Qb, Riᵀ, Ri
+  // side buffer: thin fronts, Qb, Riᵀ, Ri, Y, Z
   Level& Lt = f->flevels[C.flevel];
   long long off = 0;
-  std::vector<LrDesc> lr(nc);
   Lt.max_n = 0; Lt.max_nb = 0;
   std::vector<long long> thin_off(nc);
   for (int c = C.c0; c < C.c1; ++c) {
     CompFront& cf = f->comp[c];
-    cf.r1 = ranks[2 * (c - C.c0)];
-    cf.r2 = ranks[2 * (c - C.c0) + 1];
-    if (cf.r1 < 0 || cf.r2 < 0) throw hs_error(HS_ECUDA, "pivoted QR did not terminate");
+    LrDesc& d = lr[c - C.c0];
+    cf.rx1 = ranks[2 * (c - C.c0)];
+    cf.rx2 = ranks[2 * (c - C.c0) + 1];
+    if (cf.rx1 < 0 || cf.rx2 < 0) throw hs_error(HS_ECUDA, "pivoted QR did not terminate");
+    d.off1 = d.off2 = 0;
+    if (cf.hchild) {
+      // L = [blkdiag(Ub1, Ub2)  Q]·[blkdiag(Vi1, Vi2)  Rᴴ]ᴴ (factorization.jl:185-191), R likewise (:198-204): the ranks add up
+      const HssFront &Hl = f->hss[f->comp[cf.cl].hss], &Hr = f->hss[f->comp[cf.cr].hss];
+      d.off1 = Hl.ra1 + Hr.ra1;
+      d.off2 = Hl.rb1 + Hr.rb1;
+    }
+    d.r1x = cf.rx1; d.r2x = cf.rx2;
+    cf.r1 = d.off1 + cf.rx1;
+    cf.r2 = d.off2 + cf.rx2;
     cf.r = std::max(cf.r1, cf.r2);
+    if (cf.r > cf.vcap) throw hs_error(HS_ESIZE, "low-rank Gauss transform of a front exceeds its reserved border rows");
     f->stats.maxrank = std::max<int64_t>(f->stats.maxrank, cf.r);
     const int nt = cf.ni + cf.r, ldt = even_up(nt);
     thin_off[c - C.c0] = off; off += up32((long long)ldt * nt);
@@ -403,6 +457,8 @@ template <typename T> void prepare_impl(hs_fac* f, CompLevel& C) {
     cf.qb = off; off += up32((long long)cf.qb_ld * std::max(cf.r1, 1));
     cf.vit = off; off += up32((long long)cf.qb_ld * std::max(cf.r2, 1));
     cf.ri = off; off += up32((long long)cf.ri_ld * cf.nb);
+    cf.yoff = off; off += up32((long long)even_up(cf.ni) * std::max(cf.r2, 1));
+    cf.zoff = off; off += up32((long long)even_up(cf.nb) * std::max(cf.r2, 1));
     Lt.max_n = std::max(Lt.max_n, nt);
     Lt.max_nb = std::max(Lt.max_nb, cf.r);
   }
@@ -417,15 +473,15 @@ template <typename T> void prepare_impl(hs_fac* f, CompLevel& C) {
   const long long base = (long long)(((char*)C.side - (char*)f->pool) / (long long)sizeof(T));
   for (int c = C.c0; c < C.c1; ++c) {
     CompFront& cf = f->comp[c];
-    cf.qb += base; cf.vit += base; cf.ri += base;
+    cf.qb += base; cf.vit += base; cf.ri += base; cf.yoff += base; cf.zoff += base;
     Front& th = f->fronts[f->nfr + cf.fi];
     th.n = cf.ni + cf.r;
     th.ld = even_up(th.n);
     th.off = base + thin_off[c - C.c0];
     LrDesc& d = lr[c - C.c0];
-    d.fi = cf.fi; d.thin = f->nfr + cf.fi; d.ni = cf.ni; d.nb = cf.nb;
-    d.r1 = cf.r1; d.r2 = cf.r2; d.r = cf.r; d.pad = 0; d.voff = cf.voff;
+    d.r1 = cf.r1; d.r2 = cf.r2; d.r = cf.r;
     d.qb = cf.qb; d.vit = cf.vit; d.ri = cf.ri; d.qb_ld = cf.qb_ld; d.ri_ld = cf.ri_ld;
+    d.y = cf.yoff; d.z = cf.zoff;
   }
   // thin descriptors of a level are contiguous (the level's compressed fronts are)
   const int t0 = f->nfr + f->comp[C.c0].fi;
@@ -441,6 +497,35 @@ template <typename T> void prepare_impl(hs_fac* f, CompLevel& C) {
     CUDA_OK(cudaGetLastError());
     f->stats.launches_factor += 2;
   }
+  if (any_hchild) {
+    // the children's generator blocks (:129-137, kept in the children's HSS stores by hs_hss.cu) in front of the pivoted-QR
+    // factors:  Qb = [blkdiag(Û22·B21)ₗ,ᵣ  Qx],  Rb = [blkdiag(V̂11ᴴ)ₗ,ᵣ ; Rx],  Qi = [blkdiag(Û11·B12)ₗ,ᵣ  Qx'],  Ri = [blkdiag(V̂22ᴴ)ₗ,ᵣ ; Rx']
+    std::vector<CopyDesc> cp;
+    auto add = [&](long long src, int lds, long long dst, int ldd, int rows, int cols, int mode) {
+      if (rows <= 0 || cols <= 0) return;
+      CopyDesc d{};
+      d.src = src; d.lds = lds; d.dst = dst; d.ldd = ldd; d.rows = rows; d.cols = cols; d.gap_at = rows; d.gap_skip = 0; d.mode = mode;
+      cp.push_back(d);
+    };
+    for (int c = C.c0; c < C.c1; ++c) {
+      const CompFront& cf = f->comp[c];
+      if (!cf.hchild) continue;
+      const Front& th = f->fronts[f->nfr + cf.fi];
+      const HssFront* Hc[2] = {&f->hss[f->comp[cf.cl].hss], &f->hss[f->comp[cf.cr].hss]};
+      int io = 0, bo = 0, ao = 0, co = 0;   // offsets: int rows, bnd rows, columns of the L part, columns of the R part
+      for (int s2 = 0; s2 < 2; ++s2) {
+        const HssFront& H = *Hc[s2];
+        const int n1 = H.n1, nbc = H.m - H.n1;
+        add(H.sbase + H.tb, H.ld_tb, cf.qb + bo + (long long)ao * cf.qb_ld, cf.qb_ld, nbc, H.ra1, 0);                                   // Qb
+        add(H.sbase + H.vha, H.ld_vha, th.off + (cf.ni + ao) + (long long)io * th.ld, th.ld, H.ra1, n1, 0);                              // Rb
+        add(H.sbase + H.ta, H.ld_ta, th.off + io + (long long)(cf.ni + co) * th.ld, th.ld, n1, H.rb1, 0);                                // Qi
+        add(H.sbase + H.vhb, H.ld_vhb, cf.ri + co + (long long)bo * cf.ri_ld, cf.ri_ld, H.rb1, nbc, 0);                                  // Ri
+        add(H.sbase + H.vhb, H.ld_vhb, cf.vit + bo + (long long)co * cf.qb_ld, cf.qb_ld, H.rb1, nbc, 2);                                 // Riᵀ
+        io += n1; bo += nbc; ao += H.ra1; co += H.rb1;
+      }
+    }
+    hs_hss_copy(f, cp);
+  }
 }
 
 template <typename T> void schur_impl(hs_fac* f, CompLevel& C) {
@@ -450,7 +535,6 @@ template <typename T> void schur_impl(hs_fac* f, CompLevel& C) {
   const IdRun* d_runs = f->d_runs + 2 * C.c0;
   const LrDesc* d_lr = f->d_lr + C.c0;
   T* ws = (T*)f->d_cws;
-  const long long wbase = (long long)(((char*)f->d_cws - (char*)f->pool) / (long long)sizeof(T));
   int max_r2 = 0, max_ni = 0, max_nb = 0;
   for (int c = C.c0; c < C.c1; ++c) {
     const CompFront& cf = f->comp[c];
@@ -469,7 +553,7 @@ template <typename T> void schur_impl(hs_fac* f, CompLevel& C) {
       if (b0 >= cf.ni || cf.r2 == 0) continue;
       const Front& th = f->fronts[f->nfr + cf.fi];
       const int ldy = even_up(cf.ni);
-      const long long y = wbase + f->runs[2 * c].rws;
+      const long long y = cf.yoff;
       GemmDesc d{};
       d.a = th.off + (long long)b0 * th.ld; d.lda = th.ld;      // U[0:b0, b0:b0+db]
       d.b = y + b0; d.ldb = ldy;                                // Y[b0:b0+db, :]
@@ -488,8 +572,8 @@ template <typename T> void schur_impl(hs_fac* f, CompLevel& C) {
     const Front& fd = f->fronts[cf.fi];
     GemmDesc d{};
     d.a = fd.off + cf.ni; d.lda = fd.ld;                                    // Abi
-    d.b = wbase + f->runs[2 * c].rws; d.ldb = even_up(cf.ni);               // Y = Aii⁻¹·Qi
-    d.c = wbase + f->runs[2 * c + 1].rws; d.ldc = even_up(cf.nb);           // Z
+    d.b = cf.yoff; d.ldb = even_up(cf.ni);                                  // Y = Aii⁻¹·Qi
+    d.c = cf.zoff; d.ldc = even_up(cf.nb);                                  // Z (zeroed with the side buffer)
     d.M = cf.nb; d.N = cf.r2; d.K = cf.ni; d.sign = +1;
     gd.push_back(d);
   }
@@ -499,7 +583,7 @@ template <typename T> void schur_impl(hs_fac* f, CompLevel& C) {
     if (cf.hss >= 0) continue;   // HSS Schur complement: the operator stays matrix-free (Abb, Z, Ri), see hs_hss.cu
     const Front& fd = f->fronts[cf.fi];
     GemmDesc d{};
-    d.a = wbase + f->runs[2 * c + 1].rws; d.lda = even_up(cf.nb);           // Z
+    d.a = cf.zoff; d.lda = even_up(cf.nb);                                  // Z
     d.b = cf.ri; d.ldb = cf.ri_ld;                                          // Ri
     d.c = fd.off + (long long)cf.ni * fd.ld + cf.ni; d.ldc = fd.ld;         // S (dense slot)
     d.M = cf.nb; d.N = cf.nb; d.K = cf.r2; d.sign = -1;
@@ -516,21 +600,16 @@ template <typename T> void schur_impl(hs_fac* f, CompLevel& C) {
   const GemmDesc* dg = (const GemmDesc*)f->d_gd;
   {
     dim3 g(nc, std::min((max_r2 + 7) / 8, 64));
-    k_copy_y<T><<<g, 256, 0, st>>>(d_lr, d_runs, f->d_fronts, (const T*)f->pool, ws);
+    k_copy_y<T><<<g, 256, 0, st>>>(d_lr, d_runs, f->d_fronts, (T*)f->pool, ws);
     ++f->stats.launches_factor;
   }
   for (int b = nblk - 1; b >= 0; --b) {
     dim3 g(nc, std::min((max_r2 + 3) / 4, 64));
-    k_diag_apply<T><<<g, 128, 0, st>>>(d_lr, d_runs, f->d_fronts, (const T*)f->pool, ws, b);
+    k_diag_apply<T><<<g, 128, 0, st>>>(d_lr, d_runs, f->d_fronts, (T*)f->pool, ws, b);
     ++f->stats.launches_factor;
     if (b >= 1) gen_gemm<T>(f, dg + g0[b], gcount[b], gmaxM[b], max_r2);
   }
   CUDA_OK(cudaGetLastError());
-  // Z = 0, then Z += Abi·Y
-  for (int c = C.c0; c < C.c1; ++c) {
-    const CompFront& cf = f->comp[c];
-    CUDA_OK(cudaMemsetAsync(ws + f->runs[2 * c + 1].rws, 0, (size_t)even_up(cf.nb) * std::max(cf.r2, 1) * sizeof(T), st));
-  }
   gen_gemm<T>(f, dg + gz, nc, max_nb, max_r2);
   gen_gemm<T>(f, dg + gs, (int)gd.size() - gs, max_nb, max_nb);
 }
@@ -595,6 +674,29 @@ void hs_comp_plan(hs_fac* f) {
       }
     }
     max_ws = std::max(max_ws, ws); max_st = std::max(max_st, stt); max_int = std::max(max_int, ip);
+    // HSS-children fronts: the pivoted QRs run on copies of the sparse coupling blocks alone (factorization.jl:186-190,199-203)
+    long long xo = 0;
+    for (int c = C.c0; c < C.c1; ++c) {
+      CompFront& cf = f->comp[c];
+      if (!cf.hchild) continue;
+      cf.ldx1 = even_up(cf.nb); cf.x1 = xo; xo += up32((long long)cf.ldx1 * cf.ni);
+      cf.ldx2 = even_up(cf.ni); cf.x2 = xo; xo += up32((long long)cf.ldx2 * cf.nb);
+    }
+    if (xo > 0) {
+      C.xws_bytes = (size_t)xo * f->esz;
+      CUDA_OK(cudaMalloc(&C.xws, C.xws_bytes));
+      const long long xb = (long long)(((char*)C.xws - (char*)f->pool) / (long long)f->esz);
+      for (int c = C.c0; c < C.c1; ++c) {
+        CompFront& cf = f->comp[c];
+        if (!cf.hchild) continue;
+        cf.x1 += xb; cf.x2 += xb;
+        IdRun& Ra = f->runs[2 * c];
+        IdRun& Rb = f->runs[2 * c + 1];
+        Ra.moff = cf.x1; Ra.ld = cf.ldx1;
+        Rb.moff = cf.x2; Rb.ld = cf.ldx2;
+        Rb.pad = 1;   // pqrfact(…; atol = 0.5·atol, rtol = 0.5·rtol) on top of the halved tolerances (:202)
+      }
+    }
   }
   CUDA_OK(cudaMalloc(&f->d_cws, (size_t)std::max<long long>(max_ws, 32) * f->esz));
   CUDA_OK(cudaMalloc((void**)&f->d_cstate, (size_t)std::max<long long>(max_st, 1) * sizeof(double)));

@@ -80,7 +80,10 @@ struct Level {
 struct CompFront {
   int fi = 0;        // dense front id; the thin descriptor is fronts[nfr + fi]
   int ni = 0, nb = 0;
-  int rcap = 0;      // min(ni, nb)
+  int rcap = 0;      // min(ni, nb): largest rank a pivoted QR of Abi / Aib can reveal
+  int vcap = 0;      // virtual slots reserved for the thin front's border rows: rcap, or ni + nb for a front whose L, R start
+                     // from its HSS children's generators (their ranks add up without recompression, factorization.jl:184-209)
+  long long yoff = 0, zoff = 0;   // Y = Aii⁻¹·Qi (ni×r2) and Z = Abi·Y (nb×r2) in the level's side buffer, offsets from pool
   int r1 = 0, r2 = 0, r = 0;
   long long voff = 0;                   // first virtual slot (x index n + voff)
   long long qb = 0, vit = 0, ri = 0;    // element offsets from `pool` of Qb (nb×r1), Riᵀ (nb×r2), Ri (r2×nb)
@@ -88,6 +91,10 @@ struct CompFront {
   int hss = -1;      // index into hs_fac::hss when this front's Schur complement is stored as an HSS matrix
   int rx1 = 0, rx2 = 0;  // HSS-children Gauss transforms: ranks of the sketched sparse couplings appended to L / R
   int hchild = 0;    // 1: both children are HSS with the split at their int/bnd boundary → generator-concatenating transforms
+  int cl = -1, cr = -1;           // hchild: indices of the two children in hs_fac::comp
+  int ni_l = 0, nb_l = 0;         // rows of int / bnd that come from the left child
+  long long x1 = 0, x2 = 0;       // hchild: anti-diagonal copies of Abi (nb×ni) / Aib (ni×nb) in CompLevel::xws, offsets from pool
+  int ldx1 = 0, ldx2 = 0;
 };
 struct IdRun {       // one truncated column-pivoted QR (pivoted Cholesky of the Gram matrix), device + host
   long long moff;    // pool offset of M(0,0);  M is m × ncol with leading dimension ld
@@ -106,6 +113,19 @@ struct LrDesc {      // device image of one compressed front once its ranks are 
   long long voff;
   long long qb, vit, ri;
   int qb_ld, ri_ld;
+  // HSS-children fronts: the first off1 (off2) columns of Qb (Qi) / rows of Rb (Ri) come from the children's generators,
+  // the pivoted QR of the sparse couplings contributes r1x (r2x) more; dense-children fronts: off = 0, r?x = r?
+  int off1, off2, r1x, r2x;
+  long long y, z;      // Y = Aii⁻¹·Qi, Z = Abi·Y
+  long long x1, x2;    // copies of the anti-diagonal (sparse coupling) blocks of Abi / Aib the pivoted QR runs on
+  int ldx1, ldx2, hchild, ni_l, nb_l, pad2;
+};
+struct CopyDesc {      // one block of a batched copy (hs_hss.cu: k_copy_desc)
+  long long src, dst;
+  int lds, ldd, rows, cols;
+  int gap_at, gap_skip;   // logical source row i ≥ gap_at lives at physical row i + gap_skip
+  int mode;               // 0: dst[i,j] = src[i,j]   1: dst[j,i] = conj(src[i,j])   2: dst[j,i] = src[i,j]
+  int pad;
 };
 struct CompLevel {
   int li = 0;             // assembly level
@@ -125,7 +145,7 @@ struct HssTreeNode {       // cluster-tree node of one front, numbered in pre-or
   int left = -1, right = -1, parent = -1;
   int height = 0, isright = 0;
 };
-struct HssStored {         // generators of one HSS node inside the level's store; offsets are element offsets from `pool`
+struct HssStored {         // generators of one HSS node; element offsets from the start of the level's store (add HssFront::sbase)
   int r0 = 0, r1 = 0;      // rank of the row basis (U / [R1;R2]) and of the column basis (V / [W1;W2])
   long long D = -1, U = -1, VH = -1;   // leaf: D m×m, U m×r0, Vᴴ r1×m
   long long R = -1, WH = -1;           // non-root branch: R (r0a+r0b)×r0, Wᴴ r1×(r1a+r1b)
@@ -142,7 +162,8 @@ struct HssFront {
   int k = 0, rounds = 0;   // sample count of the last round, adaptive rounds taken
   bool done = false;
   int hssrank = 0;
-  // what the parent's Gauss transforms take from this HSS matrix (:129-137), element offsets from `pool` into the store:
+  long long sbase = 0;     // start of the level's store as an element offset from `pool` (may be negative)
+  // what the parent's Gauss transforms take from this HSS matrix (:129-137), element offsets into the store (add sbase):
   // ta = Û(A11)·B12 (n1×rb1), tb = Û(A22)·B21 ((m−n1)×ra1), vha = V̂(A11)ᴴ (ra1×n1), vhb = V̂(A22)ᴴ (rb1×(m−n1))
   long long ta = -1, tb = -1, vha = -1, vhb = -1;
   int ld_ta = 0, ld_tb = 0, ld_vha = 0, ld_vhb = 0;
@@ -253,4 +274,5 @@ void hs_gen_gemm(hs_fac* f, const GemmDesc* d_items, int nitems, int maxM, int m
 void hs_hss_setup();
 void hs_hss_plan(hs_fac* f);                         // cluster trees of the compressed fronts, perm tables, sketch matrices
 void hs_hss_build(hs_fac* f, CompLevel& C);          // randomized adaptive HSS construction + expansion into the dense slots
-void hs_hss_dense(hs_fac* f, int hi, void* out_host);  // dense S[perm,perm] a stored HSS matrix represents (m×m, column-major)
+void hs_hss_dense(hs_fac* f, int hi, void* out_host);
+void hs_hss_copy(hs_fac* f, const std::vector<CopyDesc>& blocks);   // batched block copies on the context's stream (synchronous)  // dense S[perm,perm] a stored HSS matrix represents (m×m, column-major)

@@ -87,13 +87,6 @@ struct HNode {
   long long ycat[2], xcat[2], wq[2], e[2], ec[2];
   long long m0, mt, mc, m1, m1t, m1c;
 };
-struct CopyDesc {
-  long long src, dst;
-  int lds, ldd, rows, cols;
-  int gap_at, gap_skip;   // logical source row i ≥ gap_at lives at physical row i + gap_skip
-  int mode;               // 0: dst[i,j] = src[i,j]   1: dst[j,i] = conj(src[i,j])
-  int pad;
-};
 
 // ---- counter-based Gaussian generator (used when the caller supplies no sketch matrices) -----------------------------
 __device__ __forceinline__ unsigned long long mix64(unsigned long long z) {  // splitmix64 finaliser
@@ -400,7 +393,7 @@ __global__ void __launch_bounds__(256) k_copy_desc(const CopyDesc* __restrict__ 
     const int si = i < d.gap_at ? i : i + d.gap_skip;
     const T v = src[(long long)j * d.lds + si];
     if (d.mode == 0) dst[(long long)j * d.ldd + i] = v;
-    else dst[(long long)i * d.ldd + j] = hconj(v);
+    else dst[(long long)i * d.ldd + j] = d.mode == 1 ? hconj(v) : v;
   }
 }
 // slot[perm[i], perm[j]] = P[i, j]: the dense matrix the HSS form represents goes back into the front's S block
@@ -487,7 +480,7 @@ template <typename T> Round* make_round(hs_fac* f, const std::vector<int>& act) 
     F.ldf = fd.ld; F.ldz = even_up(cf.nb); F.ldri = cf.ri_ld;
     F.nbld = even_up(cf.nb); F.kld = even_up(H.k); F.r2ld = even_up(std::max(cf.r2, 1));
     F.abb = fd.off + (long long)cf.ni * fd.ld + cf.ni;
-    F.z = rel<T>(f, f->d_cws) + f->runs[2 * H.comp + 1].rws;
+    F.z = cf.zoff;
     F.ri = cf.ri;
     F.omz = B.take((long long)F.nbld * F.k); F.psh = B.take((long long)F.kld * F.nb);
     F.yu = B.take((long long)F.nbld * F.k);  F.cp = B.take((long long)F.kld * F.nb);
@@ -681,39 +674,43 @@ template <typename T> void expand(hs_fac* f, const std::vector<int>& hids, bool 
   if (hids.empty()) return;
   cudaStream_t st = f->ctx->stream;
   Bump B;
-  struct Asm { long long U = -1, VH = -1; int ldU = 0, ldVH = 0; };
+  // assembled (nested) bases of every node: Û (m×r0) and V̂ᴴ (r1×m); `wsU` / `wsV`: offset is into the workspace (not yet relocated)
+  struct Asm { long long U = 0, VH = 0; int ldU = 0, ldVH = 0; bool wsU = false, wsV = false, have = false; };
+  struct TT { long long a = 0, b = 0; int lda = 0, ldb = 0; bool ws = false; };   // Ta = Û_a·B12, Tb = Û_b·B21 of a branch
   std::vector<std::vector<Asm>> as(hids.size());
-  std::vector<long long> Poff(hids.size()), Ta(hids.size()), Tb(hids.size());
-  std::vector<std::vector<long long>> tA(hids.size()), tB(hids.size());
-  int max_height = 0, max_m = 0, max_r = 0;
+  std::vector<std::vector<TT>> tt(hids.size());
+  std::vector<long long> Poff(hids.size());
+  int max_height = 0, max_m = 0;
   for (size_t q = 0; q < hids.size(); ++q) {
     const HssFront& H = f->hss[hids[q]];
     const int nn = (int)H.tree.size();
-    as[q].resize(nn); tA[q].assign(nn, -1); tB[q].assign(nn, -1);
+    as[q].resize(nn); tt[q].resize(nn);
     Poff[q] = B.take((long long)even_up(H.m) * H.m);
     max_m = std::max(max_m, H.m);
     for (int t = 0; t < nn; ++t) {
       const HssTreeNode& tn = H.tree[t];
       const HssStored& S = H.st[t];
       max_height = std::max(max_height, tn.height);
-      max_r = std::max(max_r, std::max(S.r0, S.r1));
       const int m = tn.hi - tn.lo;
-      if (tn.left < 0) { as[q][t].U = S.U; as[q][t].ldU = S.ldU; as[q][t].VH = S.VH; as[q][t].ldVH = S.ldVH; }
-      else if (tn.parent >= 0) {
-        as[q][t].ldU = even_up(m); as[q][t].ldVH = even_up(std::max(S.r1, 1));
-        as[q][t].U = B.take((long long)as[q][t].ldU * std::max(S.r0, 1));
+      Asm& A = as[q][t];
+      if (tn.left < 0) {
+        A.U = H.sbase + S.U; A.ldU = S.ldU; A.VH = H.sbase + S.VH; A.ldVH = S.ldVH; A.have = true;
+      } else if (tn.parent >= 0) {
+        A.have = true;
+        A.ldU = even_up(m); A.U = B.take((long long)A.ldU * std::max(S.r0, 1)); A.wsU = true;
         // the assembled column bases of the two depth-1 nodes are what the parent's Gauss transforms read: they live in the store
-        if (to_slot && tn.parent == 0) { as[q][t].VH = tn.isright ? H.vhb : H.vha; as[q][t].ldVH = tn.isright ? H.ld_vhb : H.ld_vha; }
-        else as[q][t].VH = -2;   // workspace, relocated below
-        if (as[q][t].VH == -2) as[q][t].VH = -(B.take((long long)as[q][t].ldVH * m) + 3);
+        if (to_slot && tn.parent == 0) { A.VH = H.sbase + (tn.isright ? H.vhb : H.vha); A.ldVH = tn.isright ? H.ld_vhb : H.ld_vha; }
+        else { A.ldVH = even_up(std::max(S.r1, 1)); A.VH = B.take((long long)A.ldVH * m); A.wsV = true; }
       }
       if (tn.left >= 0) {
         const HssTreeNode &a = H.tree[tn.left], &b = H.tree[tn.right];
         const HssStored &Sa = H.st[tn.left], &Sb = H.st[tn.right];
-        if (to_slot && t == 0) { tA[q][t] = -1; tB[q][t] = -1; }   // root: Ta, Tb live in the store (H.ta, H.tb)
+        TT& X = tt[q][t];
+        if (to_slot && t == 0) { X.a = H.sbase + H.ta; X.lda = H.ld_ta; X.b = H.sbase + H.tb; X.ldb = H.ld_tb; }   // kept for the parent front
         else {
-          tA[q][t] = B.take((long long)even_up(a.hi - a.lo) * std::max(Sb.r1, 1));
-          tB[q][t] = B.take((long long)even_up(b.hi - b.lo) * std::max(Sa.r1, 1));
+          X.ws = true;
+          X.lda = even_up(a.hi - a.lo); X.a = B.take((long long)X.lda * std::max(Sb.r1, 1));
+          X.ldb = even_up(b.hi - b.lo); X.b = B.take((long long)X.ldb * std::max(Sa.r1, 1));
         }
       }
     }
@@ -739,18 +736,18 @@ template <typename T> void expand(hs_fac* f, const std::vector<int>& hids, bool 
     const long long P = base + Poff[q];
     const int ldP = even_up(H.m);
     for (int t = 0; t < nn; ++t) {   // relocate workspace offsets
-      if (as[q][t].U >= 0 && H.tree[t].left >= 0) as[q][t].U += base;
-      if (as[q][t].VH <= -3) as[q][t].VH = base + (-as[q][t].VH - 3);
-      if (tA[q][t] >= 0) { tA[q][t] += base; tB[q][t] += base; }
+      Asm& A = as[q][t];
+      if (A.wsU) A.U += base;
+      if (A.wsV) A.VH += base;
+      if (tt[q][t].ws) { tt[q][t].a += base; tt[q][t].b += base; }
     }
-    if (to_slot && !H.tree.empty()) { tA[q][0] = H.ta; tB[q][0] = H.tb; }
     for (int t = 0; t < nn; ++t) {
       const HssTreeNode& tn = H.tree[t];
       const HssStored& S = H.st[t];
       const int m = tn.hi - tn.lo;
       if (tn.left < 0) {
         CopyDesc c{};
-        c.src = S.D; c.lds = S.ldD; c.dst = P + (long long)tn.lo * ldP + tn.lo; c.ldd = ldP; c.rows = m; c.cols = m; c.gap_at = m; c.mode = 0;
+        c.src = H.sbase + S.D; c.lds = S.ldD; c.dst = P + (long long)tn.lo * ldP + tn.lo; c.ldd = ldP; c.rows = m; c.cols = m; c.gap_at = m; c.mode = 0;
         cds.push_back(c);
         continue;
       }
@@ -761,17 +758,18 @@ template <typename T> void expand(hs_fac* f, const std::vector<int>& hids, bool 
       if (tn.parent >= 0) {
         // Û = [Û_a·R1; Û_b·R2],  V̂ᴴ = [W1ᴴ·V̂ᴴ_a, W2ᴴ·V̂ᴴ_b]
         const Asm& At = as[q][t];
-        item(gh[tn.height], Aa.U, Aa.ldU, S.R, S.ldR, At.U, At.ldU, ma, S.r0, Sa.r0);
-        item(gh[tn.height], Ab.U, Ab.ldU, S.R + Sa.r0, S.ldR, At.U + ma, At.ldU, mb, S.r0, Sb.r0);
-        item(gh[tn.height], S.WH, S.ldWH, Aa.VH, Aa.ldVH, At.VH, At.ldVH, S.r1, ma, Sa.r1);
-        item(gh[tn.height], S.WH + (long long)Sa.r1 * S.ldWH, S.ldWH, Ab.VH, Ab.ldVH, At.VH + (long long)ma * At.ldVH, At.ldVH, S.r1, mb, Sb.r1);
+        const long long R = H.sbase + S.R, WH = H.sbase + S.WH;
+        item(gh[tn.height], Aa.U, Aa.ldU, R, S.ldR, At.U, At.ldU, ma, S.r0, Sa.r0);
+        item(gh[tn.height], Ab.U, Ab.ldU, R + Sa.r0, S.ldR, At.U + ma, At.ldU, mb, S.r0, Sb.r0);
+        item(gh[tn.height], WH, S.ldWH, Aa.VH, Aa.ldVH, At.VH, At.ldVH, S.r1, ma, Sa.r1);
+        item(gh[tn.height], WH + (long long)Sa.r1 * S.ldWH, S.ldWH, Ab.VH, Ab.ldVH, At.VH + (long long)ma * At.ldVH, At.ldVH, S.r1, mb, Sb.r1);
       }
       // off-diagonal blocks  P[Ia, Jb] = (Û_a·B12)·V̂ᴴ_b,  P[Ib, Ja] = (Û_b·B21)·V̂ᴴ_a
-      const int ldta = (to_slot && t == 0) ? H.ld_ta : even_up(ma), ldtb = (to_slot && t == 0) ? H.ld_tb : even_up(mb);
-      item(gT, Aa.U, Aa.ldU, S.B12, S.ldB12, tA[q][t], ldta, ma, Sb.r1, Sa.r0);
-      item(gT, Ab.U, Ab.ldU, S.B21, S.ldB21, tB[q][t], ldtb, mb, Sa.r1, Sb.r0);
-      item(gP, tA[q][t], ldta, Ab.VH, Ab.ldVH, P + (long long)b.lo * ldP + a.lo, ldP, ma, mb, Sb.r1);
-      item(gP, tB[q][t], ldtb, Aa.VH, Aa.ldVH, P + (long long)a.lo * ldP + b.lo, ldP, mb, ma, Sa.r1);
+      const TT& X = tt[q][t];
+      item(gT, Aa.U, Aa.ldU, H.sbase + S.B12, S.ldB12, X.a, X.lda, ma, Sb.r1, Sa.r0);
+      item(gT, Ab.U, Ab.ldU, H.sbase + S.B21, S.ldB21, X.b, X.ldb, mb, Sa.r1, Sb.r0);
+      item(gP, X.a, X.lda, Ab.VH, Ab.ldVH, P + (long long)b.lo * ldP + a.lo, ldP, ma, mb, Sb.r1);
+      item(gP, X.b, X.ldb, Aa.VH, Aa.ldVH, P + (long long)a.lo * ldP + b.lo, ldP, mb, ma, Sa.r1);
     }
     if (to_slot) {
       const CompFront& cf = f->comp[H.comp];
@@ -921,30 +919,24 @@ template <typename T> void build_impl(hs_fac* f, CompLevel& C) {
     const Round& R = *rounds[where[hi].first];
     const int q = where[hi].second;
     const int nn = (int)H.tree.size();
-    auto fix = [&](long long& o) { if (o >= 0) o += sbase; };
-    // leaves' VH may have been aliased into vha / vhb before relocation: relocate every stored offset exactly once
-    const bool alias_a = H.tree[H.tree[0].left].left < 0, alias_b = H.tree[H.tree[0].right].left < 0;
-    for (int t = 0; t < nn; ++t) { HssStored& S = H.st[t]; fix(S.D); fix(S.U); fix(S.VH); fix(S.R); fix(S.WH); fix(S.B12); fix(S.B21); }
-    fix(H.ta); fix(H.tb);
-    if (alias_a) H.vha = H.st[H.tree[0].left].VH; else fix(H.vha);
-    if (alias_b) H.vhb = H.st[H.tree[0].right].VH; else fix(H.vhb);
+    H.sbase = sbase;
     for (int t = 0; t < nn; ++t) {
       const HssTreeNode& tn = H.tree[t];
       const HssStored& S = H.st[t];
       const HNode& N = R.nd[R.nbase[q] + t];
       const int m = tn.hi - tn.lo;
       if (tn.left < 0) {
-        cpy(N.m0, N.ldm0, S.D, S.ldD, m, m, m, 0, 0);
-        cpy(N.e[0], N.lde, S.U, S.ldU, m, S.r0, m, 0, 0);
-        cpy(N.e[1], N.lde, S.VH, S.ldVH, m, S.r1, m, 0, 1);
+        cpy(N.m0, N.ldm0, sbase + S.D, S.ldD, m, m, m, 0, 0);
+        cpy(N.e[0], N.lde, sbase + S.U, S.ldU, m, S.r0, m, 0, 0);
+        cpy(N.e[1], N.lde, sbase + S.VH, S.ldVH, m, S.r1, m, 0, 1);
       } else {
         const HssStored &Sa = H.st[tn.left], &Sb = H.st[tn.right];
         if (tn.parent >= 0) {
-          cpy(N.e[0], N.lde, S.R, S.ldR, Sa.r0 + Sb.r0, S.r0, Sa.r0, N.capl - Sa.r0, 0);
-          cpy(N.e[1], N.lde, S.WH, S.ldWH, Sa.r1 + Sb.r1, S.r1, Sa.r1, N.capl - Sa.r1, 1);
+          cpy(N.e[0], N.lde, sbase + S.R, S.ldR, Sa.r0 + Sb.r0, S.r0, Sa.r0, N.capl - Sa.r0, 0);
+          cpy(N.e[1], N.lde, sbase + S.WH, S.ldWH, Sa.r1 + Sb.r1, S.r1, Sa.r1, N.capl - Sa.r1, 1);
         }
-        cpy(N.m0, N.ldm0, S.B12, S.ldB12, Sa.r0, Sb.r1, Sa.r0, 0, 0);
-        cpy(N.m1, N.ldm1, S.B21, S.ldB21, Sb.r0, Sa.r1, Sb.r0, 0, 0);
+        cpy(N.m0, N.ldm0, sbase + S.B12, S.ldB12, Sa.r0, Sb.r1, Sa.r0, 0, 0);
+        cpy(N.m1, N.ldm1, sbase + S.B21, S.ldB21, Sb.r0, Sa.r1, Sb.r0, 0, 0);
       }
     }
     f->stats.hss_nodes += nn;
@@ -1036,6 +1028,18 @@ void hs_hss_plan(hs_fac* f) {
   // the caller's sketch buffers are not referenced after this call
   f->opts.sketch_psi = nullptr;
   if (f->opts.sketch_omega) f->opts.sketch_omega = (const void*)f->d_sk;   // keeps "host-supplied" distinguishable from "generate"
+}
+
+void hs_hss_copy(hs_fac* f, const std::vector<CopyDesc>& blocks) {
+  if (blocks.empty()) return;
+  cudaStream_t st = f->ctx->stream;
+  DevVec<CopyDesc> dc;
+  dc.upload(blocks, st);
+  if (f->dtype == HS_F64) k_copy_desc<double><<<dim3((unsigned)blocks.size(), 4), 256, 0, st>>>(dc.d, (double*)f->pool);
+  else k_copy_desc<cplx><<<dim3((unsigned)blocks.size(), 4), 256, 0, st>>>(dc.d, (cplx*)f->pool);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaStreamSynchronize(st));
+  ++f->stats.launches_factor;
 }
 
 void hs_hss_build(hs_fac* f, CompLevel& C) {
