@@ -189,8 +189,22 @@ template <typename T> static void factor_level(hs_fac* f, const Level& L) {
     solve_prep(f, L);
     return;
   }
-  const int W = hs_panel_width(f, L.max_n, L.f1 - L.f0);
-  if (W < 0) throw hs_error(HS_ESIZE, "front with " + std::to_string(L.max_n) + " rows exceeds the panel kernels");
+  // the panel cluster spans the rows pivots are taken from (the pivot block, or one half of a split pivot block)
+  int max_prow = 0;
+  bool has_split = false;
+  for (int i = L.f0; i < L.f1; ++i) {
+    const Front& fr = f->fronts[i];
+    max_prow = std::max(max_prow, fr.split > 0 ? std::max(fr.split, fr.ni - fr.split) : fr.ni);
+    has_split = has_split || fr.split > 0;
+  }
+  const int W = hs_panel_width(f, max_prow, L.f1 - L.f0);
+  if (W < 0) throw hs_error(HS_ESIZE, "pivot block with " + std::to_string(max_prow) + " rows exceeds the panel kernels");
+  auto pivot_rows = [&](int j0, int nact) {   // tallest panel among the active fronts
+    if (!has_split) return L.max_ni - j0;
+    int m = 0;
+    for (int i = L.f0; i < L.f0 + nact; ++i) m = std::max(m, hs_plim(f->fronts[i], j0) - j0);
+    return m;
+  };
   const int NB = std::max(W, f->ctx->outer_block / W * W);
   constexpr int smem_gemm = gemm_smem_bytes<T>();
   using Cfg = GemmCfg<T>;
@@ -220,12 +234,15 @@ template <typename T> static void factor_level(hs_fac* f, const Level& L) {
       const int m = L.max_n - j0;
       {
         PhaseTimer t(f, &f->stats.ms_panel);
-        hs_panel_launch(f, W, L.f0, nact, j0, m, s_);
+        hs_panel_launch(f, W, L.f0, nact, j0, pivot_rows(j0, nact), s_);
         ++f->stats.panel_launches;
         ++f->stats.launches_factor;
       }
       {
         PhaseTimer t(f, &f->stats.ms_trsm);
+        // rows below the pivot rows (boundary rows, second half of a split pivot block): L21 = A_bi·U_pp⁻¹, one thread per row
+        const int below = has_split ? L.max_n - j0 - 1 : L.max_nb;
+        if (below > 0) { hs_trsm_rows(f, W, L.f0, nact, j0, below, s_); ++f->stats.launches_factor; }
         trsm_dispatch<T>(f, W, L.f0, nact, J0, j0, NB, 0, JE - J0, s_);
       }
       gemm(nact, J0, j0, 0, m, JE - j0, s_);
@@ -325,12 +342,15 @@ template <typename T> static void numeric(hs_fac* f) {
       if (li > 0 && !f->levels[li - 1].pseudo) {
         const Level& Lc = f->levels[li - 1];
         if (Lc.max_nb > 0) {
-          constexpr int CB = 8;
-          // one CTA covers ~4096 elements of a child's Schur block: whole small blocks, column groups of large ones
-          const int cols_per_cta = std::max(1, 4096 / Lc.max_nb);
+          // a CTA covers ~8192 elements of a child's Schur block: whole small blocks, column groups of large ones;
+          // lanes per column sized so that one or two passes cover the rows of the level's fronts
+          constexpr int RPL = sizeof(T) == 8 ? 2 : 1;
+          const int cols_per_cta = std::max(32, (8192 / Lc.max_nb + 31) / 32 * 32);
           dim3 g2(Lc.f1 - Lc.f0, (Lc.max_nb + cols_per_cta - 1) / cols_per_cta);
           PhaseTimer t2(f, &s.ms_extend_add);
-          k_extend_add<T, CB><<<g2, 256, 0, st>>>(f->d_fronts, pool, f->d_cmap, Lc.f0, cols_per_cta);
+          if (Lc.max_nb <= 8 * RPL * 4) k_extend_add<T, 2, 8><<<g2, 256, 0, st>>>(f->d_fronts, pool, f->d_cmap, Lc.f0, cols_per_cta);
+          else if (Lc.max_nb <= 16 * RPL * 4) k_extend_add<T, 2, 16><<<g2, 256, 0, st>>>(f->d_fronts, pool, f->d_cmap, Lc.f0, cols_per_cta);
+          else k_extend_add<T, 4, 32><<<g2, 256, 0, st>>>(f->d_fronts, pool, f->d_cmap, Lc.f0, cols_per_cta);
           s.launches_factor += 1;
         }
       }
@@ -578,6 +598,9 @@ static void build_plan(hs_fac* f, const hs_tree* t) {
   f->node2front.assign(nn, -1);
   for (int i = 0; i < (int)nn; ++i) f->node2front[order[i]] = i;
   f->root_front = f->node2front[root];
+  // rows one panel cluster covers with its narrowest register tile (hs_panel.cuh: 256·R rows per CTA, R ≤ 8 (f64) / 4 (c64))
+  int prow_cap = 256 * (f->dtype == HS_F64 ? 8 : 4) * std::max(1, f->ctx->max_cluster);
+  if (getenv("HS_PROW_CAP")) prow_cap = std::min(prow_cap, std::max(64, atoi(getenv("HS_PROW_CAP"))));  // tests: force the split path
   IntBuf &gidx = f->ctx->sc_gidx, &cmap = f->ctx->sc_cmap;  // grow-only scratch: no page faults after the first call
   long long poff = 0, ioff = 0;
   const long long align = 32;
@@ -603,6 +626,18 @@ static void build_plan(hs_fac* f, const hs_tree* t) {
     fr.flags = 0;
     if (f->left[k] < 0) { fr.ni_l = -1; fr.nb_l = 0; }
     else { fr.ni_l = (int)nloc(f->iloc_ptr, f->left[k]); fr.nb_l = (int)nloc(f->bloc_ptr, f->left[k]); }
+    fr.split = 0;
+    if (fr.ni > prow_cap) {
+      // pivot block taller than one panel cluster: eliminate it as the reference's blockfactor does (blockmatrix.jl:115-120),
+      // [A11 A12; A21 A22] with pivoting inside A11 and inside S22 — split at the children's boundary, moved down to a
+      // multiple of the outer block so that no panel straddles it
+      const int NB0 = std::max(64, f->ctx->outer_block / 64 * 64);
+      int sp = fr.ni_l > 0 ? fr.ni_l / NB0 * NB0 : 0;
+      if (sp <= 0 || sp > prow_cap || fr.ni - sp > prow_cap)
+        throw hs_error(HS_ESIZE, "pivot block with " + std::to_string(fr.ni) + " rows exceeds the panel kernels (" + std::to_string(prow_cap) +
+                                     " rows per diagonal block)");
+      fr.split = sp;
+    }
     if (f->levels.empty() || f->level[k] != f->level[order[f->levels.back().f0]]) {
       Level L; L.f0 = i; L.f1 = i; L.fm = i; L.ioff0 = ioff; L.poff0 = poff;
       f->levels.push_back(L);

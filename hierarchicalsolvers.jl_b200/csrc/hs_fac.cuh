@@ -65,6 +65,8 @@ struct Level {
   long long tpoff0 = 0, tpoff1 = 0;  // dense slots of the level's compressed fronts inside a transient arena
   bool pseudo = false;
   std::vector<int> ni_sorted;  // ni of the fronts in this level (descending)
+  int max_prow = 0;            // tallest diagonal block pivots are searched in (max ni, or max(split, ni − split) of split fronts)
+  bool has_split = false;
   int fm = 0;                  // assembly levels: fronts [fm, f1) are compressed (fm = f1: none)
   int thin = -1;               // factor/solve levels: index into hs_fac::clevels when this is a level of thin fronts
 };
@@ -244,6 +246,11 @@ int hs_panel_width_f64(const hs_fac* f, int max_n, int nfronts);
 int hs_panel_width_c64(const hs_fac* f, int max_n, int nfronts);
 void hs_panel_launch_f64(hs_fac* f, int W, int f0, int nact, int j0, int m, cudaStream_t st);
 void hs_panel_launch_c64(hs_fac* f, int W, int f0, int nact, int j0, int m, cudaStream_t st);
+void hs_trsm_rows_f64(hs_fac* f, int W, int f0, int nact, int j0, int max_rows, cudaStream_t st);
+void hs_trsm_rows_c64(hs_fac* f, int W, int f0, int nact, int j0, int max_rows, cudaStream_t st);
+inline void hs_trsm_rows(hs_fac* f, int W, int f0, int nact, int j0, int max_rows, cudaStream_t st) {
+  if (f->dtype == HS_F64) hs_trsm_rows_f64(f, W, f0, nact, j0, max_rows, st); else hs_trsm_rows_c64(f, W, f0, nact, j0, max_rows, st);
+}
 inline int hs_panel_width(const hs_fac* f, int max_n, int nfronts) {
   return f->dtype == HS_F64 ? hs_panel_width_f64(f, max_n, nfronts) : hs_panel_width_c64(f, max_n, nfronts);
 }

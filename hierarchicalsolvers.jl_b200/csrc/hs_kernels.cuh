@@ -63,7 +63,7 @@ __global__ void k_scatter_A(const Front* __restrict__ fronts, T* __restrict__ po
 // boundaries are disjoint, so nothing is accumulated — it is a collision-free permuted block copy
 // (factorization.jl:118-121 diagonal blocks; the S[perm,perm] of :41,:74 is folded into the map).
 // cmap[a] = row of the parent front that receives the child's boundary row a (-1: dropped).
-template <typename T, int CB>
+template <typename T, int CB, int LW>
 __global__ void __launch_bounds__(256) k_extend_add(const Front* __restrict__ fronts, T* __restrict__ pool,
                                                      const int* __restrict__ cmap, int c0, int cols_per_cta) {
   const int ci = c0 + blockIdx.x;
@@ -77,34 +77,50 @@ __global__ void __launch_bounds__(256) k_extend_add(const Front* __restrict__ fr
   const int* map = cmap + ch.ioff + ch.ni;
   const T* S = pool + ch.off + (long long)ch.ni * ch.ld + ch.ni;
   T* P = pool + pa.off;
-  // elements (a, b) of the child's Schur block, a fastest: consecutive threads read consecutive rows of one column;
-  // CB elements per thread are loaded before the first store (source and destination live in the same pool)
-  const int total = nb * (b1 - b0);
-  for (int e0 = threadIdx.x; e0 < total; e0 += 256 * CB) {
-    T v[CB];
-    int dst[CB];
+  // LW lanes walk the rows of one column of the child's Schur block (no per-element div/mod), so a warp covers 32/LW
+  // columns at a time (LW = 8 / 16 for the small fronts of the deep levels, 32 above).  CB row chunks are loaded before
+  // the first store (source and destination live in the same pool).  f64: two rows per lane through one 16-byte load
+  // when the column start is 16-byte aligned (ni even; the leading dimension always is even).
+  constexpr int CPW = 32 / LW;                  // columns per warp and pass
+  constexpr int RPL = sizeof(T) == 8 ? 2 : 1;   // rows per lane and chunk
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lr = lane % LW, lc = lane / LW;
+  const bool vec = RPL == 2 && ((ch.off + (long long)ch.ni * ch.ld + ch.ni) & 1) == 0;
+  for (int b = b0 + warp * CPW + lc; b < b1; b += 8 * CPW) {
+    const int pc = map[b];
+    if (pc < 0) continue;
+    const T* src = S + (long long)b * ch.ld;
+    T* dst = P + (long long)pc * pa.ld;
+    for (int a0 = 0; a0 < nb; a0 += LW * RPL * CB) {
+      T v[CB][RPL];
+      int d[CB][RPL];
 #pragma unroll
-    for (int q = 0; q < CB; ++q) {
-      const int e = e0 + q * 256;
-      dst[q] = -1;
-      v[q] = hs_zero<T>();
-      if (e < total) {
-        const int a = e % nb, b = b0 + e / nb;
-        const int pr = map[a], pc = map[b];
-        if (pr >= 0 && pc >= 0) {
-          v[q] = S[(long long)b * ch.ld + a];
-          dst[q] = 1;
-          // destination offset computed again below (keeps the register count down)
+      for (int q = 0; q < CB; ++q) {
+        const int a = a0 + (q * LW + lr) * RPL;
+        if constexpr (RPL == 2) {
+          if (vec && a + 1 < nb) {
+            const double2 t = *reinterpret_cast<const double2*>(src + a);
+            v[q][0] = t.x; v[q][1] = t.y;
+            d[q][0] = map[a]; d[q][1] = map[a + 1];
+          } else {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const bool ok = a + h < nb;
+              v[q][h] = ok ? src[a + h] : hs_zero<T>();
+              d[q][h] = ok ? map[a + h] : -1;
+            }
+          }
+        } else {
+          const bool ok = a < nb;
+          v[q][0] = ok ? src[a] : hs_zero<T>();
+          d[q][0] = ok ? map[a] : -1;
         }
       }
-    }
 #pragma unroll
-    for (int q = 0; q < CB; ++q) {
-      const int e = e0 + q * 256;
-      if (dst[q] >= 0) {
-        const int a = e % nb, b = b0 + e / nb;
-        P[(long long)map[b] * pa.ld + map[a]] = v[q];
-      }
+      for (int q = 0; q < CB; ++q)
+#pragma unroll
+        for (int h = 0; h < RPL; ++h)
+          if (d[q][h] >= 0) dst[d[q][h]] = v[q][h];
     }
   }
 }

@@ -12,7 +12,11 @@ namespace cg = cooperative_groups;
 // ------------------------------------------------------------------------------------------------
 // LU panel with partial pivoting restricted to the pivot block rows (rows < ni)
 // ------------------------------------------------------------------------------------------------
-// Panel = front rows [j0, n) × columns [j0, j0+wc).  The 256 threads of a CTA form a 32×8 grid; thread (tr, tc)
+// Panel = front rows [j0, plim) × columns [j0, j0+wc), plim = end of the diagonal block pivots are taken from (ni, or
+// the split of a pivot block eliminated as 2×2 blocks).  The rows below — the rest of the pivot block behind a split and
+// all boundary rows — take no part in the pivot search: they are X·U_pp = B triangular solves done by k_trsm_rows with
+// one thread per row, so the latency-bound cluster spans the pivot rows only (half the CTAs or less at the upper levels).
+// The 256 threads of a CTA form a 32×8 grid; thread (tr, tc)
 // keeps rows tr + 32·i (i < 8·R) and columns tc + 8·k (k < W/8) of the CTA's row block in registers, a cluster of C
 // CTAs covers 256·R·C rows.  Per pivot column:
 //   (a) the 32 threads that own the column publish it and |.| of the eligible rows to shared memory      → barrier
@@ -24,6 +28,10 @@ namespace cg = cooperative_groups;
 // Pivoting is implicit: rows stay where they are until CTA 0 moves them to their LAPACK positions at the end (the
 // interchange sequence `ipiv` is replayed from the pivot order).  Column indices are static in the unrolled outer
 // loop (k = j / 8), so the body is small and stays in the instruction cache.
+template <typename T> struct PanelW;  // widest register tile per scalar type
+template <> struct PanelW<double> { static constexpr int W0 = 64; };
+template <> struct PanelW<cplx> { static constexpr int W0 = 32; };
+
 struct PanelCand {
   double val;
   int row;
@@ -54,8 +62,9 @@ __global__ void __launch_bounds__(256, 1) k_panel(const Front* __restrict__ fron
   const int fi = f0 + (CL ? blockIdx.x / C : blockIdx.x);
   const Front fr = fronts[fi];
   if (fr.ni <= j0) return;  // uniform across the cluster
-  const int wc = min(W, fr.ni - j0);
-  const int m = fr.n - j0;
+  const int plim = hs_plim(fr, j0);
+  const int wc = min(W, plim - j0);
+  const int m = plim - j0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tr = tid % TR, tc = tid / TR;
   const int rbase = crank * ROWS;
@@ -112,7 +121,7 @@ __global__ void __launch_bounds__(256, 1) k_panel(const Front* __restrict__ fron
         for (int i = 0; i < RPT; ++i) {
           const int rl = tr + TR * i, r = rbase + rl;
           colp[rl] = a[i][kj];
-          absp[rl] = (!((done >> i) & 1ull) && r < m && j0 + r < fr.ni) ? hs_abs1(a[i][kj]) : -1.0;
+          absp[rl] = (!((done >> i) & 1ull) && r < m) ? hs_abs1(a[i][kj]) : -1.0;
         }
       }
       __syncthreads();
@@ -297,13 +306,67 @@ static void launch_panel(hs_fac* f, int f0, int nact, int j0, int C, cudaStream_
   CUDA_OK(cudaGetLastError());
 }
 
-template <typename T> struct PanelW;  // widest register tile per scalar type
-template <> struct PanelW<double> { static constexpr int W0 = 64; };
-template <> struct PanelW<cplx> { static constexpr int W0 = 32; };
-
 static int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
-// panel width used for a level whose tallest front has n rows
+// rows [plim, n) of panel [j0, j0+wc):  X·U_pp = B with U_pp the upper triangle of the factored wc×wc pivot block; one
+// thread per row, the row in registers (coalesced over consecutive rows of a column)
+template <typename T, int W>
+__global__ void __launch_bounds__(128) k_trsm_rows(const Front* __restrict__ fronts, T* __restrict__ pool, int f0, int j0) {
+  const Front fr = fronts[f0 + blockIdx.x];
+  if (fr.ni <= j0) return;
+  const int plim = hs_plim(fr, j0);
+  const int wc = min(W, plim - j0);
+  const int nrows = fr.n - plim;
+  if ((int)(blockIdx.y * blockDim.x) >= nrows) return;
+  T* F = pool + fr.off;
+  __shared__ T sU[W * W];   // sU[k·W + c] = U[k, c] for k < c, 1/U[c, c] on the diagonal
+  for (int e = threadIdx.x; e < W * W; e += blockDim.x) {
+    const int k = e / W, c = e % W;
+    T v = hs_zero<T>();
+    if (k < wc && c < wc && k <= c) {
+      v = F[(long long)(j0 + c) * fr.ld + (j0 + k)];
+      if (k == c) v = hs_recip_pivot(v);
+    }
+    sU[e] = v;
+  }
+  __syncthreads();
+  const int r = blockIdx.y * blockDim.x + threadIdx.x;
+  if (r >= nrows) return;
+  T* row = F + plim + r;
+  T x[W];
+#pragma unroll
+  for (int c = 0; c < W; ++c) x[c] = c < wc ? row[(long long)(j0 + c) * fr.ld] : hs_zero<T>();
+  // right-looking: once x[c] is final it is eliminated from all later entries — W independent FMAs per step instead of a
+  // dependent chain of c FMAs per entry
+#pragma unroll
+  for (int c = 0; c < W; ++c) {
+    if (c < wc) {
+      const T xc = hs_mul(x[c], sU[c * W + c]);
+      x[c] = xc;
+#pragma unroll
+      for (int j = c + 1; j < W; ++j) x[j] = hs_fnma(x[j], xc, sU[c * W + j]);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < W; ++c)
+    if (c < wc) row[(long long)(j0 + c) * fr.ld] = x[c];
+}
+
+template <typename T, int W> static void launch_trsm_rows(hs_fac* f, int f0, int nact, int j0, int max_rows, cudaStream_t st) {
+  if (max_rows <= 0) return;
+  dim3 grid(nact, (max_rows + 127) / 128);
+  k_trsm_rows<T, W><<<grid, 128, 0, st>>>(f->d_fronts, (T*)f->pool, f0, j0);
+  CUDA_OK(cudaGetLastError());
+}
+template <typename T> static void trsm_rows_dispatch(hs_fac* f, int W, int f0, int nact, int j0, int max_rows, cudaStream_t st) {
+  constexpr int W0 = PanelW<T>::W0;
+  if (W == W0) launch_trsm_rows<T, W0>(f, f0, nact, j0, max_rows, st);
+  else if (W == W0 / 2) launch_trsm_rows<T, W0 / 2>(f, f0, nact, j0, max_rows, st);
+  else if (W == W0 / 4) launch_trsm_rows<T, W0 / 4>(f, f0, nact, j0, max_rows, st);
+  else if constexpr (W0 / 8 >= 8) launch_trsm_rows<T, W0 / 8>(f, f0, nact, j0, max_rows, st);
+}
+
+// panel width used for a level whose tallest panel has max_n PIVOT rows
 template <typename T> static int choose_width(const hs_fac* f, int max_n, int nfronts) {
   const int W0 = PanelW<T>::W0;
   const int maxC = f->ctx->max_cluster;

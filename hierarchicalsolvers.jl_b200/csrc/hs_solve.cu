@@ -10,8 +10,8 @@
 //            for b = B-1..1:  t[0:b0] -= F[0:b0, b]·t_b ;  t_{b-1} = U_{b-1,b-1}⁻¹ t_{b-1}
 //
 // All of it streams each factor entry exactly once per right-hand side: the roofline is HBM bandwidth
-// (esz·Σ(ni² + 2·ni·nb) bytes per RHS).  Fronts with ni ≤ DB run in one fused CTA per front; larger fronts run one
-// launch per block step with one CTA per 32-row tile.
+// (esz·Σ(ni² + 2·ni·nb) bytes per RHS).  Fronts with ni ≤ DB run in one fused CTA per front; larger fronts run their
+// triangular part in super-block steps (k_sv_tri_*) and their rectangular part as one streamed mat-vec (k_gemv_rect).
 #include <cuda_runtime.h>
 
 #include <cooperative_groups.h>
@@ -195,161 +195,206 @@ __global__ void __launch_bounds__(NTH) k_sv_small_bwd(const Front* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------
-// large fronts (ni > DB): one thread-block CLUSTER per (front, rhs) runs the whole sweep; block steps are separated
-// by cluster barriers instead of kernel launches.  A warp owns 32-row tiles (lane = row) and streams its rows of the
-// current block column; global warp 0 additionally owns the next diagonal block and applies its inverse, so that the
-// next step starts from a final v_b.  The working vector lives in `work` (global, read/written with .cg accesses).
+// large fronts (ni > DB): triangular part of the sweeps in SUPER-BLOCKS of SB = 256 pivot rows, one launch per
+// super-block step over all large fronts of the level.  In a step
+//   * CTA 0 of a front (the "diagonal CTA", 1024 threads) finishes the rows of the current super-block: it subtracts the
+//     contribution of the previous super-block's 256 solution entries (a 256×256 mat-vec split over 4 thread groups) and
+//     solves the 256×256 triangular system with the inverted 64×64 diagonal blocks (4 dependent sub-steps);
+//   * the other CTAs stream the same 256 columns over the remaining rows of the pivot block, 256 rows each.
+// The chain of dependent steps per front is ni/256 kernel boundaries instead of ni/64 cluster barriers with a global
+// exchange (round 1: 188 barriers of ~6 µs per sweep at the 2048² workload), and every panel is streamed by as many CTAs
+// as it has 256-row tiles.  The rectangular parts (2/3 of the bytes) stay with k_gemv_rect.
 // ------------------------------------------------------------------------------------------------
-template <typename T> __device__ __forceinline__ T ldcg(const T* p);
-template <> __device__ __forceinline__ double ldcg<double>(const double* p) { return __ldcg(p); }
-template <> __device__ __forceinline__ cplx ldcg<cplx>(const cplx* p) {
-  const double2 v = __ldcg(reinterpret_cast<const double2*>(p));
-  return cplx{v.x, v.y};
-}
-template <typename T> __device__ __forceinline__ void stcg(T* p, T v);
-template <> __device__ __forceinline__ void stcg<double>(double* p, double v) { __stcg(p, v); }
-template <> __device__ __forceinline__ void stcg<cplx>(cplx* p, cplx v) { __stcg(reinterpret_cast<double2*>(p), make_double2(v.x, v.y)); }
+constexpr int SB = 256;        // super-block
+constexpr int TRI_T = 1024;    // threads per CTA of the triangular step kernels
 
-// Σ_k M[r, k]·v[k] for one row per lane, v (≤ 64 values) in shared memory
+template <typename T> __device__ __forceinline__ T shfl_xor_t(T v, int o);
+template <> __device__ __forceinline__ double shfl_xor_t<double>(double v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
+template <> __device__ __forceinline__ cplx shfl_xor_t<cplx>(cplx v, int o) {
+  return cplx{__shfl_xor_sync(0xffffffffu, v.x, o), __shfl_xor_sync(0xffffffffu, v.y, o)};
+}
+
+// acc[t] = Σ_{c<ncol} M[t, c]·v[c] for the 256 rows t of a tile (row t valid when t < nrow): thread (g, t) takes the columns
+// c ≡ its quarter, the four partial sums meet in `red`.  Returns the sum to threads with g == 0.
 template <typename T>
-__device__ __forceinline__ T row_dot(const T* __restrict__ Mrow, long long ld, int kcnt, const T* __restrict__ v, bool ok) {
+__device__ __forceinline__ T tile_matvec(const T* __restrict__ M, long long ld, int nrow, int ncol, const T* __restrict__ v, T (*red)[SB]) {
+  const int g = threadIdx.x >> 8, t = threadIdx.x & 255;
   T acc = hs_zero<T>();
-  if (ok) {
+  if (t < nrow) {
+    const int c0 = g * (SB / 4), c1 = min(ncol, c0 + SB / 4);
+    const T* p = M + t;
 #pragma unroll 16
-    for (int k = 0; k < kcnt; ++k) acc = hs_fma(acc, Mrow[(long long)k * ld], v[k]);
+    for (int c = c0; c < c1; ++c) acc = hs_fma(acc, p[(long long)c * ld], v[c]);
   }
-  return acc;
+  red[g][t] = acc;
+  __syncthreads();
+  T s = hs_zero<T>();
+  if (g == 0) s = hs_add(hs_add(red[0][t], red[1][t]), hs_add(red[2][t], red[3][t]));
+  __syncthreads();
+  return s;
 }
 
-// two consecutive rows per lane through one 16-byte load (f64 only; Mrow must be 16-byte aligned): keeps
-// 16 × 16 B per thread in flight, which is what lets a handful of SMs pull a useful share of HBM bandwidth
-__device__ __forceinline__ void row_dot2(const double* __restrict__ Mrow, long long ld, int kcnt,
-                                         const double* __restrict__ v, double& a0, double& a1) {
-  double s0 = 0.0, s1 = 0.0;
-#pragma unroll 16
-  for (int k = 0; k < kcnt; ++k) {
-    const double2 m = *reinterpret_cast<const double2*>(Mrow + (long long)k * ld);
-    const double vk = v[k];
-    s0 = fma(m.x, vk, s0);
-    s1 = fma(m.y, vk, s1);
-  }
-  a0 = s0; a1 = s1;
-}
-
-// one tile of the streamed update  w[r] −= Σ_k M[r,k]·v[k]  (or the final scatter into x when `fin`);
-// a tile is 64 rows for aligned f64 fronts (2 rows per lane) and 32 rows otherwise
-template <typename T> struct TileRows { static constexpr int N = 32; };
-template <> struct TileRows<double> { static constexpr int N = 64; };
-
+// forward: step s finishes super-block s of every large front (rows [s·SB, …) of v = L11⁻¹·P·x_int)
 template <typename T>
-__device__ __forceinline__ void tile_update(const T* __restrict__ Mb, long long ld, int kcnt, const T* __restrict__ v,
-                                            int rbase, int rend, bool al, T* __restrict__ w, T* __restrict__ xr,
-                                            const int* __restrict__ gi, bool fin, const T* __restrict__ src_x) {
-  const int lane = threadIdx.x & 31;
-  auto put = [&](int r, T acc) {
-    const T cur = src_x ? src_x[gi[r]] : ldcg(&w[r]);
-    const T val = hs_sub(cur, acc);
-    if (fin) xr[gi[r]] = val; else stcg(&w[r], val);
-  };
-  if constexpr (sizeof(T) == 8) {
-    const int r = rbase + 2 * lane;
-    if (al && (rbase & 1) == 0 && r + 1 < rend) {
-      double a0, a1;
-      row_dot2(reinterpret_cast<const double*>(Mb) + r, ld, kcnt, reinterpret_cast<const double*>(v), a0, a1);
-      put(r, a0); put(r + 1, a1);
-    } else {
-      // unaligned front or ragged tail: scalar fallback over the two rows this lane owns
-      for (int q = 0; q < 2; ++q) {
-        const int rr = r + q;
-        if (rr < rend) put(rr, row_dot<T>(Mb + rr, ld, kcnt, v, true));
+__global__ void __launch_bounds__(TRI_T) k_sv_tri_fwd(const Front* __restrict__ fronts, const T* __restrict__ pool,
+                                                       const int* __restrict__ gidx, const int* __restrict__ rperm,
+                                                       T* __restrict__ x, long long ldx, T* __restrict__ work,
+                                                       long long wstride, long long ioff0, int f0, int s) {
+  const Front fr = fronts[f0 + blockIdx.x];
+  const int ni = fr.ni;
+  const int R0 = s * SB;
+  if (R0 >= ni) return;
+  const int R1 = min(R0 + SB, ni), cnt = R1 - R0;
+  const T* F = pool + fr.off;
+  const long long ld = fr.ld;
+  T* xr = x + (long long)blockIdx.z * ldx;
+  T* w = work + (long long)blockIdx.z * wstride + (fr.ioff - ioff0);
+  const int* gi = gidx + fr.ioff;
+  const int* rp = rperm + fr.ioff;
+  const int tid = threadIdx.x, g = tid >> 8, t = tid & 255;
+  __shared__ T sv[SB], su[SB];
+  __shared__ T red[4][SB];
+  const int P0 = R0 - SB;   // previous super-block (always full)
+  if (s > 0 && tid < SB) sv[tid] = w[P0 + tid];
+  __syncthreads();
+  if (blockIdx.y > 0) {
+    // worker tile: rows behind the current super-block
+    const int r0 = R1 + (blockIdx.y - 1) * SB;
+    if (r0 >= ni) return;
+    const int nrow = min(SB, ni - r0);
+    if (s == 0) {   // gather v = P·x_int
+      if (g == 0 && t < nrow) w[r0 + t] = xr[gi[rp[r0 + t]]];
+      return;
+    }
+    const T sum = tile_matvec<T>(F + (long long)P0 * ld + r0, ld, nrow, SB, sv, red);
+    if (g == 0 && t < nrow) w[r0 + t] = hs_sub(w[r0 + t], sum);
+    return;
+  }
+  // diagonal CTA
+  {
+    T sum = hs_zero<T>();
+    if (s > 0) sum = tile_matvec<T>(F + (long long)P0 * ld + R0, ld, cnt, SB, sv, red);
+    if (g == 0 && t < cnt) su[t] = hs_sub(s == 0 ? xr[gi[rp[R0 + t]]] : w[R0 + t], sum);
+  }
+  __syncthreads();
+  const T* D = F + (long long)R0 * ld + R0;   // the super-block's diagonal 256×256 block
+  for (int B0 = 0; B0 < cnt; B0 += DB) {
+    const int bw = min(DB, cnt - B0);
+    {  // (i) y_B = u_B + strict_lower(L_BB⁻¹)·u_B : row i = tid & 63, 16 column groups of 4
+      const int i = tid & 63, pp = tid >> 6;
+      T acc = hs_zero<T>();
+      if (i < bw) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const int k = pp * 4 + kk;
+          if (k < i) acc = hs_fma(acc, D[(long long)(B0 + k) * ld + (B0 + i)], su[B0 + k]);
+        }
       }
+      red[pp >> 2][(pp & 3) * 64 + i] = acc;
+      __syncthreads();
+      if (tid < bw) {
+        T y = su[B0 + tid];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) y = hs_add(y, red[q >> 2][(q & 3) * 64 + tid]);
+        su[B0 + tid] = y;
+      }
+      __syncthreads();
     }
-  } else {
-    const int r = rbase + lane;
-    if (r < rend) put(r, row_dot<T>(Mb + r, ld, kcnt, v, true));
+    if (B0 + bw < cnt) {  // (ii) rows behind block B inside the super-block: u −= L[:, B]·y_B, 4 column groups of 16
+      const int rr = B0 + bw + t;
+      T acc = hs_zero<T>();
+      if (rr < cnt) {
+        const int c0 = g * 16, c1 = min(bw, c0 + 16);
+        const T* p = D + (long long)B0 * ld + rr;
+#pragma unroll 16
+        for (int c = c0; c < c1; ++c) acc = hs_fma(acc, p[(long long)c * ld], su[B0 + c]);
+      }
+      red[g][t] = acc;
+      __syncthreads();
+      if (g == 0 && rr < cnt) su[rr] = hs_sub(su[rr], hs_add(hs_add(red[0][t], red[1][t]), hs_add(red[2][t], red[3][t])));
+      __syncthreads();
+    }
   }
+  if (tid < cnt) { const T v = su[tid]; w[R0 + tid] = v; xr[gi[R0 + tid]] = v; }
 }
 
-// Work of the "diagonal CTA" in one step, executed by all NTH threads of that CTA:
-//   u[i]  = win[i] − Σ_{k<db} M[i, k]·vb[k]                 for the cnt ≤ 64 rows starting at Mrows / win
-//   y[i]  = (tri == 1 ? u[i] : 0) + Σ_k Tinv[i, k]·u[k]      for i < dn   (k < i lower-unit, k ≥ i upper)
-//   y[i]  = u[i]                                             for dn ≤ i < cnt (rows below a partial last block)
-// Returns y[tid] to threads tid < cnt (others get zero).
+// backward: step s finishes super-block b = nsb − 1 − s of every large front (x_int = U11⁻¹·t, t = work[0:ni] from k_gemv_rect)
 template <typename T>
-__device__ __forceinline__ T diag_cta(const T* __restrict__ Mrows, long long ld, int db, const T* __restrict__ vb,
-                                      T win, int cnt, const T* __restrict__ Tinv, int dn, int tri, T* sT, T (*spart)[64],
-                                      T* su) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int LDT = 65;
-  // all global loads of this step are issued up front with static addressing (16 + 16 per thread in flight)
+__global__ void __launch_bounds__(TRI_T) k_sv_tri_bwd(const Front* __restrict__ fronts, const T* __restrict__ pool,
+                                                       const int* __restrict__ gidx, T* __restrict__ x, long long ldx,
+                                                       T* __restrict__ work, long long wstride, long long ioff0, int f0, int s) {
+  const Front fr = fronts[f0 + blockIdx.x];
+  const int ni = fr.ni;
+  const int nsb = (ni + SB - 1) / SB;
+  const int b = nsb - 1 - s;
+  if (b < 0) return;
+  const int R0 = b * SB, R1 = min(R0 + SB, ni), cnt = R1 - R0;
+  const T* F = pool + fr.off;
+  const long long ld = fr.ld;
+  T* xr = x + (long long)blockIdx.z * ldx;
+  T* w = work + (long long)blockIdx.z * wstride + (fr.ioff - ioff0);
+  const int* gi = gidx + fr.ioff;
+  const int tid = threadIdx.x, g = tid >> 8, t = tid & 255;
+  __shared__ T sv[SB], su[SB];
+  __shared__ T red[4][SB];
+  const int pc = s > 0 ? min(SB, ni - R1) : 0;   // columns of the super-block solved in the previous step: [R1, R1 + pc)
+  if (tid < SB) sv[tid] = tid < pc ? w[R1 + tid] : hs_zero<T>();
+  __syncthreads();
+  if (blockIdx.y > 0) {
+    // worker tile: rows above the current super-block
+    if (s == 0) return;
+    const int r0 = (blockIdx.y - 1) * SB;
+    if (r0 >= R0) return;
+    const int nrow = min(SB, R0 - r0);
+    const T sum = tile_matvec<T>(F + (long long)R1 * ld + r0, ld, nrow, pc, sv, red);
+    if (g == 0 && t < nrow) w[r0 + t] = hs_sub(w[r0 + t], sum);
+    return;
+  }
   {
-    const int i = tid & 63, kq = tid >> 6;  // 4 columns per pass
-    T pre[16];
-#pragma unroll
-    for (int q = 0; q < 16; ++q) {
-      const int k = kq + 4 * q;
-      pre[q] = (i < dn && k < dn) ? Tinv[(long long)k * ld + i] : hs_zero<T>();
-    }
-    T a0 = hs_zero<T>(), a1 = hs_zero<T>();
-    const bool ok0 = lane < cnt, ok1 = lane + 32 < cnt;
-    T m0[8], m1[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int k = warp + NW * q;
-      m0[q] = (ok0 && k < db) ? Mrows[(long long)k * ld + lane] : hs_zero<T>();
-      m1[q] = (ok1 && k < db) ? Mrows[(long long)k * ld + lane + 32] : hs_zero<T>();
-    }
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int k = warp + NW * q;
-      const T vk = k < db ? vb[k] : hs_zero<T>();
-      a0 = hs_fma(a0, m0[q], vk);
-      a1 = hs_fma(a1, m1[q], vk);
-    }
-    spart[warp][lane] = a0;
-    spart[warp][lane + 32] = a1;
-#pragma unroll
-    for (int q = 0; q < 16; ++q) sT[(kq + 4 * q) * LDT + i] = pre[q];
+    T sum = hs_zero<T>();
+    if (s > 0) sum = tile_matvec<T>(F + (long long)R1 * ld + R0, ld, cnt, pc, sv, red);
+    if (g == 0 && t < cnt) su[t] = hs_sub(w[R0 + t], sum);
   }
   __syncthreads();
-  if (tid < 64) {
-    T u = hs_zero<T>();
-    if (tid < cnt) {
-      T sum = hs_zero<T>();
+  const T* D = F + (long long)R0 * ld + R0;
+  const int nblk = (cnt + DB - 1) / DB;
+  for (int q = nblk - 1; q >= 0; --q) {
+    const int B0 = q * DB, bw = min(DB, cnt - B0);
+    {  // (i) y_B = upper(U_BB⁻¹)·u_B (diagonal included)
+      const int i = tid & 63, pp = tid >> 6;
+      T acc = hs_zero<T>();
+      if (i < bw) {
 #pragma unroll
-      for (int w = 0; w < NW; ++w) sum = hs_add(sum, spart[w][tid]);
-      u = hs_sub(win, sum);
-    }
-    su[tid] = u;
-  }
-  __syncthreads();
-  {
-    T a0 = hs_zero<T>(), a1 = hs_zero<T>();
-    const int r0 = lane, r1 = lane + 32;
-    for (int k = warp; k < dn; k += NW) {
-      const T uk = su[k];
-      const bool use0 = r0 < dn && (tri == 1 ? k < r0 : k >= r0);
-      const bool use1 = r1 < dn && (tri == 1 ? k < r1 : k >= r1);
-      if (use0) a0 = hs_fma(a0, sT[k * LDT + r0], uk);
-      if (use1) a1 = hs_fma(a1, sT[k * LDT + r1], uk);
-    }
-    spart[warp][lane] = a0;
-    spart[warp][lane + 32] = a1;
-  }
-  __syncthreads();
-  T y = hs_zero<T>();
-  if (tid < cnt) {
-    if (tid < dn) {
-      T sum = tri == 1 ? su[tid] : hs_zero<T>();
+        for (int kk = 0; kk < 4; ++kk) {
+          const int k = pp * 4 + kk;
+          if (k >= i && k < bw) acc = hs_fma(acc, D[(long long)(B0 + k) * ld + (B0 + i)], su[B0 + k]);
+        }
+      }
+      red[pp >> 2][(pp & 3) * 64 + i] = acc;
+      __syncthreads();
+      if (tid < bw) {
+        T y = hs_zero<T>();
 #pragma unroll
-      for (int w = 0; w < NW; ++w) sum = hs_add(sum, spart[w][tid]);
-      y = sum;
-    } else {
-      y = su[tid];
+        for (int qq = 0; qq < 16; ++qq) y = hs_add(y, red[qq >> 2][(qq & 3) * 64 + tid]);
+        su[B0 + tid] = y;
+      }
+      __syncthreads();
+    }
+    if (B0 > 0) {  // (ii) rows above block B inside the super-block: u −= U[:, B]·y_B
+      T acc = hs_zero<T>();
+      if (t < B0) {
+        const int c0 = g * 16, c1 = min(bw, c0 + 16);
+        const T* p = D + (long long)B0 * ld + t;
+#pragma unroll 16
+        for (int c = c0; c < c1; ++c) acc = hs_fma(acc, p[(long long)c * ld], su[B0 + c]);
+      }
+      red[g][t] = acc;
+      __syncthreads();
+      if (g == 0 && t < B0) su[t] = hs_sub(su[t], hs_add(hs_add(red[0][t], red[1][t]), hs_add(red[2][t], red[3][t])));
+      __syncthreads();
     }
   }
-  __syncthreads();
-  return y;
+  if (tid < cnt) { const T v = su[tid]; w[R0 + tid] = v; xr[gi[R0 + tid]] = v; }
 }
 
 // Rectangular part of a large front as ONE streamed mat-vec over the whole GPU (it holds 2/3 of the front's bytes and
@@ -402,128 +447,6 @@ __global__ void __launch_bounds__(NTH) k_gemv_rect(const Front* __restrict__ fro
   }
 }
 
-template <typename T, bool CL>
-__global__ void __launch_bounds__(NTH) k_sv_big_fwd(const Front* __restrict__ fronts, const T* __restrict__ pool,
-                                                     const int* __restrict__ gidx, const int* __restrict__ rperm,
-                                                     T* __restrict__ x, long long ldx, T* __restrict__ work,
-                                                     long long wstride, long long ioff0, int f0) {
-  cg::cluster_group cluster = cg::this_cluster();
-  const int C = CL ? (int)cluster.num_blocks() : 1;
-  const int crank = CL ? (int)cluster.block_rank() : 0;
-  const Front fr = fronts[f0 + (CL ? blockIdx.x / C : blockIdx.x)];
-  const int n = fr.n, ni = fr.ni;
-  const T* F = pool + fr.off;
-  const long long ld = fr.ld;
-  const bool al = (fr.off & 1) == 0;  // 16-byte aligned columns (false only for the root-boundary pseudo front)
-  T* xr = x + (long long)blockIdx.y * ldx;
-  T* w = work + (long long)blockIdx.y * wstride + (fr.ioff - ioff0);
-  const int* gi = gidx + fr.ioff;
-  const int* rp = rperm + fr.ioff;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* sT = reinterpret_cast<T*>(smem_raw);        // 64·65
-  T(*spart)[64] = reinterpret_cast<T(*)[64]>(sT + 64 * 65);  // NW·64
-  T* su = sT + 64 * 65 + NW * 64;                // 64
-  T* svb = su + 64;                              // 64
-  auto sync = [&]() { if (CL) cluster.sync(); else __syncthreads(); };
-  // tile workers: the warps of CTAs 1..C-1 (all warps of the only CTA when C == 1)
-  const int nworkers = C > 1 ? NW * (C - 1) : NW;
-  const int me = C > 1 ? (crank - 1) * NW + warp : warp;
-  const bool worker = C == 1 || crank > 0;
-  // gather v = P·x_int (the boundary rows are updated afterwards by k_gemv_rect)
-  for (int r = crank * NTH + tid; r < ni; r += NTH * C) stcg(&w[r], xr[gi[rp[r]]]);
-  sync();
-  const int B = (ni + DB - 1) / DB;
-  if (crank == 0) {  // v_0 = L00⁻¹·v_0
-    const int db0 = min(DB, ni);
-    const T win = tid < db0 ? ldcg(&w[tid]) : hs_zero<T>();
-    const T y = diag_cta<T>(F, ld, 0, svb, win, db0, F, db0, 1, sT, spart, su);
-    if (tid < db0) { stcg(&w[tid], y); xr[gi[tid]] = y; }
-  }
-  sync();
-  for (int b = 0; b < B; ++b) {
-    const int b0 = b * DB, b1 = min(b0 + DB, ni), db = b1 - b0;
-    const bool last = b1 >= ni;
-    if (tid < 64) svb[tid] = tid < db ? ldcg(&w[b0 + tid]) : hs_zero<T>();
-    __syncthreads();
-    const T* Fb = F + (long long)b0 * ld;
-    // rows after b1 in tiles of 32; the first 64 rows (the next diagonal block) belong to CTA 0 unless this is the
-    // last block column
-    if (!last) {
-      if (crank == 0) {
-        const int nb1 = min(b1 + DB, ni), dn = nb1 - b1;
-        const int cnt = dn;
-        const T win = tid < cnt ? ldcg(&w[b1 + tid]) : hs_zero<T>();
-        const T y = diag_cta<T>(Fb + b1, ld, db, svb, win, cnt, F + (long long)b1 * ld + b1, dn, 1, sT, spart, su);
-        if (tid < cnt) { stcg(&w[b1 + tid], y); if (tid < dn) xr[gi[b1 + tid]] = y; }
-      }
-    }
-    if (worker) {
-      constexpr int TR = TileRows<T>::N;
-      const int rstart = b1 + 64;  // rows of the pivot block below the next diagonal block
-      const int ntiles = last ? 0 : (ni - rstart + TR - 1) / TR;
-      for (int t = me; t < ntiles; t += nworkers)
-        tile_update<T>(Fb, ld, db, svb, rstart + t * TR, ni, al, w, xr, gi, false, nullptr);
-    }
-    if (b + 1 < B) sync();
-  }
-}
-
-template <typename T, bool CL>
-__global__ void __launch_bounds__(NTH) k_sv_big_bwd(const Front* __restrict__ fronts, const T* __restrict__ pool,
-                                                     const int* __restrict__ gidx, T* __restrict__ x, long long ldx,
-                                                     T* __restrict__ work, long long wstride, long long ioff0, int f0) {
-  cg::cluster_group cluster = cg::this_cluster();
-  const int C = CL ? (int)cluster.num_blocks() : 1;
-  const int crank = CL ? (int)cluster.block_rank() : 0;
-  const Front fr = fronts[f0 + (CL ? blockIdx.x / C : blockIdx.x)];
-  const int n = fr.n, ni = fr.ni, nb = n - ni;
-  const T* F = pool + fr.off;
-  const long long ld = fr.ld;
-  const bool al = (fr.off & 1) == 0;
-  T* xr = x + (long long)blockIdx.y * ldx;
-  T* w = work + (long long)blockIdx.y * wstride + (fr.ioff - ioff0);
-  const int* gi = gidx + fr.ioff;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* sT = reinterpret_cast<T*>(smem_raw);
-  T(*spart)[64] = reinterpret_cast<T(*)[64]>(sT + 64 * 65);
-  T* su = sT + 64 * 65 + NW * 64;
-  T* svb = su + 64;
-  auto sync = [&]() { if (CL) cluster.sync(); else __syncthreads(); };
-  const int nworkers = C > 1 ? NW * (C - 1) : NW;
-  const int me = C > 1 ? (crank - 1) * NW + warp : warp;
-  const bool worker = C == 1 || crank > 0;
-  const int B = (ni + DB - 1) / DB;
-  const int l0 = (B - 1) * DB, dl = ni - l0;
-  // phase 0: work[0:ni] already holds t = x_int − U12·x_bnd (k_gemv_rect); CTA 0 applies the inverse of the last
-  // diagonal block
-  if (crank == 0) {
-    const T win = tid < dl ? ldcg(&w[l0 + tid]) : hs_zero<T>();
-    const T y = diag_cta<T>(F, ld, 0, svb, win, dl, F + (long long)l0 * ld + l0, dl, 2, sT, spart, su);
-    if (tid < dl) { stcg(&w[l0 + tid], y); xr[gi[l0 + tid]] = y; }
-  }
-  for (int b = B - 1; b >= 1; --b) {
-    sync();
-    const int b0 = b * DB, b1 = min(b0 + DB, ni), db = b1 - b0;
-    const int p0 = b0 - DB;  // previous diagonal block [p0, b0), always full
-    if (tid < 64) svb[tid] = tid < db ? ldcg(&w[b0 + tid]) : hs_zero<T>();
-    __syncthreads();
-    const T* Fb = F + (long long)b0 * ld;
-    if (crank == 0) {
-      const T win = tid < 64 ? ldcg(&w[p0 + tid]) : hs_zero<T>();
-      const T y = diag_cta<T>(Fb + p0, ld, db, svb, win, 64, F + (long long)p0 * ld + p0, 64, 2, sT, spart, su);
-      if (tid < 64) { stcg(&w[p0 + tid], y); xr[gi[p0 + tid]] = y; }
-    }
-    if (worker) {
-      constexpr int TR = TileRows<T>::N;
-      const int ntop = (p0 + TR - 1) / TR;
-      for (int t = me; t < ntop; t += nworkers)
-        tile_update<T>(Fb, ld, db, svb, t * TR, p0, al, w, xr, gi, false, nullptr);
-    }
-  }
-}
-
 template <typename T> void prep_impl(hs_fac* f, const Level& L, cudaStream_t st) {
   if (L.max_ni == 0) return;
   dim3 grid(L.f1 - L.f0, (L.max_ni + DB - 1) / DB);
@@ -533,39 +456,19 @@ template <typename T> void prep_impl(hs_fac* f, const Level& L, cudaStream_t st)
   f->stats.launches_factor += 1;
 }
 
-template <typename T> constexpr size_t big_smem() { return (64 * 65 + NW * 64 + 128) * sizeof(T); }
-
-static int pow2_ceil_i(int v) { int p = 1; while (p < v) p <<= 1; return p; }
-
+// triangular part of the large fronts of a level: one launch per super-block step
 template <typename T, bool FWD> void launch_big(hs_fac* f, const Level& L, int nbig, int64_t nrhs, T* x) {
   cudaStream_t st = f->ctx->stream;
-  const int C = std::min(f->ctx->max_cluster, std::max(1, pow2_ceil_i((L.max_n + 255) / 256)));
-  const Front* fr = f->d_fronts;
-  const T* pool = (const T*)f->pool;
-  const int* gidx = f->d_gidx;
-  const int* rperm = f->d_rperm;
-  T* work = (T*)f->d_work;
-  long long ldx = f->xld, ws = f->max_level_idx, ioff0 = L.ioff0;
-  int f0 = L.f0;
-  if (C == 1) {
-    dim3 g(nbig, (unsigned)nrhs);
-    if (FWD) k_sv_big_fwd<T, false><<<g, NTH, big_smem<T>(), st>>>(fr, pool, gidx, rperm, x, ldx, work, ws, ioff0, f0);
-    else k_sv_big_bwd<T, false><<<g, NTH, big_smem<T>(), st>>>(fr, pool, gidx, x, ldx, work, ws, ioff0, f0);
-  } else {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(nbig * C), (unsigned)nrhs);
-    cfg.blockDim = dim3(NTH);
-    cfg.dynamicSmemBytes = big_smem<T>();
-    cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    if (FWD) CUDA_OK(cudaLaunchKernelEx(&cfg, k_sv_big_fwd<T, true>, fr, pool, gidx, rperm, x, ldx, work, ws, ioff0, f0));
-    else CUDA_OK(cudaLaunchKernelEx(&cfg, k_sv_big_bwd<T, true>, fr, pool, gidx, x, ldx, work, ws, ioff0, f0));
+  const int nsb = (L.max_ni + SB - 1) / SB;
+  for (int s = 0; s < nsb; ++s) {
+    // rows still to be updated behind (FWD) / above (BWD) the super-block of this step, for the largest front
+    const int rest = std::max(0, L.max_ni - (s + 1) * SB);
+    dim3 g(nbig, 1 + (rest + SB - 1) / SB, (unsigned)nrhs);
+    if (FWD) k_sv_tri_fwd<T><<<g, TRI_T, 0, st>>>(f->d_fronts, (const T*)f->pool, f->d_gidx, f->d_rperm, x, f->xld, (T*)f->d_work, f->max_level_idx, L.ioff0, L.f0, s);
+    else k_sv_tri_bwd<T><<<g, TRI_T, 0, st>>>(f->d_fronts, (const T*)f->pool, f->d_gidx, x, f->xld, (T*)f->d_work, f->max_level_idx, L.ioff0, L.f0, s);
+    ++f->stats.launches_solve;
   }
   CUDA_OK(cudaGetLastError());
-  ++f->stats.launches_solve;
 }
 
 template <typename T> void run_impl(hs_fac* f, int64_t nrhs, void* xv, int which) {
@@ -619,14 +522,6 @@ template <typename T> void run_impl(hs_fac* f, int64_t nrhs, void* xv, int which
 void hs_solve_setup() {
   CUDA_OK(cudaFuncSetAttribute(k_trtri_diag<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (DB + 1) * (DB + 1) * (int)sizeof(double)));
   CUDA_OK(cudaFuncSetAttribute(k_trtri_diag<cplx>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (DB + 1) * (DB + 1) * (int)sizeof(cplx)));
-  CUDA_OK(cudaFuncSetAttribute(k_sv_big_fwd<cplx, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_smem<cplx>()));
-  CUDA_OK(cudaFuncSetAttribute(k_sv_big_bwd<cplx, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_smem<cplx>()));
-  CUDA_OK(cudaFuncSetAttribute(k_sv_big_fwd<cplx, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_smem<cplx>()));
-  CUDA_OK(cudaFuncSetAttribute(k_sv_big_bwd<cplx, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_smem<cplx>()));
-  CUDA_OK(cudaFuncSetAttribute(k_sv_big_fwd<double, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-  CUDA_OK(cudaFuncSetAttribute(k_sv_big_bwd<double, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-  CUDA_OK(cudaFuncSetAttribute(k_sv_big_fwd<cplx, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-  CUDA_OK(cudaFuncSetAttribute(k_sv_big_bwd<cplx, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   CUDA_OK(cudaFuncSetAttribute(k_sv_small_bwd<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CUDA_OK(cudaFuncSetAttribute(k_sv_small_bwd<cplx>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 }

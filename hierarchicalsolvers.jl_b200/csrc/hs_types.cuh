@@ -23,8 +23,12 @@ struct Front {
   int parent;      // front id of the parent, -1 for the root
   int ni_l, nb_l;  // branch: #int / #bnd rows that come from the left child; leaf: ni_l = -1
   int flags;       // bit0: pseudo front (root Schur block, factornode.jl:72) — no assembly
-  int pad;
+  int split;       // > 0: pivoting is restricted to the two diagonal blocks [0, split) and [split, ni) of the pivot block —
+                   // the 2×2 block elimination of blockfactor (blockmatrix.jl:115-120) — used when the pivot block has more
+                   // rows than one panel cluster covers; 0: partial pivoting over the whole pivot block
 };
+// rows a pivot may be taken from while panel j0 is factored: [j0, hs_plim(fr, j0))
+__host__ __device__ __forceinline__ int hs_plim(const Front& fr, int j0) { return (fr.split > 0 && j0 < fr.split) ? fr.split : fr.ni; }
 
 template <typename T> struct hs_traits;
 template <> struct hs_traits<double> { static constexpr bool is_complex = false; };

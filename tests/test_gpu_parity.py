@@ -299,3 +299,28 @@ def test_spmv_with_the_resident_matrix(hs, kind):
     assert rel(yd.cpu().numpy(), Ap @ x) < 1e-13
     with pytest.raises(hs.ArgumentError):
         hs._lib.check(hs._lib.lib.hs_spmv(F._hd.h, C.c_void_p(xd.data_ptr()), C.c_void_p(xd.data_ptr())))
+
+
+@pytest.mark.parametrize("kind", ["poisson", "helmholtz"])
+def test_split_pivot_block_matches_unsplit(hs, kind):
+    """Pivot blocks taller than one panel cluster (the 32 768-row root of the 128^3 problem in complex arithmetic) are
+    eliminated as the reference's 2x2 `blockfactor` (blockmatrix.jl:115-120): pivoting inside A11 and inside S22.
+    HS_PROW_CAP forces that path on a small problem; D, L, R, S are pivot-order independent, so both factorizations
+    must agree to rounding."""
+    import os
+    prob = hs.grid_problem((513, 513), kind, nmax=100)
+    Ap, nd, nd_loc, perm = hs.prepare(prob.A, prob.elim_tree)
+    F0 = hs.factor(Ap, nd, nd_loc, swlevel=0)
+    x0 = hs.ldiv(F0, prob.b)
+    os.environ["HS_PROW_CAP"] = "600"
+    try:
+        F1 = hs.factor(Ap, nd, nd_loc, swlevel=0)
+    finally:
+        os.environ.pop("HS_PROW_CAP", None)
+    x1 = hs.ldiv(F1, prob.b)
+    assert rel(Ap @ x1, prob.b) < TOL and rel(x1, x0) < 1e-9
+    root = nd.nnodes - 1
+    assert rel(F1.node(root).D, F0.node(root).D) < TOL
+    k2 = int(nd.left[root])
+    for name in ("L", "R", "S"):
+        assert rel(getattr(F1.node(k2), name), getattr(F0.node(k2), name)) < 1e-9, name

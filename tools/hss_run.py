@@ -27,4 +27,6 @@ st = F.stats()
 print(f"  refactor: numeric {st['ms_factor_total']:.1f} ms, launches {st['launches_factor']}", flush=True)
 x, h = hs.gmres(Ap, b, Pr=F, reltol=1e-9, restart=30, maxiter=30, log=True, A_is_factored=True)
 print(f"  gmres iters {h.iters} converged {h.isconverged} residual {np.linalg.norm(Ap @ x - b) / np.linalg.norm(b):.2e}, apply {F.stats()['ms_solve_total']:.2f} ms", flush=True)
+if os.environ.get("HS_PROFILE"):
+    print("  phases:", {k: round(v, 2) for k, v in st.items() if k.startswith("ms_")})
 print("ok")
