@@ -408,6 +408,12 @@ def run_distributed(args, hs, torch, world, rank, local_rank, Ap, nd, nd_loc, b,
         stp[k] = sum(st[k] for st in sts)
     peak, peak_src = fp64_peak(b.dtype == np.complex128)
     e2e = None
+    par = {"scheme": "subtree-per-GPU; fronts above the cut owned by the left child's rank, Schur blocks sent point-to-point (NCCL); GMRES replicated", "top_mode": DF.mode,
+           "cut_nodes": [int(c) for c in DF.part.cut], "schur_bytes_exchanged": DF.schur_bytes,
+           "top_flops_share": float(1.0 - sum(_ff(sn) for sn in DF.part.sub_nd) / float(np.sum(DF.part.work)))}
+    DF.free()                      # the end-to-end run builds its own factorization: release this one first
+    del out["x"]
+    torch.cuda.empty_cache()
     if not args.no_e2e:
         dist.barrier(); torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -423,9 +429,7 @@ def run_distributed(args, hs, torch, world, rank, local_rank, Ap, nd, nd_loc, b,
     return {"ms_step": float(t[0].item()), "fac_ms": float(t[1].item()), "iters": out["iters"], "resid": resid,
             "roofline": gemm_roofline(stp, peak, peak_src), "e2e": e2e, "clocks": clocks,
             "launches": int(lc1.value - lc0.value) // max(args.steps, 1), "stats": stp, "t_first": t_first,
-            "parallelism": {"scheme": "subtree-per-GPU; fronts above the cut owned by the left child's rank, Schur blocks sent point-to-point (NCCL); GMRES replicated", "top_mode": DF.mode,
-                            "cut_nodes": [int(c) for c in DF.part.cut], "schur_bytes_exchanged": DF.schur_bytes,
-                            "top_flops_share": float(1.0 - sum(_ff(sn) for sn in DF.part.sub_nd) / float(np.sum(DF.part.work)))}}
+            "parallelism": par}
 
 
 def resident_single(args, hs, torch, ctx, stream, local_rank, Ap, nd, nd_loc, b, cx, steps, warmup, with_e2e, with_profile=True):

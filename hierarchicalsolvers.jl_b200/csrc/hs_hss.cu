@@ -28,7 +28,9 @@
 // reference's HSS `_assemble_blocks` (:126-140) does.  The parent's low-rank Gauss transforms then start from this
 // matrix's generators (hs_compress.cu, :184-209).
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <functional>
 #include <vector>
@@ -256,26 +258,31 @@ __global__ void k_hss_desc_b(const HNode* __restrict__ nodes, const int* __restr
 template <typename T>
 __global__ void __launch_bounds__(256) k_hss_qrcp(const HNode* __restrict__ nodes, const int* __restrict__ list,
                                                    const HFront* __restrict__ fronts, T* __restrict__ pool, int* __restrict__ ints,
-                                                   double atol, double rtol, int kcap, int mcap) {
+                                                   double atol, double rtol, int kcap, int mcap, int wcap) {
   const HNode nd = nodes[list[blockIdx.x]];
   if (nd.parent < 0) return;
   const int s = blockIdx.y;
   const HFront fr = fronts[nd.front];
   const int k = fr.k, mc = nd.mcat;
-  const long long kld = fr.kld;
   const T* Y = pool + nd.ycat[s];
-  T* W = pool + nd.wq[s];
   extern __shared__ __align__(16) unsigned char sm_q[];
   T* u = reinterpret_cast<T*>(sm_q);
   double* nrm = reinterpret_cast<double*>(sm_q + (size_t)kcap * sizeof(T));
   int* cidx = reinterpret_cast<int*>(nrm + mcap);
+  // the scratch copy the reflectors work on lives in shared memory whenever it fits (leaves and the lower HSS levels: a few
+  // tens of KB) — every step of the column loop is then two shared-memory passes instead of two L2 round trips
+  T* smW = reinterpret_cast<T*>(sm_q + (((size_t)kcap * sizeof(T) + (size_t)mcap * (sizeof(double) + sizeof(int)) + 15) & ~(size_t)15));
+  const bool insm = (long long)fr.kld * mc <= (long long)wcap;
+  T* W = insm ? smW : pool + nd.wq[s];
+  const long long kld = fr.kld;
+  const long long yld = fr.kld;
   __shared__ double s_v[8];
   __shared__ int s_i[8];
   __shared__ int s_rank;
   __shared__ double s_r11;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int c = warp; c < mc; c += 8) {
-    const T* y = Y + (long long)c * kld;
+    const T* y = Y + (long long)c * yld;
     T* w = W + (long long)c * kld;
     double a = 0.0;
     for (int i = lane; i < k; i += 32) { const T v = y[i]; w[i] = v; a += habs2(v); }
@@ -374,8 +381,8 @@ __global__ void __launch_bounds__(256) k_hss_qrcp(const HNode* __restrict__ node
   if (p.parent >= 0) {
     T* Yp = pool + p.ycat[s] + (long long)off * kld;
     for (int q = warp; q < r; q += 8) {
-      const T* y = Y + (long long)cidx[q] * kld;
-      T* yp = Yp + (long long)q * kld;
+      const T* y = Y + (long long)cidx[q] * yld;
+      T* yp = Yp + (long long)q * yld;
       for (int i = lane; i < k; i += 32) yp[i] = y[i];
     }
   }
@@ -411,6 +418,28 @@ __global__ void __launch_bounds__(256) k_hss_scatter(const ScatterDesc* __restri
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// host-side wall-clock breakdown of the construction (HS_PLAN_TIMING=1): the stream is synchronised at every tick
+struct HssClock {
+  bool on = getenv("HS_PLAN_TIMING") != nullptr;
+  std::chrono::steady_clock::time_point t0;
+  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  void start(cudaStream_t st) { if (on) { cudaStreamSynchronize(st); t0 = std::chrono::steady_clock::now(); } }
+  void tick(int slot, cudaStream_t st) {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    auto t1 = std::chrono::steady_clock::now();
+    acc[slot] += std::chrono::duration<double, std::milli>(t1 - t0).count();
+    t0 = t1;
+  }
+  void report() {
+    if (!on) return;
+    fprintf(stderr, "[hss] make_round %.1f  sketch %.1f  entries+desc %.1f  node gemms %.1f  qrcp %.1f  readback %.1f  store %.1f  expand %.1f ms\n",
+            acc[0], acc[1], acc[2], acc[3], acc[4], acc[5], acc[6], acc[7]);
+    for (double& a : acc) a = 0;
+  }
+};
+static HssClock g_hclk;
+
 struct Bump {
   long long off = 0;
   long long take(long long n) { const long long o = off; off += up32(std::max<long long>(n, 1)); return o; }
@@ -583,6 +612,7 @@ template <typename T> void run_round(hs_fac* f, Round& R) {
   }
   for (const HNode& N : R.nd) { max_mcat = std::max(max_mcat, N.mcat); max_cap = std::max(max_cap, N.cap); }
   ensure_sketch<T>(f, rows_need, max_k);
+  g_hclk.start(st);
   DevVec<HFront> dfr;
   DevVec<HNode> dnd;
   dfr.upload(R.fr, st);
@@ -625,6 +655,7 @@ template <typename T> void run_round(hs_fac* f, Round& R) {
   k_sk_gather<T><<<dim3(nf, (max_m + 255) / 256), 256, 0, st>>>(dfr.d, pool, f->d_hperm);
   CUDA_OK(cudaGetLastError());
   ++f->stats.launches_factor;
+  g_hclk.tick(1, st);
   // ---- HSS nodes by height ------------------------------------------------------------------------------------------------
   std::vector<std::vector<int>> byh(max_height + 1);
   for (size_t q = 0; q < R.fr.size(); ++q) {
@@ -641,8 +672,8 @@ template <typename T> void run_round(hs_fac* f, Round& R) {
   GemmDesc* dg = nullptr;
   CUDA_OK(cudaMalloc((void**)&dg, maxl * 4 * sizeof(GemmDesc)));
   const int kcap = even_up(max_k), mcap = max_mcat + 2;
-  const size_t smem = (size_t)kcap * sizeof(T) + (size_t)mcap * sizeof(double) + (size_t)mcap * sizeof(int);
-  if (smem > 200 * 1024) { cudaFree(dg); throw hs_error(HS_ESIZE, "randomized HSS construction: sample count / block size exceed the shared-memory budget of the pivoted QR"); }
+  const size_t smem0 = (((size_t)kcap * sizeof(T) + (size_t)mcap * (sizeof(double) + sizeof(int)) + 15) & ~(size_t)15);
+  if (smem0 > 200 * 1024) { cudaFree(dg); throw hs_error(HS_ESIZE, "randomized HSS construction: sample count / block size exceed the shared-memory budget of the pivoted QR"); }
   const double atol = f->opts.atol, rtol = f->opts.rtol;   // factorization.jl:110 passes atol, rtol unhalved
   try {
     for (int h = 0; h <= max_height; ++h) {
@@ -653,16 +684,29 @@ template <typename T> void run_round(hs_fac* f, Round& R) {
       k_hss_desc_a<<<(nl + 127) / 128, 128, 0, st>>>(dnd.d, lst, nl, dfr.d, R.ints, dg);
       CUDA_OK(cudaGetLastError());
       f->stats.launches_factor += 2;
+      g_hclk.tick(2, st);
       hs_gen_gemm(f, dg, 4 * nl, max_k, std::max(max_cap, max_mcat));
-      k_hss_qrcp<T><<<dim3(nl, 2), 256, smem, st>>>(dnd.d, lst, dfr.d, pool, R.ints, atol, rtol, kcap, mcap);
+      g_hclk.tick(3, st);
+      {
+        // scratch copies in shared memory for the nodes of this height whose kld × mcat block fits next to the bookkeeping
+        long long wmax = 0;
+        for (int t : byh[h]) wmax = std::max(wmax, (long long)R.fr[R.nd[t].front].kld * R.nd[t].mcat);
+        const long long budget = ((long long)200 * 1024 - (long long)smem0) / (long long)sizeof(T);
+        const int wcap = (int)std::max<long long>(0, std::min(wmax, budget));
+        const size_t smem = smem0 + (size_t)wcap * sizeof(T);
+        k_hss_qrcp<T><<<dim3(nl, 2), 256, smem, st>>>(dnd.d, lst, dfr.d, pool, R.ints, atol, rtol, kcap, mcap, wcap);
+      }
+      g_hclk.tick(4, st);
       k_hss_desc_b<<<(nl + 127) / 128, 128, 0, st>>>(dnd.d, lst, nl, dfr.d, R.ints, dg);
       CUDA_OK(cudaGetLastError());
       f->stats.launches_factor += 2;
       hs_gen_gemm(f, dg, 2 * nl, max_k, max_cap);
+      g_hclk.tick(3, st);
     }
     R.h_ints.resize(std::max(R.nints, 1));
     CUDA_OK(cudaMemcpyAsync(R.h_ints.data(), R.ints, (size_t)std::max(R.nints, 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));
+    g_hclk.tick(5, st);
   } catch (...) { cudaFree(dg); throw; }
   cudaFree(dg);
 }
@@ -836,7 +880,9 @@ template <typename T> void build_impl(hs_fac* f, CompLevel& C) {
   std::vector<std::pair<int, int>> where(f->hss.size(), {-1, -1});   // (round, slot) holding each front's final data
   const int max_rounds = 12;
   while (!act.empty()) {
+    g_hclk.start(st);
     rounds.emplace_back(make_round<T>(f, act));
+    g_hclk.tick(0, st);
     Round& R = *rounds.back();
     run_round<T>(f, R);
     ++f->stats.hss_rounds;
@@ -863,6 +909,7 @@ template <typename T> void build_impl(hs_fac* f, CompLevel& C) {
     act.swap(next);
   }
   // ---- compact store -----------------------------------------------------------------------------------------------------
+  g_hclk.start(st);
   Bump B;
   for (int hi : all) {
     HssFront& H = f->hss[hi];
@@ -951,8 +998,11 @@ template <typename T> void build_impl(hs_fac* f, CompLevel& C) {
   }
   rounds.clear();   // the sample workspaces are no longer needed
   f->stats.hss_bytes += (double)need;
+  g_hclk.tick(6, st);
   // ---- the matrix the HSS form represents goes back into the dense slots; the parent assembles from it (:126-140) ----
   expand<T>(f, all, true, nullptr);
+  g_hclk.tick(7, st);
+  if (C.li + 1 >= (int)f->levels.size() || &C == &f->clevels.back()) g_hclk.report();
 }
 
 }  // namespace

@@ -195,44 +195,93 @@ __global__ void __launch_bounds__(NTH) k_sv_small_bwd(const Front* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------
-// large fronts (ni > DB): triangular part of the sweeps in SUPER-BLOCKS of SB = 256 pivot rows, one launch per
+// large fronts (ni > DB): triangular part of the sweeps in SUPER-BLOCKS of SB = 128 pivot rows, one launch per
 // super-block step over all large fronts of the level.  In a step
-//   * CTA 0 of a front (the "diagonal CTA", 1024 threads) finishes the rows of the current super-block: it subtracts the
-//     contribution of the previous super-block's 256 solution entries (a 256×256 mat-vec split over 4 thread groups) and
-//     solves the 256×256 triangular system with the inverted 64×64 diagonal blocks (4 dependent sub-steps);
-//   * the other CTAs stream the same 256 columns over the remaining rows of the pivot block, 256 rows each.
-// The chain of dependent steps per front is ni/256 kernel boundaries instead of ni/64 cluster barriers with a global
-// exchange (round 1: 188 barriers of ~6 µs per sweep at the 2048² workload), and every panel is streamed by as many CTAs
-// as it has 256-row tiles.  The rectangular parts (2/3 of the bytes) stay with k_gemv_rect.
+//   * CTA 0 of a front (the "diagonal CTA") finishes the rows of the current super-block: it subtracts the contribution
+//     of the previous super-block's 128 solution entries (a 128×128 mat-vec, 16 entries per thread held in registers)
+//     and solves the 128×128 triangular system with the two inverted 64×64 diagonal blocks;
+//   * the other CTAs stream the same 128 columns over the remaining rows of the pivot block, 128 rows each.
+// Everything the diagonal CTA needs is requested at kernel entry — the panel into registers, the three 64×64 tiles of the
+// triangle into shared memory with cp.async — so a step costs ONE global-memory latency plus a handful of shared-memory
+// phases, instead of one latency per dependent phase.  The chain of dependent steps per front is ni/128 kernel
+// boundaries; round 1 ran ni/64 cluster barriers with a global-memory exchange each (~6 µs per barrier, 188 per sweep at
+// the 2048² workload).  The rectangular parts (2/3 of the bytes) stay with k_gemv_rect.
 // ------------------------------------------------------------------------------------------------
-constexpr int SB = 256;        // super-block
+constexpr int SB = 128;        // super-block
 constexpr int TRI_T = 1024;    // threads per CTA of the triangular step kernels
+constexpr int TG = TRI_T / SB; // column groups of the panel mat-vec (8), 16 columns each
 
-template <typename T> __device__ __forceinline__ T shfl_xor_t(T v, int o);
-template <> __device__ __forceinline__ double shfl_xor_t<double>(double v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
-template <> __device__ __forceinline__ cplx shfl_xor_t<cplx>(cplx v, int o) {
-  return cplx{__shfl_xor_sync(0xffffffffu, v.x, o), __shfl_xor_sync(0xffffffffu, v.y, o)};
+template <typename T> __device__ __forceinline__ void cp_async_elem(T* smem, const T* gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  if constexpr (sizeof(T) == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem) : "memory");
+  else asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_fence_all() { asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory"); }
+
+// 64×64 tile G[r0 + i, c0 + k] (i < nr, k < nc, zero elsewhere) → shared memory, column-major with pitch 64
+template <typename T>
+__device__ __forceinline__ void stage_tile(T* dst, const T* __restrict__ G, long long ld, int nr, int nc) {
+  for (int e = threadIdx.x; e < 64 * 64; e += TRI_T) {
+    const int i = e & 63, k = e >> 6;
+    if (i < nr && k < nc) cp_async_elem(dst + e, G + (long long)k * ld + i);
+    else dst[e] = hs_zero<T>();
+  }
 }
 
-// acc[t] = Σ_{c<ncol} M[t, c]·v[c] for the 256 rows t of a tile (row t valid when t < nrow): thread (g, t) takes the columns
-// c ≡ its quarter, the four partial sums meet in `red`.  Returns the sum to threads with g == 0.
+// Σ_c M[t, c]·v[c] over a 128×128 panel tile for row t = tid & 127 (valid when t < nrow, columns c < ncol): the loads of
+// this thread's 16 columns are issued by `panel_load`, the products are summed over the 8 column groups through `red`.
 template <typename T>
-__device__ __forceinline__ T tile_matvec(const T* __restrict__ M, long long ld, int nrow, int ncol, const T* __restrict__ v, T (*red)[SB]) {
-  const int g = threadIdx.x >> 8, t = threadIdx.x & 255;
-  T acc = hs_zero<T>();
-  if (t < nrow) {
-    const int c0 = g * (SB / 4), c1 = min(ncol, c0 + SB / 4);
-    const T* p = M + t;
-#pragma unroll 16
-    for (int c = c0; c < c1; ++c) acc = hs_fma(acc, p[(long long)c * ld], v[c]);
+__device__ __forceinline__ void panel_load(T (&m)[SB / TG], const T* __restrict__ M, long long ld, int nrow, int ncol) {
+  const int g = threadIdx.x >> 7, t = threadIdx.x & 127;
+#pragma unroll
+  for (int q = 0; q < SB / TG; ++q) {
+    const int c = g * (SB / TG) + q;
+    m[q] = (t < nrow && c < ncol) ? M[(long long)c * ld + t] : hs_zero<T>();
   }
+}
+template <typename T>
+__device__ __forceinline__ T panel_reduce(const T (&m)[SB / TG], const T* __restrict__ v, T (*red)[SB]) {
+  const int g = threadIdx.x >> 7, t = threadIdx.x & 127;
+  T acc = hs_zero<T>();
+#pragma unroll
+  for (int q = 0; q < SB / TG; ++q) acc = hs_fma(acc, m[q], v[g * (SB / TG) + q]);
   red[g][t] = acc;
   __syncthreads();
-  T s = hs_zero<T>();
-  if (g == 0) s = hs_add(hs_add(red[0][t], red[1][t]), hs_add(red[2][t], red[3][t]));
+  T sum = hs_zero<T>();
+  if (g == 0) {
+#pragma unroll
+    for (int q = 0; q < TG; ++q) sum = hs_add(sum, red[q][t]);
+  }
   __syncthreads();
-  return s;
+  return sum;
 }
+
+// y[i] = Σ_k Tile[i, k]·u[k] over a staged 64×64 tile restricted to k < i (lower == true) or k ≥ i (upper), i < nr, k < nc.
+// Row i = tid & 63, 16 column groups of 4; the result is returned to threads tid < 64.
+template <typename T>
+__device__ __forceinline__ T tile_tri_matvec(const T* __restrict__ tile, const T* __restrict__ u, int nr, int nc, int mode, T (*red)[SB]) {
+  const int i = threadIdx.x & 63, pp = threadIdx.x >> 6;
+  T acc = hs_zero<T>();
+  if (i < nr) {
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const int k = pp * 4 + kk;
+      const bool use = k < nc && (mode == 0 ? true : (mode == 1 ? k < i : k >= i));
+      if (use) acc = hs_fma(acc, tile[k * 64 + i], u[k]);
+    }
+  }
+  red[pp >> 1][(pp & 1) * 64 + i] = acc;
+  __syncthreads();
+  T y = hs_zero<T>();
+  if (threadIdx.x < 64) {
+#pragma unroll
+    for (int q = 0; q < 16; ++q) y = hs_add(y, red[q >> 1][(q & 1) * 64 + threadIdx.x]);
+  }
+  __syncthreads();
+  return y;
+}
+
+template <typename T> constexpr size_t tri_smem() { return (3 * 64 * 64 + TG * SB + 2 * SB) * sizeof(T); }
 
 // forward: step s finishes super-block s of every large front (rows [s·SB, …) of v = L11⁻¹·P·x_int)
 template <typename T>
@@ -251,12 +300,14 @@ __global__ void __launch_bounds__(TRI_T) k_sv_tri_fwd(const Front* __restrict__ 
   T* w = work + (long long)blockIdx.z * wstride + (fr.ioff - ioff0);
   const int* gi = gidx + fr.ioff;
   const int* rp = rperm + fr.ioff;
-  const int tid = threadIdx.x, g = tid >> 8, t = tid & 255;
-  __shared__ T sv[SB], su[SB];
-  __shared__ T red[4][SB];
+  const int tid = threadIdx.x, g = tid >> 7, t = tid & 127;
+  extern __shared__ __align__(16) unsigned char smem_tri[];
+  T* tiles = reinterpret_cast<T*>(smem_tri);                     // T00, T11, T10: 3 × 64×64
+  T(*red)[SB] = reinterpret_cast<T(*)[SB]>(tiles + 3 * 64 * 64);  // [TG][SB]
+  T* sv = tiles + 3 * 64 * 64 + TG * SB;                         // [SB] solution entries of the previous super-block
+  T* su = sv + SB;                                               // [SB] this super-block
   const int P0 = R0 - SB;   // previous super-block (always full)
-  if (s > 0 && tid < SB) sv[tid] = w[P0 + tid];
-  __syncthreads();
+  T m[SB / TG];
   if (blockIdx.y > 0) {
     // worker tile: rows behind the current super-block
     const int r0 = R1 + (blockIdx.y - 1) * SB;
@@ -266,52 +317,43 @@ __global__ void __launch_bounds__(TRI_T) k_sv_tri_fwd(const Front* __restrict__ 
       if (g == 0 && t < nrow) w[r0 + t] = xr[gi[rp[r0 + t]]];
       return;
     }
-    const T sum = tile_matvec<T>(F + (long long)P0 * ld + r0, ld, nrow, SB, sv, red);
+    panel_load<T>(m, F + (long long)P0 * ld + r0, ld, nrow, SB);
+    if (tid < SB) sv[tid] = w[P0 + tid];
+    __syncthreads();
+    const T sum = panel_reduce<T>(m, sv, red);
     if (g == 0 && t < nrow) w[r0 + t] = hs_sub(w[r0 + t], sum);
     return;
   }
-  // diagonal CTA
-  {
-    T sum = hs_zero<T>();
-    if (s > 0) sum = tile_matvec<T>(F + (long long)P0 * ld + R0, ld, cnt, SB, sv, red);
-    if (g == 0 && t < cnt) su[t] = hs_sub(s == 0 ? xr[gi[rp[R0 + t]]] : w[R0 + t], sum);
-  }
+  // diagonal CTA: request everything at once
+  const int bw0 = min(DB, cnt), bw1 = cnt - bw0;
+  const T* D = F + (long long)R0 * ld + R0;
+  stage_tile<T>(tiles, D, ld, bw0, bw0);                                              // L00⁻¹ (strictly lower part used)
+  stage_tile<T>(tiles + 4096, D + (long long)DB * ld + DB, ld, bw1, bw1);             // L11⁻¹
+  stage_tile<T>(tiles + 8192, D + DB, ld, bw1, bw0);                                  // L10
+  if (s > 0) panel_load<T>(m, F + (long long)P0 * ld + R0, ld, cnt, SB);
+  T base = hs_zero<T>();
+  if (tid < cnt) base = s == 0 ? xr[gi[rp[R0 + tid]]] : w[R0 + tid];
+  if (s > 0 && tid < SB) sv[tid] = w[P0 + tid];
+  cp_async_fence_all();
   __syncthreads();
-  const T* D = F + (long long)R0 * ld + R0;   // the super-block's diagonal 256×256 block
-  for (int B0 = 0; B0 < cnt; B0 += DB) {
-    const int bw = min(DB, cnt - B0);
-    {  // (i) y_B = u_B + strict_lower(L_BB⁻¹)·u_B : row i = tid & 63, 16 column groups of 4
-      const int i = tid & 63, pp = tid >> 6;
-      T acc = hs_zero<T>();
-      if (i < bw) {
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          const int k = pp * 4 + kk;
-          if (k < i) acc = hs_fma(acc, D[(long long)(B0 + k) * ld + (B0 + i)], su[B0 + k]);
-        }
-      }
-      red[pp >> 2][(pp & 3) * 64 + i] = acc;
-      __syncthreads();
-      if (tid < bw) {
-        T y = su[B0 + tid];
-#pragma unroll
-        for (int q = 0; q < 16; ++q) y = hs_add(y, red[q >> 2][(q & 3) * 64 + tid]);
-        su[B0 + tid] = y;
-      }
+  T sum = hs_zero<T>();
+  if (s > 0) sum = panel_reduce<T>(m, sv, red);
+  if (tid < SB) su[tid] = tid < cnt ? hs_sub(base, sum) : hs_zero<T>();   // g == 0 ⇔ tid < 128
+  __syncthreads();
+  {  // block 0: y0 = u0 + strict_lower(L00⁻¹)·u0
+    const T y = tile_tri_matvec<T>(tiles, su, bw0, bw0, 1, red);
+    if (tid < bw0) su[tid] = hs_add(su[tid], y);
+    __syncthreads();
+  }
+  if (bw1 > 0) {
+    {  // u1 −= L10·y0
+      const T y = tile_tri_matvec<T>(tiles + 8192, su, bw1, bw0, 0, red);
+      if (tid < bw1) su[DB + tid] = hs_sub(su[DB + tid], y);
       __syncthreads();
     }
-    if (B0 + bw < cnt) {  // (ii) rows behind block B inside the super-block: u −= L[:, B]·y_B, 4 column groups of 16
-      const int rr = B0 + bw + t;
-      T acc = hs_zero<T>();
-      if (rr < cnt) {
-        const int c0 = g * 16, c1 = min(bw, c0 + 16);
-        const T* p = D + (long long)B0 * ld + rr;
-#pragma unroll 16
-        for (int c = c0; c < c1; ++c) acc = hs_fma(acc, p[(long long)c * ld], su[B0 + c]);
-      }
-      red[g][t] = acc;
-      __syncthreads();
-      if (g == 0 && rr < cnt) su[rr] = hs_sub(su[rr], hs_add(hs_add(red[0][t], red[1][t]), hs_add(red[2][t], red[3][t])));
+    {  // block 1
+      const T y = tile_tri_matvec<T>(tiles + 4096, su + DB, bw1, bw1, 1, red);
+      if (tid < bw1) su[DB + tid] = hs_add(su[DB + tid], y);
       __syncthreads();
     }
   }
@@ -334,65 +376,58 @@ __global__ void __launch_bounds__(TRI_T) k_sv_tri_bwd(const Front* __restrict__ 
   T* xr = x + (long long)blockIdx.z * ldx;
   T* w = work + (long long)blockIdx.z * wstride + (fr.ioff - ioff0);
   const int* gi = gidx + fr.ioff;
-  const int tid = threadIdx.x, g = tid >> 8, t = tid & 255;
-  __shared__ T sv[SB], su[SB];
-  __shared__ T red[4][SB];
+  const int tid = threadIdx.x, g = tid >> 7, t = tid & 127;
+  extern __shared__ __align__(16) unsigned char smem_tri[];
+  T* tiles = reinterpret_cast<T*>(smem_tri);
+  T(*red)[SB] = reinterpret_cast<T(*)[SB]>(tiles + 3 * 64 * 64);
+  T* sv = tiles + 3 * 64 * 64 + TG * SB;
+  T* su = sv + SB;
   const int pc = s > 0 ? min(SB, ni - R1) : 0;   // columns of the super-block solved in the previous step: [R1, R1 + pc)
-  if (tid < SB) sv[tid] = tid < pc ? w[R1 + tid] : hs_zero<T>();
-  __syncthreads();
+  T m[SB / TG];
   if (blockIdx.y > 0) {
     // worker tile: rows above the current super-block
     if (s == 0) return;
     const int r0 = (blockIdx.y - 1) * SB;
     if (r0 >= R0) return;
     const int nrow = min(SB, R0 - r0);
-    const T sum = tile_matvec<T>(F + (long long)R1 * ld + r0, ld, nrow, pc, sv, red);
+    panel_load<T>(m, F + (long long)R1 * ld + r0, ld, nrow, pc);
+    if (tid < SB) sv[tid] = tid < pc ? w[R1 + tid] : hs_zero<T>();
+    __syncthreads();
+    const T sum = panel_reduce<T>(m, sv, red);
     if (g == 0 && t < nrow) w[r0 + t] = hs_sub(w[r0 + t], sum);
     return;
   }
-  {
-    T sum = hs_zero<T>();
-    if (s > 0) sum = tile_matvec<T>(F + (long long)R1 * ld + R0, ld, cnt, pc, sv, red);
-    if (g == 0 && t < cnt) su[t] = hs_sub(w[R0 + t], sum);
-  }
-  __syncthreads();
+  const int bw0 = min(DB, cnt), bw1 = cnt - bw0;
   const T* D = F + (long long)R0 * ld + R0;
-  const int nblk = (cnt + DB - 1) / DB;
-  for (int q = nblk - 1; q >= 0; --q) {
-    const int B0 = q * DB, bw = min(DB, cnt - B0);
-    {  // (i) y_B = upper(U_BB⁻¹)·u_B (diagonal included)
-      const int i = tid & 63, pp = tid >> 6;
-      T acc = hs_zero<T>();
-      if (i < bw) {
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          const int k = pp * 4 + kk;
-          if (k >= i && k < bw) acc = hs_fma(acc, D[(long long)(B0 + k) * ld + (B0 + i)], su[B0 + k]);
-        }
-      }
-      red[pp >> 2][(pp & 3) * 64 + i] = acc;
-      __syncthreads();
-      if (tid < bw) {
-        T y = hs_zero<T>();
-#pragma unroll
-        for (int qq = 0; qq < 16; ++qq) y = hs_add(y, red[qq >> 2][(qq & 3) * 64 + tid]);
-        su[B0 + tid] = y;
-      }
+  stage_tile<T>(tiles, D, ld, bw0, bw0);                                              // U00⁻¹ (upper part incl. diagonal used)
+  stage_tile<T>(tiles + 4096, D + (long long)DB * ld + DB, ld, bw1, bw1);             // U11⁻¹
+  stage_tile<T>(tiles + 8192, D + (long long)DB * ld, ld, bw0, bw1);                  // U01
+  if (s > 0) panel_load<T>(m, F + (long long)R1 * ld + R0, ld, cnt, pc);
+  T base = hs_zero<T>();
+  if (tid < cnt) base = w[R0 + tid];
+  if (tid < SB) sv[tid] = tid < pc ? w[R1 + tid] : hs_zero<T>();
+  cp_async_fence_all();
+  __syncthreads();
+  T sum = hs_zero<T>();
+  if (s > 0) sum = panel_reduce<T>(m, sv, red);
+  if (tid < SB) su[tid] = tid < cnt ? hs_sub(base, sum) : hs_zero<T>();
+  __syncthreads();
+  if (bw1 > 0) {
+    {  // block 1 first: y1 = upper(U11⁻¹)·u1
+      const T y = tile_tri_matvec<T>(tiles + 4096, su + DB, bw1, bw1, 2, red);
+      if (tid < bw1) su[DB + tid] = y;
       __syncthreads();
     }
-    if (B0 > 0) {  // (ii) rows above block B inside the super-block: u −= U[:, B]·y_B
-      T acc = hs_zero<T>();
-      if (t < B0) {
-        const int c0 = g * 16, c1 = min(bw, c0 + 16);
-        const T* p = D + (long long)B0 * ld + t;
-#pragma unroll 16
-        for (int c = c0; c < c1; ++c) acc = hs_fma(acc, p[(long long)c * ld], su[B0 + c]);
-      }
-      red[g][t] = acc;
-      __syncthreads();
-      if (g == 0 && t < B0) su[t] = hs_sub(su[t], hs_add(hs_add(red[0][t], red[1][t]), hs_add(red[2][t], red[3][t])));
+    {  // u0 −= U01·y1
+      const T y = tile_tri_matvec<T>(tiles + 8192, su + DB, bw0, bw1, 0, red);
+      if (tid < bw0) su[tid] = hs_sub(su[tid], y);
       __syncthreads();
     }
+  }
+  {  // block 0
+    const T y = tile_tri_matvec<T>(tiles, su, bw0, bw0, 2, red);
+    if (tid < bw0) su[tid] = y;
+    __syncthreads();
   }
   if (tid < cnt) { const T v = su[tid]; w[R0 + tid] = v; xr[gi[R0 + tid]] = v; }
 }
@@ -464,8 +499,8 @@ template <typename T, bool FWD> void launch_big(hs_fac* f, const Level& L, int n
     // rows still to be updated behind (FWD) / above (BWD) the super-block of this step, for the largest front
     const int rest = std::max(0, L.max_ni - (s + 1) * SB);
     dim3 g(nbig, 1 + (rest + SB - 1) / SB, (unsigned)nrhs);
-    if (FWD) k_sv_tri_fwd<T><<<g, TRI_T, 0, st>>>(f->d_fronts, (const T*)f->pool, f->d_gidx, f->d_rperm, x, f->xld, (T*)f->d_work, f->max_level_idx, L.ioff0, L.f0, s);
-    else k_sv_tri_bwd<T><<<g, TRI_T, 0, st>>>(f->d_fronts, (const T*)f->pool, f->d_gidx, x, f->xld, (T*)f->d_work, f->max_level_idx, L.ioff0, L.f0, s);
+    if (FWD) k_sv_tri_fwd<T><<<g, TRI_T, tri_smem<T>(), st>>>(f->d_fronts, (const T*)f->pool, f->d_gidx, f->d_rperm, x, f->xld, (T*)f->d_work, f->max_level_idx, L.ioff0, L.f0, s);
+    else k_sv_tri_bwd<T><<<g, TRI_T, tri_smem<T>(), st>>>(f->d_fronts, (const T*)f->pool, f->d_gidx, x, f->xld, (T*)f->d_work, f->max_level_idx, L.ioff0, L.f0, s);
     ++f->stats.launches_solve;
   }
   CUDA_OK(cudaGetLastError());
@@ -522,6 +557,10 @@ template <typename T> void run_impl(hs_fac* f, int64_t nrhs, void* xv, int which
 void hs_solve_setup() {
   CUDA_OK(cudaFuncSetAttribute(k_trtri_diag<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (DB + 1) * (DB + 1) * (int)sizeof(double)));
   CUDA_OK(cudaFuncSetAttribute(k_trtri_diag<cplx>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (DB + 1) * (DB + 1) * (int)sizeof(cplx)));
+  CUDA_OK(cudaFuncSetAttribute(k_sv_tri_fwd<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tri_smem<double>()));
+  CUDA_OK(cudaFuncSetAttribute(k_sv_tri_bwd<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tri_smem<double>()));
+  CUDA_OK(cudaFuncSetAttribute(k_sv_tri_fwd<cplx>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tri_smem<cplx>()));
+  CUDA_OK(cudaFuncSetAttribute(k_sv_tri_bwd<cplx>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tri_smem<cplx>()));
   CUDA_OK(cudaFuncSetAttribute(k_sv_small_bwd<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CUDA_OK(cudaFuncSetAttribute(k_sv_small_bwd<cplx>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 }

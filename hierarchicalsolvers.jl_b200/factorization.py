@@ -22,7 +22,8 @@ def factor(A, nd: NestedDissection, nd_loc: NDLoc, opts: SolverOptions = None, d
     chkopts(opts)                                 # :7
     if not sp.issparse(A):
         raise TypeError("factor expects a sparse matrix (SparseMatrixCSC)")
-    A = sp.csc_matrix(A)          # no copy when A already is CSC
+    if not (sp.issparse(A) and A.format == "csc"):
+        A = sp.csc_matrix(A)      # a CSC input is used as it is (its cached format flags stay valid between calls)
     if not A.has_canonical_format:
         # duplicate entries would overwrite each other in the device gather (SparseMatrixCSC cannot hold duplicates)
         A = A.copy()

@@ -152,7 +152,8 @@ class FactorNode:
     def refactor(self, A) -> "FactorNode":
         """Numeric re-factorization with new values on the same sparsity and tree."""
         import scipy.sparse as sp
-        A = sp.csc_matrix(A)
+        if not (sp.issparse(A) and A.format == "csc"):
+            A = sp.csc_matrix(A)
         if not A.has_canonical_format:
             A = A.copy()
             A.sum_duplicates()

@@ -42,7 +42,8 @@ def gmres(A, b, Pr: Optional[FactorNode] = None, reltol: float = 1e-9, restart: 
     is uploaded); ``False`` - upload ``A``; ``None`` (default) - reuse the resident copy only if ``A``'s arrays are the
     very objects handed to ``factor``/``refactor`` AND their contents still match the device copy (bitwise checksum),
     otherwise upload."""
-    A = sp.csc_matrix(A)
+    if not (sp.issparse(A) and A.format == "csc"):
+        A = sp.csc_matrix(A)
     n = A.shape[0]
     cx = np.iscomplexobj(A.data) or np.iscomplexobj(b) or (Pr is not None and Pr.dtype == np.complex128)
     dtype = np.complex128 if cx else np.float64

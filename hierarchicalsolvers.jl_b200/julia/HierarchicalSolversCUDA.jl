@@ -10,6 +10,10 @@
 #   perm = postorder(nd); A = permute(A, perm, perm); nd = permuted!(nd, invperm(perm))
 #   F = cufactor(A, nd, nd_loc; swlevel = 0)            # instead of factor(...)
 #   x, ch = gmres(A, b; Pr = F, reltol = 1e-9, restart = 30, log = true, maxiter = 30)
+#
+# To run the reference's own driver unchanged (test/rungmres.jl calls `factor(A, nd, nd_loc; ...)`), call
+# `HierarchicalSolversCUDA.activate!()` once after `using`: it adds a more specific `factor` method for
+# SparseMatrixCSC{Float64/ComplexF64, Int} that routes to `cufactor` (`deactivate!()` removes it again).
 module HierarchicalSolversCUDA
 
 using LinearAlgebra, SparseArrays
@@ -17,7 +21,7 @@ using HierarchicalSolvers
 import LinearAlgebra: ldiv!
 import HierarchicalSolvers: maxrank, isleaf, isbranch
 
-export CuFactorNode, cufactor, noderanks, nested_dissection
+export CuFactorNode, cufactor, noderanks, nested_dissection, hssrank, activate!, deactivate!
 
 const libhsolve = get(ENV, "LIBHSOLVE_CUDA", "libhsolve_cuda")
 
@@ -34,11 +38,19 @@ function check(rc::Int32)
 end
 
 # ---- plain-old-data mirrors of the ABI structs ----------------------------------------------------------------
-struct HsOpts             # SolverOptions, HierarchicalSolvers.jl:30-40
+struct HsOpts             # SolverOptions, HierarchicalSolvers.jl:30-40, followed by the library's extensions (hsolve_cuda.h)
   swlevel::Int64; swsize::Int64; atol::Float64; rtol::Float64; c_tol::Float64
   leafsize::Int64; kest::Int64; stepsize::Int64; verbose::Int32; subtree::Int32
+  hss::Int32; pad0::Int32                         # 1: Schur complements of compressed nodes stored as HSS (the reference's behaviour)
+  sketch_omega::Ptr{Cvoid}; sketch_psi::Ptr{Cvoid} # host-supplied Gaussian test matrices (C_NULL: drawn on the device)
+  sketch_rows::Int64; sketch_cols::Int64; sketch_seed::UInt64
 end
-HsOpts(o::SolverOptions) = HsOpts(o.swlevel, o.swsize, o.atol, o.rtol, o.c_tol, o.leafsize, o.kest, o.stepsize, o.verbose, 0)
+# `sketches = (Ω, Ψ)`: e.g. `Random.seed!(123); Ω = randn(T, nbmax, kmax); Ψ = randn(T, nbmax, kmax)` reproduces a run of the
+# reference that draws the same matrices (test/rungmres.jl:7); the caller keeps them alive during the call (GC.@preserve)
+HsOpts(o::SolverOptions; hss::Bool = true, sketches = nothing, seed::Integer = 123) =
+  HsOpts(o.swlevel, o.swsize, o.atol, o.rtol, o.c_tol, o.leafsize, o.kest, o.stepsize, o.verbose, 0, hss, 0,
+         sketches === nothing ? C_NULL : pointer(sketches[1]), sketches === nothing ? C_NULL : pointer(sketches[2]),
+         sketches === nothing ? 0 : size(sketches[1], 1), sketches === nothing ? 0 : size(sketches[1], 2), UInt64(seed))
 
 struct HsTree
   nnodes::Int64
@@ -80,10 +92,12 @@ mutable struct CuFactorNode{T} <: Factorization{T}
   node::Int                  # post-order id (0-based) of this node, root = nnodes-1
   nd::NestedDissection
   nd_loc::NestedDissection
-  root::Union{CuFactorNode{T}, Nothing}
+  root::Union{CuFactorNode{T}, Nothing}   # the node that owns the handle (nothing for the root itself)
+  lefts::Vector{Int64}                     # post-order child ids (1-based, -1 = none) from `flatten`
+  rights::Vector{Int64}
 end
 Base.eltype(::CuFactorNode{T}) where T = T
-Base.size(F::CuFactorNode) = (F.n, F.n)
+Base.size(F::CuFactorNode) = (getfield(F, :n), getfield(F, :n))
 Base.show(io::IO, F::CuFactorNode) = print(io, "CuFactorNode{$(eltype(F))}")
 
 dtype_code(::Type{Float64}) = Int32(0)
@@ -95,35 +109,59 @@ dtype_code(::Type{ComplexF64}) = Int32(1)
 Drop-in for `factor` (src/factorization.jl:5-11).  Copies `A` and the tree to the GPU and factors there.
 """
 function cufactor(A::SparseMatrixCSC{T,Int}, nd::NestedDissection, nd_loc::NestedDissection,
-                  opts::SolverOptions = SolverOptions(); args...) where T <: Union{Float64, ComplexF64}
+                  opts::SolverOptions = SolverOptions(); hss::Bool = true, sketches = nothing, seed::Integer = 123,
+                  args...) where T <: Union{Float64, ComplexF64}
   opts = copy(opts; args...)
   HierarchicalSolvers.chkopts!(opts)
   t = flatten(nd, nd_loc)
   h = Ref{Ptr{Cvoid}}(C_NULL)
-  GC.@preserve A t begin
+  sketches === nothing || (sketches = (Matrix{T}(sketches[1]), Matrix{T}(sketches[2])))
+  GC.@preserve A t sketches begin
     tree = HsTree(length(t.left), pointer(t.left), pointer(t.right), pointer(t.ip), pointer(t.ii), pointer(t.bp), pointer(t.bi),
                   pointer(t.lip), pointer(t.lii), pointer(t.lbp), pointer(t.lbi), Int32(1))
     rc = ccall((:hs_factor, libhsolve), Int32,
                (Ptr{Cvoid}, Int32, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Cvoid}, Ref{HsTree}, Ref{HsOpts}, Int32, Ref{Ptr{Cvoid}}),
-               context(), dtype_code(T), size(A, 1), A.colptr, A.rowval, A.nzval, tree, HsOpts(opts), Int32(0), h)
+               context(), dtype_code(T), size(A, 1), A.colptr, A.rowval, A.nzval, tree,
+               HsOpts(opts; hss = hss, sketches = sketches, seed = seed), Int32(0), h)
   end
   if rc != HS_OK
     h[] != C_NULL && ccall((:hs_factor_free, libhsolve), Int32, (Ptr{Cvoid},), h[])
     check(rc)
   end
-  F = CuFactorNode{T}(h[], size(A, 1), length(t.left) - 1, nd, nd_loc, nothing)
-  finalizer(F -> ccall((:hs_factor_free, libhsolve), Int32, (Ptr{Cvoid},), F.handle), F)
+  F = CuFactorNode{T}(h[], size(A, 1), length(t.left) - 1, nd, nd_loc, nothing, t.left, t.right)
+  finalizer(F -> ccall((:hs_factor_free, libhsolve), Int32, (Ptr{Cvoid},), getfield(F, :handle)), F)
   return F
+end
+
+# `factor(A, nd, nd_loc, opts; kw...)` itself (src/factorization.jl:5): a method on the concrete matrix types this library
+# handles is more specific than the reference's `SparseMatrixCSC{T}` method, so after activate!() the reference's driver
+# (test/rungmres.jl:32,39) reaches the GPU without an edit.  Defined at run time (extending another package's function on
+# its own types is not allowed while this module precompiles).
+function activate!()
+  @eval HierarchicalSolvers.factor(A::SparseMatrixCSC{T,Int}, nd::HierarchicalSolvers.NestedDissection,
+                                   nd_loc::HierarchicalSolvers.NestedDissection,
+                                   opts::HierarchicalSolvers.SolverOptions = HierarchicalSolvers.SolverOptions();
+                                   args...) where {T <: Union{Float64, ComplexF64}} = cufactor(A, nd, nd_loc, opts; args...)
+  nothing
+end
+function deactivate!()
+  for T in (Float64, ComplexF64)
+    m = which(HierarchicalSolvers.factor, Tuple{SparseMatrixCSC{T,Int}, HierarchicalSolvers.NestedDissection, HierarchicalSolvers.NestedDissection})
+    m.module === @__MODULE__() && Base.delete_method(m)
+  end
+  nothing
 end
 
 # ---- ldiv!  (src/factornode.jl:62-74) -----------------------------------------------------------------------
 # 3-argument forms write into C.  The 2-argument form is genuinely in place here (the reference's allocates and
 # leaves B untouched, factornode.jl:62 — see SURVEY F6); IterativeSolvers' right-preconditioned update relies on it.
 function ldiv!(C::StridedVecOrMat{T}, F::CuFactorNode{T}, B::StridedVecOrMat{T}) where T
-  size(B, 1) == F.n || throw(DimensionMismatch("B has $(size(B,1)) rows, expected $(F.n)"))
-  Bc = Matrix{T}(reshape(B, F.n, :))            # contiguous staging copy (gmres hands in SubArray columns)
+  n = getfield(F, :n)
+  getfield(F, :root) === nothing || throw(ArgumentError("ldiv! is defined on the root of the factor tree"))
+  size(B, 1) == n || throw(DimensionMismatch("B has $(size(B,1)) rows, expected $n"))
+  Bc = Matrix{T}(reshape(B, n, :))            # contiguous staging copy (gmres hands in SubArray columns)
   GC.@preserve Bc check(ccall((:hs_solve, libhsolve), Int32, (Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Int32),
-                              F.handle, size(Bc, 2), Bc, F.n, Bc, F.n, Int32(0)))
+                              getfield(F, :handle), size(Bc, 2), Bc, n, Bc, n, Int32(0)))
   copyto!(C, reshape(Bc, size(C)))
   return C
 end
@@ -132,7 +170,7 @@ Base.:\(F::CuFactorNode{T}, B::StridedVecOrMat{T}) where T = ldiv!(similar(B), F
 
 function maxrank(F::CuFactorNode)             # src/factornode.jl:49-57
   r = Ref{Int64}(0)
-  check(ccall((:hs_maxrank, libhsolve), Int32, (Ptr{Cvoid}, Ref{Int64}), F.handle, r))
+  check(ccall((:hs_maxrank, libhsolve), Int32, (Ptr{Cvoid}, Ref{Int64}), getfield(F, :handle), r))
   return Int(r[])
 end
 
@@ -195,9 +233,34 @@ function Base.getproperty(F::CuFactorNode{T}, s::Symbol) where T
   elseif s === :bnd;      return getfield(F, :nd).bnd
   elseif s === :int_loc;  return getfield(F, :nd_loc).int
   elseif s === :bnd_loc;  return getfield(F, :nd_loc).bnd
+  elseif s === :left || s === :right
+    # children (src/factornode.jl:21-22) as lazy views on the same device factorization: same handle, the child's node id
+    # and its sub-trees of (nd, nd_loc); the root is kept alive through `root` so the finalizer cannot run under a view
+    c = (s === :left ? getfield(F, :lefts) : getfield(F, :rights))[getfield(F, :node) + 1]
+    c < 0 && return nothing
+    nd, ndl = getfield(F, :nd), getfield(F, :nd_loc)
+    owner = something(getfield(F, :root), F)
+    return CuFactorNode{T}(getfield(F, :handle), getfield(F, :n), Int(c) - 1, s === :left ? nd.left : nd.right,
+                           s === :left ? ndl.left : ndl.right, owner, getfield(F, :lefts), getfield(F, :rights))
   else
     return getfield(F, s)
   end
+end
+
+# hssrank(F.S) of a compressed node (src/factornode.jl:53); 0 when S is dense
+function hssrank(F::CuFactorNode)
+  n = Ref{Int64}(0)
+  check(ccall((:hs_hss_info, libhsolve), Int32, (Ptr{Cvoid}, Int64, Ref{Int64}, Ptr{Int64}), getfield(F, :handle), getfield(F, :node), n, C_NULL))
+  n[] == 0 && return 0
+  info = zeros(Int64, 8, n[])
+  check(ccall((:hs_hss_info, libhsolve), Int32, (Ptr{Cvoid}, Int64, Ref{Int64}, Ptr{Int64}), getfield(F, :handle), getfield(F, :node), n, info))
+  r = 0
+  for t in 1:n[]
+    info[8, t] == 1 && continue                       # leaf
+    l, rgt = info[3, t] + 1, info[4, t] + 1
+    r = max(r, info[5, l], info[6, l], info[5, rgt], info[6, rgt])   # dimensions of B12 / B21
+  end
+  return Int(r)
 end
 isleaf(F::CuFactorNode) = HierarchicalSolvers.isleaf(getfield(F, :nd))
 isbranch(F::CuFactorNode) = HierarchicalSolvers.isbranch(getfield(F, :nd))

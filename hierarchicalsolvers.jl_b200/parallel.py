@@ -456,6 +456,23 @@ class DistributedFactor:
         self.ldiv_device(x)
         return self.eng.to_host(x)
 
+    def free(self):
+        """Release the device factorizations and exchange buffers of this object now (they are otherwise kept until the
+        engine goes away): needed before a second factorization of a problem that fills most of the HBM."""
+        for h in self.local_handles():
+            if h is not None and h in self.eng.handles:
+                self.eng.handles.remove(h)
+                _lib.lib.hs_factor_free(h)
+        self.h_sub = None
+        if self.mode == "replicated":
+            self.h_top = None
+            self.schur = None
+        else:
+            for st in self.steps:
+                st["h"] = None
+            self.S = {}
+        self.eng._dev_csc = None     # the resident matrix belonged to the first factorization
+
     def local_handles(self):
         """Factorization handles this rank holds: its subtree and the fronts above the cut it owns."""
         if self.mode == "replicated":

@@ -51,7 +51,10 @@ def _both(hs, orc, prob, keep_schur=False, **opts):
     return Ap, Fo, F
 
 
-@pytest.mark.parametrize("kind,shape,tol", [("poisson", (65, 65), 1e-2), ("poisson", (65, 65), 1e-5),
+# 1e-6 is the reference's default atol = rtol (HierarchicalSolvers.jl:45-46), halved to 5e-7 for the Gauss transforms
+# (factorization.jl:99-100): within a factor 5 of the Gram-matrix floor of the library's pivoted QR, still rank-exact
+@pytest.mark.parametrize("kind,shape,tol", [("poisson", (65, 65), 1e-2), ("poisson", (65, 65), 1e-5), ("poisson", (65, 65), 1e-6),
+                                            ("helmholtz", (65, 65), 1e-6),
                                             ("helmholtz", (65, 65), 1e-3), ("poisson", (12, 11, 10), 1e-3)])
 def test_compressed_nodes_match_oracle(hs, orc, kind, shape, tol):
     import hs_oracle_hss as oh

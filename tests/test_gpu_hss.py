@@ -180,3 +180,31 @@ def test_hss_children_methods_match_oracle(hs, orc, kind, shape, tol):
     xs, ch = hs.gmres(sp.csc_matrix(Ap), b, Pr=F, reltol=1e-9, restart=30, maxiter=30, log=True)
     assert ch.isconverged == convo and ch.iters == len(reso)
     assert np.allclose(np.asarray(ch.resnorm), np.asarray(reso), rtol=1e-5, atol=1e-12 * np.linalg.norm(b))
+
+
+def test_baseline_config2_standin_hss(hs, orc):
+    """BASELINE config 2 (poisson2d_p1_h128_nmax100 with the option set of test/rungmres.jl:39: swlevel = -2, atol = rtol =
+    1e-2, kest = 200, stepsize = 100, leafsize = bsz = 120) on the 129x129 stand-in, HSS Schur complements as in the
+    reference.  rungmres.jl's swsize = 4*bsz = 480 never triggers on a 5-point grid (largest boundary 160), so
+    swsize = 64; coefficients are perturbed because exactly tied column norms have no canonical pivot order.  north_star:
+    with the same sketch matrices the GMRES iteration count and the residual history must match."""
+    import hs_hss as H
+    import hs_oracle_hss as oh
+    prob = _perturbed(hs, (129, 129), "poisson", nmax=100)
+    Om, Ps = _sketches(prob, cols=320)
+    opts = dict(swlevel=-2, swsize=64, atol=1e-2, rtol=1e-2, kest=200, stepsize=100, leafsize=120, sketches=(Om, Ps))
+    Ap, Fo, F = _both(hs, orc, prob, **opts)
+    ranks_o = oh.node_ranks(Fo)
+    assert [F.node(k).ranks() for k in range(len(ranks_o))] == ranks_o
+    assert hs.maxrank(F) == orc.maxrank(Fo) > 0
+    nh = 0
+    for k, no in enumerate(orc.nodes_postorder(Fo)):
+        if isinstance(no.S, H.HssMatrix) and not no.S.leaf:
+            nh += 1
+            assert F.node(k).hssrank() == H.hssrank(no.S)
+    assert nh > 0
+    b = prob.b
+    _, reso, convo = orc.gmres(Ap, b, Pr=lambda v: orc.ldiv(Fo, v), reltol=1e-9, restart=30, maxiter=30)
+    xs, ch = hs.gmres(sp.csc_matrix(Ap), b, Pr=F, reltol=1e-9, restart=30, maxiter=30, log=True)
+    assert ch.isconverged == convo and ch.iters == len(reso)
+    assert np.allclose(np.asarray(ch.resnorm), np.asarray(reso), rtol=1e-4, atol=1e-12 * np.linalg.norm(b))

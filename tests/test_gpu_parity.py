@@ -22,8 +22,11 @@ def both(hs, orc, shape, kind, nmax=100):
     return prob, Ap, F, Fo
 
 
+# (65, 65) / (129, 129) with nmax = 100 are the stand-ins of BASELINE configs 1-3 (poisson2d / helmholtz2d p1 h64 / h128, whose
+# .mat fixtures are stripped from the reference checkout)
 CASES = [("poisson", (33, 33), 40), ("helmholtz", (33, 33), 40), ("poisson", (65, 65), 100),
-         ("helmholtz", (65, 65), 100), ("poisson", (9, 8, 7), 60), ("helmholtz", (10, 9, 8), 60),
+         ("helmholtz", (65, 65), 100), ("poisson", (129, 129), 100), ("helmholtz", (129, 129), 100),
+         ("poisson", (9, 8, 7), 60), ("helmholtz", (10, 9, 8), 60),
          ("poisson", (37, 3), 20), ("poisson", (4, 4), 100)]
 
 
