@@ -193,6 +193,9 @@ struct hs_fac {
   void* d_sk = nullptr;        // sketch matrices Ω, Ψ on the device (sk_rows × sk_cols each, Ψ behind Ω)
   long long sk_rows = 0, sk_cols = 0;
   int* d_hperm = nullptr;      // perm of every HSS front, concatenated
+  // device scratch of the HSS construction is recycled through this free list (cudaMalloc / cudaFree per adaptive round
+  // and per level cost more than the kernels they serve); released with the factorization
+  std::vector<std::pair<void*, size_t>> dev_cache;
   int nfr = 0;                // number of dense front descriptors; thin descriptors follow at nfr + fi
   bool transient_schur = true; // dense slots of compressed fronts are recycled two levels up
   long long nvirt = 0;        // virtual slots appended to the solution vector
@@ -233,6 +236,7 @@ struct hs_fac {
     cudaFree(d_cws); cudaFree(d_cstate); cudaFree(d_cint); cudaFree(d_runs); cudaFree(d_lr); cudaFree(d_gd);
     for (auto& c : clevels) { cudaFree(c.side); cudaFree(c.hss_store); cudaFree(c.xws); }
     cudaFree(d_sk); cudaFree(d_hperm);
+    for (auto& b : dev_cache) cudaFree(b.first);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
   }

@@ -445,18 +445,52 @@ struct Bump {
   long long take(long long n) { const long long o = off; off += up32(std::max<long long>(n, 1)); return o; }
 };
 
-template <typename V> struct DevVec {   // small helper: device copy of a host vector
+// recycled device scratch (hs_fac::dev_cache): smallest cached block that fits and is not more than 4x too large
+void* cache_take(hs_fac* f, size_t bytes, size_t* got) {
+  bytes = std::max<size_t>(bytes, 256);
+  int best = -1;
+  for (int i = 0; i < (int)f->dev_cache.size(); ++i) {
+    const size_t c = f->dev_cache[i].second;
+    if (c >= bytes && c <= 4 * bytes + (1u << 20) && (best < 0 || c < f->dev_cache[best].second)) best = i;
+  }
+  if (best >= 0) {
+    void* p = f->dev_cache[best].first;
+    *got = f->dev_cache[best].second;
+    f->dev_cache.erase(f->dev_cache.begin() + best);
+    return p;
+  }
+  const size_t want = bytes + bytes / 4;   // head room: the next round / level usually asks for a little more
+  void* p = nullptr;
+  if (cudaMalloc(&p, want) != cudaSuccess) {
+    // out of memory with blocks of the wrong size parked in the cache: release them and try once more
+    cudaGetLastError();
+    cudaStreamSynchronize(f->ctx->stream);
+    for (auto& b : f->dev_cache) cudaFree(b.first);
+    f->dev_cache.clear();
+    CUDA_OK(cudaMalloc(&p, want));
+  }
+  *got = want;
+  return p;
+}
+void cache_give(hs_fac* f, void* p, size_t bytes) { if (p) f->dev_cache.emplace_back(p, bytes); }
+
+template <typename V> struct DevVec {   // small helper: device copy of a host vector (scratch from the cache)
+  hs_fac* f;
   V* d = nullptr;
-  size_t cap = 0;
-  ~DevVec() { cudaFree(d); }
+  size_t bytes = 0;
+  explicit DevVec(hs_fac* f_) : f(f_) {}
+  DevVec(const DevVec&) = delete;
+  ~DevVec() { cache_give(f, d, bytes); }
   void upload(const std::vector<V>& h, cudaStream_t st) {
-    if (h.size() > cap) { cudaFree(d); d = nullptr; cap = 0; CUDA_OK(cudaMalloc((void**)&d, h.size() * sizeof(V))); cap = h.size(); }
+    if (h.size() * sizeof(V) > bytes) { cache_give(f, d, bytes); d = nullptr; bytes = 0; d = (V*)cache_take(f, h.size() * sizeof(V), &bytes); }
     if (!h.empty()) CUDA_OK(cudaMemcpyAsync(d, h.data(), h.size() * sizeof(V), cudaMemcpyHostToDevice, st));
   }
 };
 
 struct Round {
+  hs_fac* f = nullptr;
   void* ws = nullptr;
+  size_t ws_bytes = 0, ints_bytes = 0;
   int* ints = nullptr;
   int nints = 0;
   std::vector<int> hidx;     // index into f->hss of every front of this round
@@ -464,7 +498,7 @@ struct Round {
   std::vector<HFront> fr;
   std::vector<HNode> nd;
   std::vector<int> h_ints;   // ranks / flags read back
-  ~Round() { cudaFree(ws); cudaFree(ints); }
+  ~Round() { if (f) { cache_give(f, ws, ws_bytes); cache_give(f, ints, ints_bytes); } }
 };
 
 template <typename T> long long rel(const hs_fac* f, const void* p) {
@@ -497,6 +531,7 @@ template <typename T> void ensure_sketch(hs_fac* f, long long rows_need, long lo
 
 template <typename T> Round* make_round(hs_fac* f, const std::vector<int>& act) {
   std::unique_ptr<Round> R(new Round());
+  R->f = f;
   Bump B;
   int nints = 0;
   auto take_int = [&](int n) { const int o = nints; nints += std::max(n, 1); return o; };
@@ -569,8 +604,8 @@ template <typename T> Round* make_round(hs_fac* f, const std::vector<int>& act) 
     R->fr.push_back(F);
   }
   cudaStream_t st = f->ctx->stream;
-  CUDA_OK(cudaMalloc(&R->ws, (size_t)std::max<long long>(B.off, 32) * sizeof(T)));
-  CUDA_OK(cudaMalloc((void**)&R->ints, (size_t)std::max(nints, 1) * sizeof(int)));
+  R->ws = cache_take(f, (size_t)std::max<long long>(B.off, 32) * sizeof(T), &R->ws_bytes);
+  R->ints = (int*)cache_take(f, (size_t)std::max(nints, 1) * sizeof(int), &R->ints_bytes);
   R->nints = nints;
   CUDA_OK(cudaMemsetAsync(R->ws, 0, (size_t)std::max<long long>(B.off, 32) * sizeof(T), st));
   CUDA_OK(cudaMemsetAsync(R->ints, 0, (size_t)std::max(nints, 1) * sizeof(int), st));
@@ -613,8 +648,8 @@ template <typename T> void run_round(hs_fac* f, Round& R) {
   for (const HNode& N : R.nd) { max_mcat = std::max(max_mcat, N.mcat); max_cap = std::max(max_cap, N.cap); }
   ensure_sketch<T>(f, rows_need, max_k);
   g_hclk.start(st);
-  DevVec<HFront> dfr;
-  DevVec<HNode> dnd;
+  DevVec<HFront> dfr(f);
+  DevVec<HNode> dnd(f);
   dfr.upload(R.fr, st);
   dnd.upload(R.nd, st);
   T* pool = (T*)f->pool;
@@ -645,7 +680,7 @@ template <typename T> void run_round(hs_fac* f, Round& R) {
     }
     const double cx = f->dtype == HS_C64 ? 4.0 : 1.0;
     for (const GemmDesc& d : gd) f->stats.sketch_flops += cx * 2.0 * d.M * (double)d.N * d.K;
-    DevVec<GemmDesc> dgd;
+    DevVec<GemmDesc> dgd(f);
     dgd.upload(gd, st);
     const int mm = std::max(max_nb, max_k), nn = std::max(max_nb, max_k);
     hs_gen_gemm(f, dgd.d, n1, mm, nn);
@@ -665,17 +700,18 @@ template <typename T> void run_round(hs_fac* f, Round& R) {
   std::vector<int> flat, off(max_height + 2, 0);
   for (int h = 0; h <= max_height; ++h) { off[h] = (int)flat.size(); flat.insert(flat.end(), byh[h].begin(), byh[h].end()); }
   off[max_height + 1] = (int)flat.size();
-  DevVec<int> dlist;
+  DevVec<int> dlist(f);
   dlist.upload(flat, st);
   size_t maxl = 1;
   for (auto& v : byh) maxl = std::max(maxl, v.size());
-  GemmDesc* dg = nullptr;
-  CUDA_OK(cudaMalloc((void**)&dg, maxl * 4 * sizeof(GemmDesc)));
+  size_t dg_bytes = 0;
+  GemmDesc* dg = (GemmDesc*)cache_take(f, maxl * 4 * sizeof(GemmDesc), &dg_bytes);
+  struct GiveBack { hs_fac* f; void* p; size_t b; ~GiveBack() { cache_give(f, p, b); } } dg_guard{f, dg, dg_bytes};
   const int kcap = even_up(max_k), mcap = max_mcat + 2;
   const size_t smem0 = (((size_t)kcap * sizeof(T) + (size_t)mcap * (sizeof(double) + sizeof(int)) + 15) & ~(size_t)15);
-  if (smem0 > 200 * 1024) { cudaFree(dg); throw hs_error(HS_ESIZE, "randomized HSS construction: sample count / block size exceed the shared-memory budget of the pivoted QR"); }
+  if (smem0 > 200 * 1024) { throw hs_error(HS_ESIZE, "randomized HSS construction: sample count / block size exceed the shared-memory budget of the pivoted QR"); }
   const double atol = f->opts.atol, rtol = f->opts.rtol;   // factorization.jl:110 passes atol, rtol unhalved
-  try {
+  {
     for (int h = 0; h <= max_height; ++h) {
       const int nl = (int)byh[h].size();
       if (nl == 0) continue;
@@ -707,8 +743,7 @@ template <typename T> void run_round(hs_fac* f, Round& R) {
     CUDA_OK(cudaMemcpyAsync(R.h_ints.data(), R.ints, (size_t)std::max(R.nints, 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));
     g_hclk.tick(5, st);
-  } catch (...) { cudaFree(dg); throw; }
-  cudaFree(dg);
+  }
 }
 
 // ---- expansion: the dense matrix a stored HSS form represents ----------------------------------------------------------
@@ -759,9 +794,9 @@ template <typename T> void expand(hs_fac* f, const std::vector<int>& hids, bool 
       }
     }
   }
-  void* ws = nullptr;
-  CUDA_OK(cudaMalloc(&ws, (size_t)std::max<long long>(B.off, 32) * sizeof(T)));
-  struct Free { void* p; ~Free() { cudaFree(p); } } fr_{ws};
+  size_t ws_bytes = 0;
+  void* ws = cache_take(f, (size_t)std::max<long long>(B.off, 32) * sizeof(T), &ws_bytes);
+  struct GiveBack { hs_fac* f; void* p; size_t b; ~GiveBack() { cache_give(f, p, b); } } fr_{f, ws, ws_bytes};
   CUDA_OK(cudaMemsetAsync(ws, 0, (size_t)std::max<long long>(B.off, 32) * sizeof(T), st));
   const long long base = rel<T>(f, ws);
   std::vector<CopyDesc> cds;
@@ -829,13 +864,13 @@ template <typename T> void expand(hs_fac* f, const std::vector<int>& hids, bool 
     if (v.empty()) return;
     int mM = 0, mN = 0;
     for (const GemmDesc& d : v) { mM = std::max(mM, d.M); mN = std::max(mN, d.N); }
-    DevVec<GemmDesc> dv;
+    DevVec<GemmDesc> dv(f);
     dv.upload(v, st);
     hs_gen_gemm(f, dv.d, (int)v.size(), mM, mN);
     CUDA_OK(cudaStreamSynchronize(st));
   };
   if (!cds.empty()) {
-    DevVec<CopyDesc> dc;
+    DevVec<CopyDesc> dc(f);
     dc.upload(cds, st);
     k_copy_desc<T><<<dim3((unsigned)cds.size(), 4), 256, 0, st>>>(dc.d, pool);
     CUDA_OK(cudaGetLastError());
@@ -846,7 +881,7 @@ template <typename T> void expand(hs_fac* f, const std::vector<int>& hids, bool 
   run_gemms(gT);
   run_gemms(gP);
   if (to_slot) {
-    DevVec<ScatterDesc> ds;
+    DevVec<ScatterDesc> ds(f);
     ds.upload(sds, st);
     k_hss_scatter<T><<<dim3((unsigned)sds.size(), std::min(max_m, 256)), 256, 0, st>>>(ds.d, pool, f->d_hperm);
     CUDA_OK(cudaGetLastError());
@@ -989,7 +1024,7 @@ template <typename T> void build_impl(hs_fac* f, CompLevel& C) {
     f->stats.hss_nodes += nn;
   }
   if (!cds.empty()) {
-    DevVec<CopyDesc> dc;
+    DevVec<CopyDesc> dc(f);
     dc.upload(cds, st);
     k_copy_desc<T><<<dim3((unsigned)cds.size(), 2), 256, 0, st>>>(dc.d, (T*)f->pool);
     CUDA_OK(cudaGetLastError());
@@ -1083,7 +1118,7 @@ void hs_hss_plan(hs_fac* f) {
 void hs_hss_copy(hs_fac* f, const std::vector<CopyDesc>& blocks) {
   if (blocks.empty()) return;
   cudaStream_t st = f->ctx->stream;
-  DevVec<CopyDesc> dc;
+  DevVec<CopyDesc> dc(f);
   dc.upload(blocks, st);
   if (f->dtype == HS_F64) k_copy_desc<double><<<dim3((unsigned)blocks.size(), 4), 256, 0, st>>>(dc.d, (double*)f->pool);
   else k_copy_desc<cplx><<<dim3((unsigned)blocks.size(), 4), 256, 0, st>>>(dc.d, (cplx*)f->pool);
