@@ -299,11 +299,12 @@ class DistributedFactor:
         # Compression (factorization.jl:8,15) is decided by the level in the WHOLE tree: resolve swlevel here and hand
         # every partial tree the level budget that is left below its own root.
         lev = np.zeros(nd.nnodes, dtype=np.int64)
-        lev[nd.nnodes - 1] = 1
-        for k in range(nd.nnodes - 1, -1, -1):          # post-order numbering: parents after children
-            for c in (int(nd.left[k]), int(nd.right[k])):
-                if c >= 0:
-                    lev[c] = lev[k] + 1
+        cur, d = np.array([nd.nnodes - 1], dtype=np.int64), 1
+        left_a, right_a = np.asarray(nd.left, dtype=np.int64), np.asarray(nd.right, dtype=np.int64)
+        while cur.size:                                  # one vectorised step per tree level
+            lev[cur] = d
+            kids = np.concatenate([left_a[cur], right_a[cur]])
+            cur, d = kids[kids >= 0], d + 1
         self._level = lev
         sw = int(opts.swlevel)
         self._sw = max(int(lev.max()) + sw, 0) if sw < 0 else sw
