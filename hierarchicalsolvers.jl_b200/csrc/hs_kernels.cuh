@@ -167,9 +167,22 @@ __global__ void __launch_bounds__(128) k_swap_trsm(const Front* __restrict__ fro
   T* F = pool + fr.off;
   __shared__ T sL[W * W];
   __shared__ int spiv[W];
-  for (int e = threadIdx.x; e < W * W; e += blockDim.x) {
-    const int i = e % W, k = e / W;
-    sL[e] = (i < wc && k < wc && i > k) ? F[(long long)(j0 + k) * fr.ld + (j0 + i)] : hs_zero<T>();
+  {
+    // all loads of the W×W block are issued before the first store (a rolled loop pays one L2 latency per element:
+    // ~20 µs per launch, most of what these launches cost in round 1)
+    constexpr int NT = 128, NE = (W * W + NT - 1) / NT;
+    T tmp[NE];
+#pragma unroll
+    for (int q = 0; q < NE; ++q) {
+      const int e = threadIdx.x + q * NT;
+      const int i = e % W, k = e / W;
+      tmp[q] = (e < W * W && i < wc && k < wc && i > k) ? F[(long long)(j0 + k) * fr.ld + (j0 + i)] : hs_zero<T>();
+    }
+#pragma unroll
+    for (int q = 0; q < NE; ++q) {
+      const int e = threadIdx.x + q * NT;
+      if (e < W * W) sL[e] = tmp[q];
+    }
   }
   if (threadIdx.x < W) spiv[threadIdx.x] = threadIdx.x < wc ? ipiv[fr.ioff + j0 + threadIdx.x] : 0;
   __syncthreads();

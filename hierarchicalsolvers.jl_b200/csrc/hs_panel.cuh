@@ -320,14 +320,22 @@ __global__ void __launch_bounds__(128) k_trsm_rows(const Front* __restrict__ fro
   if ((int)(blockIdx.y * blockDim.x) >= nrows) return;
   T* F = pool + fr.off;
   __shared__ T sU[W * W];   // sU[k·W + c] = U[k, c] for k < c, 1/U[c, c] on the diagonal
-  for (int e = threadIdx.x; e < W * W; e += blockDim.x) {
-    const int k = e / W, c = e % W;
-    T v = hs_zero<T>();
-    if (k < wc && c < wc && k <= c) {
-      v = F[(long long)(j0 + c) * fr.ld + (j0 + k)];
-      if (k == c) v = hs_recip_pivot(v);
+  {
+    // consecutive threads read consecutive rows of a column (coalesced), every load issued before the first use
+    constexpr int NT = 128, NE = (W * W + NT - 1) / NT;
+    T tmp[NE];
+#pragma unroll
+    for (int q = 0; q < NE; ++q) {
+      const int e = threadIdx.x + q * NT;
+      const int k = e % W, c = e / W;
+      tmp[q] = (e < W * W && k < wc && c < wc && k <= c) ? F[(long long)(j0 + c) * fr.ld + (j0 + k)] : hs_zero<T>();
     }
-    sU[e] = v;
+#pragma unroll
+    for (int q = 0; q < NE; ++q) {
+      const int e = threadIdx.x + q * NT;
+      const int k = e % W, c = e / W;
+      if (e < W * W) sU[k * W + c] = (k == c && k < wc) ? hs_recip_pivot(tmp[q]) : tmp[q];
+    }
   }
   __syncthreads();
   const int r = blockIdx.y * blockDim.x + threadIdx.x;

@@ -49,9 +49,20 @@ __global__ void __launch_bounds__(128) k_trtri_diag(const Front* __restrict__ fr
   T* G = pool + fr.off + (long long)b0 * fr.ld + b0;
   const long long ld = fr.ld;
   const int tid = threadIdx.x;
-  for (int e = tid; e < db * db; e += blockDim.x) {
-    const int i = e % db, j = e / db;
-    S[j * LDS + i] = G[(long long)j * ld + i];
+  {
+    // the whole block is requested before the first shared-memory store (a rolled loop pays one latency per element)
+    constexpr int NE = DB * DB / 128;
+    T tmp[NE];
+#pragma unroll
+    for (int q = 0; q < NE; ++q) {
+      const int e = tid + q * 128;
+      tmp[q] = e < db * db ? G[(long long)(e / db) * ld + (e % db)] : hs_zero<T>();
+    }
+#pragma unroll
+    for (int q = 0; q < NE; ++q) {
+      const int e = tid + q * 128;
+      if (e < db * db) S[(e / db) * LDS + (e % db)] = tmp[q];
+    }
   }
   __syncthreads();
   // all lanes walk the same (i, k) pairs: S[k,i] is a broadcast read, X[.,j] is private to the lane
@@ -544,7 +555,16 @@ template <typename T> void run_impl(hs_fac* f, int64_t nrhs, void* xv, int which
     }
     if (nf - nbig > 0) {
       dim3 g(nf - nbig, (unsigned)nrhs);
-      const size_t sm = (size_t)std::max(L.max_nb, 1) * sizeof(T);
+      // shared-memory staging of x[bnd]: sized by the small fronts that do eliminate something (external leaves of the
+      // subtree-per-GPU top trees have ni = 0 and boundaries of 10^4 rows: they return at once and must not size it)
+      size_t sm = (size_t)std::max(L.max_nb, 1) * sizeof(T);
+      if (sm > 48 * 1024) {
+        int mnb = 1;
+        for (int i = L.f0 + nbig; i < L.f1; ++i)
+          if (f->fronts[i].ni > 0) mnb = std::max(mnb, f->fronts[i].n - f->fronts[i].ni);
+        sm = (size_t)mnb * sizeof(T);
+        if (sm > 200 * 1024) throw hs_error(HS_ESIZE, "tree solve: a front with at most 64 pivot rows has a boundary too long for the small-front kernel");
+      }
       k_sv_small_bwd<T><<<g, NTH, sm, st>>>(f->d_fronts, pool, f->d_gidx, x, f->xld, L.f0 + nbig);
       ++s.launches_solve;
     }

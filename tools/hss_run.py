@@ -11,7 +11,9 @@ swsize = int(sys.argv[3]) if len(sys.argv) > 3 else 128
 tol = float(sys.argv[4]) if len(sys.argv) > 4 else 1e-5
 leaf = int(sys.argv[5]) if len(sys.argv) > 5 else 32
 hss = int(sys.argv[6]) if len(sys.argv) > 6 else 1
-prob = hs.grid_problem((grid, grid), kind, nmax=100)
+dim3 = kind.endswith("3d")
+kind = kind.replace("3d", "")
+prob = hs.grid_problem((grid, grid, grid) if dim3 else (grid, grid), kind, nmax=100)
 Ap, nd, nd_loc, perm = hs.prepare(prob.A, prob.elim_tree)
 Ap.sort_indices()
 b = prob.b
