@@ -316,7 +316,16 @@ DEFAULT_WORKLOAD = True
 
 def gemm_roofline(stp, peak, peak_src):
     gemm_tf = stp["gemm_flops"] / (stp["ms_gemm"] * 1e-3) / 1e12 if stp["ms_gemm"] > 0 else 0.0
-    return {"kernel": "k_gemm (FP64 DMMA m8n8k4 Schur/trailing update)", "bound": "tensor", "achieved": gemm_tf,
+    split = None
+    if stp.get("ms_gemm_big", 0) > 0 and stp["ms_gemm"] > stp["ms_gemm_big"]:
+        big_tf = stp["gemm_flops_big"] / (stp["ms_gemm_big"] * 1e-3) / 1e12
+        sm_tf = (stp["gemm_flops"] - stp["gemm_flops_big"]) / ((stp["ms_gemm"] - stp["ms_gemm_big"]) * 1e-3) / 1e12
+        split = {"trailing_updates_K_outer_block": {"tflops": big_tf, "frac": big_tf / peak, "ms": stp["ms_gemm_big"],
+                                                    "flops_share": stp["gemm_flops_big"] / max(stp["gemm_flops"], 1.0)},
+                 "in_block_updates_K_panel_width": {"tflops": sm_tf, "frac": sm_tf / peak, "ms": stp["ms_gemm"] - stp["ms_gemm_big"],
+                                                    "note": "launches of a few CTAs, bounded by pipeline fill + C-tile epilogue; they overlap the trailing "
+                                                            "updates on the look-ahead stream outside profile mode"}}
+    return {"split": split,"kernel": "k_gemm (FP64 DMMA m8n8k4 Schur/trailing update)", "bound": "tensor", "achieved": gemm_tf,
             "peak": peak, "unit": "TFLOP/s", "frac": gemm_tf / peak,
             "traffic": ncu_traffic("k_gemm") if DEFAULT_WORKLOAD else None, "traffic_unit": "bytes per launch (ncu, all launches averaged)",
             "peak_source": peak_src,
@@ -404,7 +413,7 @@ def run_distributed(args, hs, torch, world, rank, local_rank, Ap, nd, nd_loc, b,
     sts = [eng.stats(h) for h in DF.local_handles()]
     stp = dict(sts[0])
     for k in ("gemm_flops", "ms_gemm", "gemm_launches", "ms_assemble", "ms_small", "ms_panel", "ms_trsm", "ms_solve_prep",
-              "solve_bytes", "front_bytes"):
+              "solve_bytes", "front_bytes", "gemm_flops_big", "ms_gemm_big"):
         stp[k] = sum(st[k] for st in sts)
     peak, peak_src = fp64_peak(b.dtype == np.complex128)
     e2e = None

@@ -51,7 +51,7 @@ class hs_stats_t(C.Structure):
                 ("panel_launches", C.c_int64), ("ms_extend_add", C.c_double), ("ms_small", C.c_double), ("ms_solve_prep", C.c_double),
                 ("ms_compress", C.c_double), ("lowrank_bytes", C.c_double),
                 ("ms_hss", C.c_double), ("hss_bytes", C.c_double), ("hss_maxrank", C.c_int64), ("hss_rounds", C.c_int64),
-                ("hss_nodes", C.c_int64), ("sketch_flops", C.c_double)]
+                ("hss_nodes", C.c_int64), ("sketch_flops", C.c_double), ("gemm_flops_big", C.c_double), ("ms_gemm_big", C.c_double)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

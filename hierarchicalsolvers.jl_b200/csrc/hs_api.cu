@@ -214,10 +214,26 @@ template <typename T> static void factor_level(hs_fac* f, const Level& L) {
   };
   auto gemm = [&](int nact, int J0, int j0, int mode, int mrows, int mcols, cudaStream_t stream) {
     if (nact <= 0 || mrows <= 0 || mcols <= 0) return;
-    PhaseTimer t(f, &f->stats.ms_gemm);
-    dim3 grid(nact, (mrows + Cfg::TM - 1) / Cfg::TM + 1, (mcols + Cfg::TN - 1) / Cfg::TN);
-    k_gemm<T><<<grid, gemm_threads<T>(), smem_gemm, stream>>>(f->d_fronts, (T*)f->pool, L.f0, J0, j0, NB, W, mode, nullptr);
-    CUDA_OK(cudaGetLastError());
+    const bool big = mode == 1 || mode >= 3;
+    if (big) {   // flops of this trailing update, for the big / in-block split of the GEMM roofline
+      const double cxf = f->dtype == HS_C64 ? 4.0 : 1.0;
+      for (int i = L.f0; i < L.f0 + nact; ++i) {
+        const Front& fr = f->fronts[i];
+        if (fr.ni <= J0) continue;
+        const int BE = std::min(J0 + NB, fr.ni), BE2 = std::min(BE + NB, fr.ni);
+        const double rows = fr.n - BE, cols = mode == 1 ? fr.n - BE : (mode == 3 ? BE2 - BE : fr.n - BE2);
+        f->stats.gemm_flops_big += cxf * 2.0 * rows * cols * (BE - J0);
+      }
+    }
+    double dt = 0;
+    {
+      PhaseTimer t(f, &dt);
+      dim3 grid(nact, (mrows + Cfg::TM - 1) / Cfg::TM + 1, (mcols + Cfg::TN - 1) / Cfg::TN);
+      k_gemm<T><<<grid, gemm_threads<T>(), smem_gemm, stream>>>(f->d_fronts, (T*)f->pool, L.f0, J0, j0, NB, W, mode, nullptr);
+      CUDA_OK(cudaGetLastError());
+    }
+    f->stats.ms_gemm += dt;
+    if (big) f->stats.ms_gemm_big += dt;
     ++f->stats.gemm_launches;
     ++f->stats.launches_factor;
   };
@@ -319,6 +335,7 @@ template <typename T> static void numeric(hs_fac* f) {
   s.launches_factor = 0;
   s.gemm_launches = s.panel_launches = 0;
   s.gemm_flops = 0;
+  s.gemm_flops_big = 0; s.ms_gemm_big = 0;
   CUDA_OK(cudaEventRecord(f->ev0, st));
   CUDA_OK(cudaMemsetAsync(f->d_info, 0, 4 * sizeof(int), st));
   for (size_t li = 0; li < f->levels.size(); ++li) {

@@ -388,6 +388,146 @@ __global__ void __launch_bounds__(256) k_hss_qrcp(const HNode* __restrict__ node
   }
 }
 
+// Warp-per-problem variant of the interpolative decomposition for the SMALL sample blocks — leaves and the lower HSS levels,
+// where a block is a few dozen columns by a few dozen samples and there are tens of thousands of them per tree level: one
+// warp per (HSS node, side), 4 per CTA, the scratch copy in shared memory with an odd pitch (lane l owns columns l, l+32,
+// l+64, l+96: conflict-free), no block-wide barrier anywhere — the 256-thread kernel above spends most of its time in the
+// three __syncthreads per pivot step.  No column swaps: a `done` mask marks the pivots, the pivot order is recorded.
+// Same arithmetic, same truncation rule, same outputs as k_hss_qrcp.
+constexpr int QW_WARPS = 4;
+template <typename T>
+__global__ void __launch_bounds__(QW_WARPS * 32) k_hss_qrcp_warp(const HNode* __restrict__ nodes, const int* __restrict__ list, int nitems,
+                                                                  const HFront* __restrict__ fronts, T* __restrict__ pool,
+                                                                  int* __restrict__ ints, double atol, double rtol, int wcapw, int kcap, int mcap) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int item = blockIdx.x * QW_WARPS + warp;
+  if (item >= nitems) return;
+  const HNode nd = nodes[list[item >> 1]];
+  if (nd.parent < 0) return;
+  const int s = item & 1;
+  const HFront fr = fronts[nd.front];
+  const int k = fr.k, mc = nd.mcat;
+  const long long yld = fr.kld;
+  const int pitch = k | 1;
+  const T* Y = pool + nd.ycat[s];
+  extern __shared__ __align__(16) unsigned char sm_w[];
+  const size_t per_warp = (((size_t)(wcapw + kcap) * sizeof(T) + (size_t)mcap * sizeof(int) + 15) & ~(size_t)15);
+  T* W = reinterpret_cast<T*>(sm_w + (size_t)warp * per_warp);
+  T* u = W + wcapw;
+  int* piv = reinterpret_cast<int*>(u + kcap);
+  // scratch copy (coalesced over the rows of a column) and column norms (each lane its own columns)
+  for (int c = 0; c < mc; ++c)
+    for (int i = lane; i < k; i += 32) W[c * pitch + i] = Y[(long long)c * yld + i];
+  __syncwarp();
+  constexpr int CPL = 4;   // columns per lane (mc ≤ 128)
+  double nrm[CPL];
+  bool done[CPL];
+#pragma unroll
+  for (int q = 0; q < CPL; ++q) {
+    const int c = lane + 32 * q;
+    double a = 0.0;
+    if (c < mc)
+      for (int i = 0; i < k; ++i) a += habs2(W[c * pitch + i]);
+    nrm[q] = c < mc ? a : -1.0;
+    done[q] = c >= mc;
+  }
+  const int jmax = min(k, mc);
+  int r = jmax;
+  double r11 = 0.0;
+  for (int j = 0; j < jmax; ++j) {
+    double best = -1.0;
+    int bp = 0x7fffffff;
+#pragma unroll
+    for (int q = 0; q < CPL; ++q)
+      if (!done[q] && nrm[q] > best) { best = nrm[q]; bp = lane + 32 * q; }
+    warp_argmax(best, bp);
+    const double rkk = sqrt(fmax(best, 0.0));
+    if (j == 0) r11 = rkk;
+    const double ptol = fmax(atol, rtol * r11);
+    if (!(best > 0.0) || !(rkk > ptol)) { r = j; break; }
+    const int pc = bp;
+    const T alpha = W[pc * pitch + j];
+    const double am = hmag(alpha);
+    const T phase = am > 0.0 ? hscal(alpha, 1.0 / am) : hs_one<T>();
+    const T beta = hscal(phase, -rkk);
+    for (int i = j + lane; i < k; i += 32) u[i - j] = i == j ? hs_sub(alpha, beta) : W[pc * pitch + i];
+    __syncwarp();
+    const double f2 = 2.0 / (2.0 * rkk * (rkk + am));
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) {
+      const int c = lane + 32 * q;
+      if (c == pc) { done[q] = true; nrm[q] = -1.0; }
+      if (done[q]) continue;
+      T* y = W + c * pitch;
+      T dot = hs_zero<T>();
+      for (int i = j; i < k; ++i) dot = hcjfma(dot, u[i - j], y[i]);
+      dot = hscal(dot, f2);
+      double a = 0.0;
+      for (int i = j; i < k; ++i) {
+        const T v = hs_fnma(y[i], u[i - j], dot);
+        y[i] = v;
+        if (i > j) a += habs2(v);
+      }
+      nrm[q] = a;
+    }
+    if (lane == 0) { piv[j] = pc; W[pc * pitch + j] = beta; }   // R[j, j]
+    __syncwarp();
+  }
+  __syncwarp();
+  if (lane == 0) {
+    ints[nd.rk + s] = r;
+    if (r >= k - 10) ints[fr.flag] = 1;
+  }
+  // T = R11⁻¹·R12 in place, each lane its own non-pivot columns
+#pragma unroll
+  for (int q = 0; q < CPL; ++q) {
+    const int c = lane + 32 * q;
+    if (c >= mc) continue;
+    bool isp = false;
+    for (int l = 0; l < r; ++l) isp = isp || piv[l] == c;
+    done[q] = isp;
+    if (isp) continue;
+    T* t = W + c * pitch;
+    for (int i = r - 1; i >= 0; --i) {
+      T acc = t[i];
+      for (int l = i + 1; l < r; ++l) acc = hs_fnma(acc, W[piv[l] * pitch + i], t[l]);
+      t[i] = hs_mul(acc, hs_recip(W[piv[i] * pitch + i]));
+    }
+  }
+  __syncwarp();
+  T* E = pool + nd.e[s];
+  T* Ec = pool + nd.ec[s];
+  const long long lde = nd.lde;
+#pragma unroll
+  for (int q = 0; q < CPL; ++q) {
+    const int c = lane + 32 * q;
+    if (c >= mc || done[q]) continue;
+    for (int l = 0; l < r; ++l) {
+      const T v = W[c * pitch + l];
+      E[(long long)l * lde + c] = v;
+      Ec[(long long)l * lde + c] = hconj(v);
+    }
+  }
+  for (int l = lane; l < r; l += 32) {
+    E[(long long)l * lde + piv[l]] = hs_one<T>();
+    Ec[(long long)l * lde + piv[l]] = hs_one<T>();
+  }
+  const HNode p = nodes[nd.parent];
+  const int off = nd.isright ? p.capl : 0;
+  for (int l = lane; l < r; l += 32) {
+    const int c = piv[l];
+    ints[p.icat[s] + off + l] = nd.leaf ? nd.lo + c : ints[nd.icat[s] + c];
+  }
+  if (p.parent >= 0) {
+    T* Yp = pool + p.ycat[s] + (long long)off * yld;
+    for (int l = 0; l < r; ++l) {
+      const T* y = Y + (long long)piv[l] * yld;
+      T* yp = Yp + (long long)l * yld;
+      for (int i = lane; i < k; i += 32) yp[i] = y[i];
+    }
+  }
+}
+
 // ---- generic batched block copy (compaction of the generators, diagonal blocks of the expansion) ----------------------
 template <typename T>
 __global__ void __launch_bounds__(256) k_copy_desc(const CopyDesc* __restrict__ descs, T* __restrict__ pool) {
@@ -724,13 +864,42 @@ template <typename T> void run_round(hs_fac* f, Round& R) {
       hs_gen_gemm(f, dg, 4 * nl, max_k, std::max(max_cap, max_mcat));
       g_hclk.tick(3, st);
       {
-        // scratch copies in shared memory for the nodes of this height whose kld × mcat block fits next to the bookkeeping
-        long long wmax = 0;
-        for (int t : byh[h]) wmax = std::max(wmax, (long long)R.fr[R.nd[t].front].kld * R.nd[t].mcat);
-        const long long budget = ((long long)200 * 1024 - (long long)smem0) / (long long)sizeof(T);
-        const int wcap = (int)std::max<long long>(0, std::min(wmax, budget));
-        const size_t smem = smem0 + (size_t)wcap * sizeof(T);
-        k_hss_qrcp<T><<<dim3(nl, 2), 256, smem, st>>>(dnd.d, lst, dfr.d, pool, R.ints, atol, rtol, kcap, mcap, wcap);
+        // small sample blocks (≤ 128 columns, scratch ≤ 40 KB) go to the warp-per-problem kernel, 4 per CTA; the rest to
+        // the CTA-per-problem kernel with the scratch in shared memory whenever it fits next to the bookkeeping
+        const long long budget_w = (long long)(40 * 1024) / (long long)sizeof(T);
+        std::vector<int> small, large;
+        long long wmax = 0, wmax_w = 0;
+        int kmax_w = 2, mmax_w = 2;
+        for (int t : byh[h]) {
+          const HNode& N = R.nd[t];
+          if (N.parent < 0) continue;
+          const int kk = R.fr[N.front].k;
+          const long long need_w = (long long)(kk | 1) * N.mcat;
+          if (N.mcat <= 128 && need_w + kk <= budget_w) {
+            small.push_back(t); wmax_w = std::max(wmax_w, need_w); kmax_w = std::max(kmax_w, kk); mmax_w = std::max(mmax_w, N.mcat);
+          } else {
+            large.push_back(t); wmax = std::max(wmax, (long long)R.fr[N.front].kld * N.mcat);
+          }
+        }
+        std::vector<int> both(small);
+        both.insert(both.end(), large.begin(), large.end());
+        DevVec<int> dsplit(f);
+        dsplit.upload(both, st);
+        if (!small.empty()) {
+          const int wcapw = (int)((wmax_w + 1) & ~1ll), kcw = even_up(kmax_w), mcw = (mmax_w + 3) & ~3;
+          const size_t per_warp = (((size_t)(wcapw + kcw) * sizeof(T) + (size_t)mcw * sizeof(int) + 15) & ~(size_t)15);
+          const int nitems = 2 * (int)small.size();
+          k_hss_qrcp_warp<T><<<(nitems + QW_WARPS - 1) / QW_WARPS, QW_WARPS * 32, per_warp * QW_WARPS, st>>>(
+              dnd.d, dsplit.d, nitems, dfr.d, pool, R.ints, atol, rtol, wcapw, kcw, mcw);
+        }
+        if (!large.empty()) {
+          const long long budget = ((long long)200 * 1024 - (long long)smem0) / (long long)sizeof(T);
+          const int wcap = (int)std::max<long long>(0, std::min(wmax, budget));
+          const size_t smem = smem0 + (size_t)wcap * sizeof(T);
+          k_hss_qrcp<T><<<dim3((unsigned)large.size(), 2), 256, smem, st>>>(dnd.d, dsplit.d + small.size(), dfr.d, pool, R.ints, atol, rtol, kcap, mcap, wcap);
+        }
+        CUDA_OK(cudaGetLastError());
+        CUDA_OK(cudaStreamSynchronize(st));   // `dsplit` goes back to the cache
       }
       g_hclk.tick(4, st);
       k_hss_desc_b<<<(nl + 127) / 128, 128, 0, st>>>(dnd.d, lst, nl, dfr.d, R.ints, dg);
@@ -1045,6 +1214,8 @@ template <typename T> void build_impl(hs_fac* f, CompLevel& C) {
 void hs_hss_setup() {
   CUDA_OK(cudaFuncSetAttribute(k_hss_qrcp<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CUDA_OK(cudaFuncSetAttribute(k_hss_qrcp<cplx>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CUDA_OK(cudaFuncSetAttribute(k_hss_qrcp_warp<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CUDA_OK(cudaFuncSetAttribute(k_hss_qrcp_warp<cplx>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 }
 
 // cluster tree of `bisection_cluster((n1, m); leafsize)` (factorization.jl:109), pre-order

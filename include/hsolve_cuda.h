@@ -146,6 +146,9 @@ typedef struct {
   int64_t hss_rounds;      /* adaptive rounds taken in total (1 per compressed level when no rank saturated)      */
   int64_t hss_nodes;       /* HSS tree nodes over all compressed fronts                                           */
   double sketch_flops;     /* flops of the sketch GEMMs S·Ω, Sᴴ·Ψ (matrix-free: Abb·X − Z·(Ri·X))                 */
+  double gemm_flops_big;   /* part of gemm_flops issued by the K = outer-block trailing updates (the rest are the K = panel-width
+                              in-block updates, launches of a few CTAs bounded by their prologue / epilogue)       */
+  double ms_gemm_big;      /* their share of ms_gemm (HS_PROFILE)                                                 */
 } hs_stats_t;
 
 typedef enum { HS_GET_D = 0, HS_GET_S = 1, HS_GET_L = 2, HS_GET_R = 3, HS_GET_FRONT = 4, HS_GET_PIV = 5 } hs_which;
