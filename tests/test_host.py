@@ -1,6 +1,7 @@
 """CPU: host logic of the product — C ABI surface, symbolic phase (C++) against the oracle, problem I/O, options."""
 import ctypes
 import os
+import sys
 import re
 
 import numpy as np
@@ -173,3 +174,43 @@ def test_generator_invariants(hs):
     assert (seen == 1).all()
     root = int(np.nonzero(et.fathers == -1)[0][0])
     assert len(et.bound(root)) == 0
+
+
+def test_reference_arm_is_measured_and_never_loads_the_product_library():
+    """`bench.py --impl reference` (the CPU arm): its value is the measured time of the grid its config names — no scaling to
+    the full workload — and the process never maps libhsolve_cuda.so (only oracle/ and the pure-Python problem generator)."""
+    import json
+    import subprocess
+    code = ("import sys, json, io, contextlib; sys.argv = ['bench.py', '--impl', 'reference', '--cpu-grid', '48', '--steps', '1', "
+            "'--warmup', '0', '--cpu-extra', 'none'];\n"
+            "import bench\n"
+            "buf = io.StringIO()\n"
+            "with contextlib.redirect_stdout(buf): bench.main()\n"
+            "maps = open('/proc/self/maps').read()\n"
+            "assert 'libhsolve_cuda' not in maps, 'product library mapped in the reference arm'\n"
+            "assert 'hsolve_b200' not in sys.modules\n"
+            "print(buf.getvalue().strip().splitlines()[-1])\n")
+    out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port"
+    assert "48x48" in line["config"]["workload"] and line["config"]["n"] == 48 * 48
+    assert line["value"] == line["e2e"]["value"] == line["cpu_baseline"]["value"] > 0
+    assert line["residual"] < 1e-10 and line["gmres_iters"] <= 2
+    assert "measured_sample_s" not in line and "flop ratio" not in json.dumps(line)
+
+
+def test_solver_options_extensions_and_sketch_marshalling(hs):
+    """The library's extensions of SolverOptions (hss, sketches, sketch_seed) reach the C struct; the reference's nine fields
+    keep their defaults (HierarchicalSolvers.jl:43-54)."""
+    from hsolve_b200.options import to_c
+    o = hs.SolverOptions()
+    assert o.hss is True and o.sketches is None and o.sketch_seed == 123
+    c, keep = to_c(o)
+    assert c.hss == 1 and not c.sketch_omega and c.sketch_rows == 0 and c.sketch_seed == 123 and keep == []
+    Om, Ps = np.arange(12.0).reshape(4, 3), np.ones((4, 3))
+    c, keep = to_c(o.copy(sketches=(Om, Ps), hss=False), dtype=np.complex128)
+    assert c.hss == 0 and c.sketch_rows == 4 and c.sketch_cols == 3 and c.sketch_omega and c.sketch_psi
+    assert keep[0].dtype == np.complex128 and keep[0].flags.f_contiguous and np.array_equal(keep[0].real, Om)
+    with pytest.raises(hs.DimensionMismatch):
+        to_c(o.copy(sketches=(Om, Ps[:3])))
