@@ -632,6 +632,8 @@ def main():
             del prob_c, Ac
         except Exception as exc:
             c64 = {"error": repr(exc)}
+        if not (c64.get("residual", 0.0) <= 1e-8):   # same gate as the main workload: a wrong answer is not a timing
+            raise SystemExit(f"bench: complex Helmholtz block, relative residual {c64.get('residual')!r} > 1e-8")
 
     # ---- CPU baseline + like-for-like: the oracle port and this library on the SAME bounded sample grid ----
     cpu_baseline = like = None

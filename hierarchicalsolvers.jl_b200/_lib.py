@@ -8,7 +8,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhsolve_cuda.so")
+# LIBHSOLVE_CUDA selects another build of the same library (kernel-variant experiments); default: the in-tree build
+LIB_PATH = os.environ.get("LIBHSOLVE_CUDA") or os.path.join(_HERE, "libhsolve_cuda.so")
 
 HS_OK, HS_EARG, HS_EDIM, HS_ETREE, HS_ESINGULAR, HS_ECUDA, HS_ENOMEM, HS_ENOTIMPL, HS_ESIZE = range(9)
 HS_F64, HS_C64 = 0, 1

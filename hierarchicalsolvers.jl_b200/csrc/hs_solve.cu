@@ -368,7 +368,15 @@ __global__ void __launch_bounds__(TRI_T) k_sv_tri_fwd(const Front* __restrict__ 
       __syncthreads();
     }
   }
-  if (tid < cnt) { const T v = su[tid]; w[R0 + tid] = v; xr[gi[R0 + tid]] = v; }
+  // Step 0 must not touch x while the worker tiles of the same launch are still gathering P·x_int from it (a row
+  // interchanged out of the first super-block is read from x[gi[0 .. SB)) by a worker): its entries are written by the
+  // diagonal CTA of step 1, from the copy in `work`.
+  if (tid < cnt) {
+    const T v = su[tid];
+    w[R0 + tid] = v;
+    if (s > 0 || R1 >= ni) xr[gi[R0 + tid]] = v;
+  }
+  if (s == 1 && tid < SB) xr[gi[tid]] = sv[tid];
 }
 
 // backward: step s finishes super-block b = nsb − 1 − s of every large front (x_int = U11⁻¹·t, t = work[0:ni] from k_gemv_rect)

@@ -327,3 +327,21 @@ def test_split_pivot_block_matches_unsplit(hs, kind):
     k2 = int(nd.left[root])
     for name in ("L", "R", "S"):
         assert rel(getattr(F1.node(k2), name), getattr(F0.node(k2), name)) < 1e-9, name
+
+
+def test_large_pivot_block_with_interchanges(hs):
+    """Complex Helmholtz 1536^2: the root pivot block has 3072 rows and its LU really interchanges rows, so the forward
+    sweep gathers P·x_int across super-blocks (rows pivoted out of the first 128 are read by other CTAs of the same
+    launch).  Round 2 shipped a step-0 kernel that overwrote those entries of x too early; Poisson never pivots and
+    did not see it.  Direct solve, two right-hand sides and one GMRES iteration must all reach rounding level."""
+    prob = hs.grid_problem((1536, 1536), "helmholtz", nmax=100)
+    Ap, nd, nd_loc, perm = hs.prepare(prob.A, prob.elim_tree)
+    F = hs.factor(Ap, nd, nd_loc, swlevel=0)
+    assert F.stats()["max_ni"] >= 3072
+    for _ in range(3):
+        x = hs.ldiv(F, prob.b)
+        assert rel(Ap @ x, prob.b) < 1e-10
+    B = np.stack([prob.b, prob.b[::-1]], axis=1)
+    assert rel(Ap @ hs.ldiv(F, B), B) < 1e-10
+    xg, h = hs.gmres(Ap, prob.b, Pr=F, reltol=1e-9, restart=30, maxiter=30, log=True)
+    assert h.isconverged and h.iters == 1 and rel(Ap @ xg, prob.b) < 1e-9
