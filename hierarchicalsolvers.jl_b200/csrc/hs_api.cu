@@ -1228,8 +1228,22 @@ template <typename T> static void node_get_impl(hs_fac* f, int64_t node, hs_whic
   std::vector<int> piv(ni);
   if (n) CUDA_OK(cudaMemcpy2DAsync(Fh.data(), (size_t)n * sizeof(T), (T*)f->pool + fr.off, (size_t)fr.ld * sizeof(T), (size_t)n * sizeof(T), n,
                                    cudaMemcpyDeviceToHost, st));
-  if (ni) CUDA_OK(cudaMemcpyAsync(piv.data(), f->d_ipiv + fr.ioff, (size_t)ni * sizeof(int), cudaMemcpyDeviceToHost, st));
-  CUDA_OK(cudaStreamSynchronize(st));
+  // The LAPACK interchange sequence is replayed from the pivot order (rperm[k] = original row that ends at row k):
+  // every kernel family records rperm, the row-per-thread small-front kernel records nothing else.
+  auto interchanges = [&](const Front& ff, int m, std::vector<int>& pv) {
+    std::vector<int> rp(m), what(m), where(m);
+    if (m) CUDA_OK(cudaMemcpyAsync(rp.data(), f->d_rperm + ff.ioff, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    pv.resize(m);
+    for (int k = 0; k < m; ++k) what[k] = where[k] = k;
+    for (int k = 0; k < m; ++k) {
+      const int pr = rp[k], q = where[pr], other = what[k];   // row pr sits at position q ≥ k; swap positions k and q
+      pv[k] = q;
+      what[k] = pr; what[q] = other;
+      where[pr] = k; where[other] = q;
+    }
+  };
+  interchanges(fr, ni, piv);
   auto Fm = [&](int i, int j) -> T& { return Fh[(size_t)j * n + i]; };
   T* o = (T*)out;
   auto undo_prep = [&](int off, int m) {
@@ -1275,8 +1289,8 @@ template <typename T> static void node_get_impl(hs_fac* f, int64_t node, hs_whic
     if (f->pseudo_front >= 0 && f->node2front[node] == f->root_front && nb > 0) {
       // the root's Schur block was LU-factored in place for the boundary solve (factornode.jl:72): S = Pᵀ·L·U
       const Front& pf = f->fronts[f->pseudo_front];
-      std::vector<int> pv(nb);
-      CUDA_OK(cudaMemcpy(pv.data(), f->d_ipiv + pf.ioff, (size_t)nb * sizeof(int), cudaMemcpyDeviceToHost));
+      std::vector<int> pv;
+      interchanges(pf, nb, pv);
       Sd.assign((size_t)nb * nb, hs_zero<T>());
       for (int j = 0; j < nb; ++j)
         for (int k = 0; k <= j; ++k) {

@@ -155,6 +155,102 @@ __global__ void __launch_bounds__(TR* TC, MINB) k_front_small(const Front* __res
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// real fronts with n ≤ 64 (the two bottom levels of a 2D tree: 3/4 of all fronts): ONE THREAD PER FRONT ROW, the row in
+// 64 registers, two warps per front.  Per pivot column: each warp finds its candidate with three REDUX operations, the
+// candidate's owner publishes the rest of its row, one barrier, both warps pick the winner from shared memory and
+// eliminate from registers — the pivot row is a broadcast LDS.128 stream, and there are no per-element predicates, no
+// select chains over register tiles and no second barrier (the TR×TC tile kernel above spends 85% of its issue slots on
+// those: 43 000 warp instructions per leaf front, this one ≈ 14 000).  Register indices must be static, so the column
+// loop is unrolled over blocks of 8 columns only: after a block the row is ROTATED by 8 registers (finished columns go
+// to a shared-memory stash until the row's final position is known), which keeps the loop body at ~40 KB of code.
+// Measured variants: 6 CTAs per SM (168 registers, spills) 5.3 ms for the two bottom levels of the 2048² workload, 4 CTAs
+// without spills 4.5 ms, blocks of 4 columns 6.4 ms, pivot search of column j+1 issued inside step j 5.9 ms; the TR×TC
+// tile kernel 6.8 ms.
+// Rows are not moved until the write-back; rperm records the pivot order (the LAPACK interchange sequence is derived
+// from it on the host when a caller asks for it).
+// ------------------------------------------------------------------------------------------------
+constexpr int RW_NC = 64, RW_JB = 8;
+__global__ void __launch_bounds__(RW_NC, 4) k_front_rows(const Front* __restrict__ fronts, double* __restrict__ pool,
+                                                         int* __restrict__ rperm, int f0, int* __restrict__ info) {
+  constexpr int NC = RW_NC, JB = RW_JB;
+  const int fi = f0 + blockIdx.x;
+  const Front fr = fronts[fi];
+  const int n = fr.n, ni = fr.ni;
+  if (n == 0) return;
+  double* F = pool + fr.off;
+  const long long ld = fr.ld;
+  const int r = threadIdx.x, lane = r & 31, warp = r >> 5;
+  __shared__ __align__(16) double s_u[2][2][NC];     // [column parity][warp] rest of the warp's candidate row
+  __shared__ unsigned long long s_key[2][2];         // candidate |.| as an ordered key (0: the warp has none)
+  __shared__ int s_row[2][2];
+  __shared__ double s_stash[(NC - JB) * NC];         // finished columns of every row, column-major
+
+  double a[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) a[c] = (r < n && c < n) ? F[(long long)c * ld + r] : 0.0;
+  bool cand = r < ni;   // may still be chosen as a pivot
+  bool live = true;     // has not been a pivot yet: takes part in the elimination
+  int mypos = r;        // final row position
+  int base = 0;         // a[k] holds column base + k
+  for (;;) {
+#pragma unroll
+    for (int jt = 0; jt < JB; ++jt) {
+      const int j = base + jt;
+      if (j >= ni) break;
+      const int par = jt & 1;
+      double v = cand ? fabs(a[jt]) : -1.0;
+      int idx = r;
+      warp_argmax(v, idx);
+      if (r == idx && v >= 0.0) {
+        // columns jt.. of the candidate row, 16 bytes at a time from the even column at or below jt
+#pragma unroll
+        for (int k = jt & ~1; k < NC; k += 2) *reinterpret_cast<double2*>(&s_u[par][warp][k]) = make_double2(a[k], a[k + 1]);
+      }
+      if (lane == 0) {
+        s_key[par][warp] = v < 0.0 ? 0ull : (unsigned long long)__double_as_longlong(v) + 1ull;
+        s_row[par][warp] = idx;
+      }
+      __syncthreads();
+      const unsigned long long k0 = s_key[par][0], k1 = s_key[par][1];
+      const int w = k1 > k0 ? 1 : 0;                 // ties go to the smaller row, which lives in warp 0
+      const int p = s_row[par][w];
+      const bool ok = (w ? k1 : k0) >= 2ull;         // key 1 is |.| = 0: exactly singular column, formal pivot only
+      if (r == p) { cand = false; live = false; mypos = j; }
+      if (!ok) {
+        if (r == 0 && atomicCAS(&info[0], 0, 1) == 0) { info[1] = fi; info[2] = j; }
+      } else if (live) {
+        const double* u = s_u[par][w];
+        const double l = a[jt] * hs_recip_pivot(u[jt]);
+        a[jt] = l;
+        if ((jt & 1) == 0) a[jt + 1] = fma(-l, u[jt + 1], a[jt + 1]);
+#pragma unroll
+        for (int k = (jt + 2) & ~1; k < NC; k += 2) {
+          const double2 uu = *reinterpret_cast<const double2*>(&u[k]);
+          a[k] = fma(-l, uu.x, a[k]);
+          a[k + 1] = fma(-l, uu.y, a[k + 1]);
+        }
+      }
+    }
+    if (base + JB >= ni) break;
+    // rotate: the block's columns are final for this row
+#pragma unroll
+    for (int c = 0; c < JB; ++c) s_stash[(base + c) * NC + r] = a[c];
+#pragma unroll
+    for (int k = 0; k < NC - JB; ++k) a[k] = a[k + JB];
+#pragma unroll
+    for (int k = NC - JB; k < NC; ++k) a[k] = 0.0;
+    base += JB;
+  }
+  if (r >= n) return;
+  if (r < ni) rperm[fr.ioff + mypos] = r;
+  double* dst = F + mypos;
+  for (int c = 0; c < base; ++c) dst[(long long)c * ld] = s_stash[c * NC + r];
+#pragma unroll
+  for (int k = 0; k < NC; ++k)
+    if (base + k < n) dst[(long long)(base + k) * ld] = a[k];
+}
+
 template <typename T, int TR, int TC, int RPT, int CPT, int MINB = 1> void launch(hs_fac* f, int f0, int nf) {
   k_front_small<T, TR, TC, RPT, CPT, MINB><<<nf, TR * TC, 0, f->ctx->stream>>>(f->d_fronts, (T*)f->pool, f->d_ipiv, f->d_rperm, f0, f->d_info);
   CUDA_OK(cudaGetLastError());
@@ -173,7 +269,11 @@ void hs_small_factor(hs_fac* f, const Level& L) {
   const int nf = L.f1 - L.f0, n = L.max_n;
   if (f->dtype == HS_F64) {
     static const int mb = getenv("HS_SMALL_MINB") ? atoi(getenv("HS_SMALL_MINB")) : 3;
-    if (n <= 80) { if (mb >= 4) launch<double, 16, 8, 5, 10, 4>(f, L.f0, nf); else if (mb == 3) launch<double, 16, 8, 5, 10, 3>(f, L.f0, nf); else launch<double, 16, 8, 5, 10, 1>(f, L.f0, nf); }
+    static const bool rows = !(getenv("HS_SMALL_ROWS") && atoi(getenv("HS_SMALL_ROWS")) == 0);
+    if (n <= RW_NC && L.max_ni <= RW_NC && rows) {
+      k_front_rows<<<nf, RW_NC, 0, f->ctx->stream>>>(f->d_fronts, (double*)f->pool, f->d_rperm, L.f0, f->d_info);
+      CUDA_OK(cudaGetLastError());
+    } else if (n <= 80) { if (mb >= 4) launch<double, 16, 8, 5, 10, 4>(f, L.f0, nf); else if (mb == 3) launch<double, 16, 8, 5, 10, 3>(f, L.f0, nf); else launch<double, 16, 8, 5, 10, 1>(f, L.f0, nf); }
     else if (n <= 96) launch<double, 16, 16, 6, 6>(f, L.f0, nf);
     else launch<double, 16, 16, 8, 8>(f, L.f0, nf);
   } else {

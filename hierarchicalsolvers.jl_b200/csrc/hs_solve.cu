@@ -31,70 +31,160 @@ constexpr int NW = 8;          // warps per CTA
 constexpr int NTH = NW * 32;
 
 // ------------------------------------------------------------------------------------------------
-// in-place inversion of the DB×DB diagonal blocks of L11 (unit lower) and U11 (upper); one CTA per (front, block).
-// Thread j < db builds column j of L_bb⁻¹ by forward substitution, thread 64 + j column j of U_bb⁻¹ by back
-// substitution; columns are independent, so there is no barrier inside the loops.  The factor is read from global
-// memory (every lane reads the same entry → one broadcast transaction), the inverse grows in shared memory.
+// in-place inversion of the DB×DB diagonal blocks of L11 (unit lower) and U11 (upper); one CTA of 4 warps per
+// (front, block): warps 0,1 invert the lower triangle, warps 2,3 the upper one, everything inside ONE shared copy of the
+// block (33 KB in f64: six CTAs per SM).  Each 64×64 triangle is inverted as a 2×2 block matrix of 32×32 blocks,
+//   inv [A 0; B C] = [A⁻¹ 0; −C⁻¹·B·A⁻¹  C⁻¹],        inv [A B; 0 C] = [A⁻¹  −A⁻¹·B·C⁻¹; 0 C⁻¹]:
+//   phase 1   warp h: the 32×32 diagonal triangle h, lane j = column j of its inverse by RIGHT-looking substitution with
+//             the column in registers — 31 − k independent FMAs per step instead of one dependent chain per entry
+//   phase 2a  T = B·A⁻¹ (lower) / B·C⁻¹ (upper), 2b  off-diagonal block = −C⁻¹·T / −A⁻¹·T; lane j = column j, warp h =
+//             rows ≡ h (mod 2), so the statically known zeros of the broadcast factor are skipped evenly in both warps
+// Results replace their operands in shared memory (registers → barrier → store), the block goes back in one pass.
+// Round 2 before this: one thread per column with a left-looking dependent FMA chain, 6.0 ms at the 2048² workload.
 // ------------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(128) k_trtri_diag(const Front* __restrict__ fronts, T* __restrict__ pool, int f0, int lds) {
+// HB = half block: a CTA inverts one (2·HB)×(2·HB) block.  HB = 32 is the DB-blocked layout of the large fronts; levels
+// whose pivot blocks all fit one smaller block (the bottom of the tree: ni ≤ 14, 30, 49 at the 2048² workload) use
+// HB = 8, 16, 25 — the work goes with HB³.
+template <typename T, int HB>
+__global__ void __launch_bounds__(128, sizeof(T) == 8 ? 4 : 3) k_trtri_diag(const Front* __restrict__ fronts, T* __restrict__ pool, int f0) {
+  constexpr int DBT = 2 * HB, LDS = DBT + 1, HH = (HB + 1) / 2;
   const Front fr = fronts[f0 + blockIdx.x];
-  const int b0 = blockIdx.y * DB;
+  const int b0 = blockIdx.y * DBT;
   if (b0 >= fr.ni) return;
-  const int db = min(DB, fr.ni - b0);
-  const int LDS = lds;
+  const int db = min(DBT, fr.ni - b0);
   extern __shared__ __align__(16) unsigned char smem_x[];
-  T* S = reinterpret_cast<T*>(smem_x);  // the factor block (both triangles), column-major db × LDS
-  T* X = S + (size_t)lds * lds;         // its inverse
+  T* S = reinterpret_cast<T*>(smem_x);  // the block, column-major with pitch LDS; padded with the identity beyond db
   T* G = pool + fr.off + (long long)b0 * fr.ld + b0;
   const long long ld = fr.ld;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, j = tid & 31, h = (tid >> 5) & 1;
+  const bool lower = tid < 64, act = j < HB;
   {
     // the whole block is requested before the first shared-memory store (a rolled loop pays one latency per element)
-    constexpr int NE = DB * DB / 128;
-    T tmp[NE];
+    constexpr int NE = (DBT * DBT + 127) / 128, NBATCH = (NE * (int)sizeof(T) > 256) ? 2 : 1, NQ = (NE + NBATCH - 1) / NBATCH;
 #pragma unroll
-    for (int q = 0; q < NE; ++q) {
-      const int e = tid + q * 128;
-      tmp[q] = e < db * db ? G[(long long)(e / db) * ld + (e % db)] : hs_zero<T>();
-    }
+    for (int bt = 0; bt < NBATCH; ++bt) {
+      T tmp[NQ];
 #pragma unroll
-    for (int q = 0; q < NE; ++q) {
-      const int e = tid + q * 128;
-      if (e < db * db) S[(e / db) * LDS + (e % db)] = tmp[q];
+      for (int q = 0; q < NQ; ++q) {
+        const int e = tid + (bt * NQ + q) * 128, r = e % DBT, c = e / DBT;
+        tmp[q] = (r < db && c < db) ? G[(long long)c * ld + r] : (r == c ? hs_one<T>() : hs_zero<T>());
+      }
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const int e = tid + (bt * NQ + q) * 128;
+        if (e < DBT * DBT) S[(e / DBT) * LDS + (e % DBT)] = tmp[q];
+      }
     }
   }
   __syncthreads();
-  // all lanes walk the same (i, k) pairs: S[k,i] is a broadcast read, X[.,j] is private to the lane
-  if (tid < 64) {
-    const int j = tid;  // column j of L⁻¹:  x_ij = −(L_ij + Σ_{j<k<i} L_ik·x_kj)
-    const bool act = j < db;
-    for (int i = 1; i < db; ++i) {
-      T sacc = (act && i > j) ? S[j * LDS + i] : hs_zero<T>();
-      for (int k = 1; k < i; ++k) {
-        const T g = S[k * LDS + i];
-        if (act && k > j) sacc = hs_fma(sacc, g, X[j * LDS + k]);
+  const int o = HB * h;
+  if (act) {  // phase 1
+    T x[HB];
+#pragma unroll
+    for (int i = 0; i < HB; ++i) x[i] = i == j ? hs_one<T>() : hs_zero<T>();
+    if (lower) {
+#pragma unroll
+      for (int k = 0; k < HB - 1; ++k) {
+        const T* col = S + (o + k) * LDS + o;
+#pragma unroll
+        for (int i = k + 1; i < HB; ++i) x[i] = hs_fnma(x[i], col[i], x[k]);
       }
-      if (act && i > j) X[j * LDS + i] = hs_sub(hs_zero<T>(), sacc);
-    }
-  } else {
-    const int j = tid - 64;  // column j of U⁻¹:  x_ij = −(Σ_{i<k≤j} U_ik·x_kj)/U_ii
-    const bool act = j < db;
-    if (act) X[j * LDS + j] = hs_recip_pivot(S[j * LDS + j]);
-    for (int i = db - 2; i >= 0; --i) {
-      T sacc = hs_zero<T>();
-      for (int k = i + 1; k < db; ++k) {
-        const T g = S[k * LDS + i];
-        if (act && k <= j && i < j) sacc = hs_fma(sacc, g, X[j * LDS + k]);
+      __syncwarp(__activemask());
+#pragma unroll
+      for (int i = 0; i < HB; ++i)
+        if (i > j) S[(o + j) * LDS + o + i] = x[i];
+    } else {
+#pragma unroll
+      for (int k = HB - 1; k >= 0; --k) {
+        const T* col = S + (o + k) * LDS + o;
+        x[k] = hs_mul(x[k], hs_recip_pivot(col[k]));
+#pragma unroll
+        for (int i = 0; i < k; ++i) x[i] = hs_fnma(x[i], col[i], x[k]);
       }
-      const T dinv = hs_recip_pivot(S[i * LDS + i]);
-      if (act && i < j) X[j * LDS + i] = hs_sub(hs_zero<T>(), hs_mul(sacc, dinv));
+      __syncwarp(__activemask());
+#pragma unroll
+      for (int i = 0; i < HB; ++i)
+        if (i <= j) S[(o + j) * LDS + o + i] = x[i];
     }
   }
   __syncthreads();
-  for (int e = tid; e < db * db; e += blockDim.x) {
-    const int i = e % db, j = e / db;
-    G[(long long)j * ld + i] = X[j * LDS + i];
+  if (db > HB) {   // uniform: a block that fits the first half has no off-diagonal part
+    // phase 2: this thread's rows i = 2·ii + h of column j of the off-diagonal block
+    T acc[HH];
+#pragma unroll
+    for (int ii = 0; ii < HH; ++ii) acc[ii] = hs_zero<T>();
+    // B = the off-diagonal block of the factor: rows HB.. × columns 0.. (lower), rows 0.. × columns HB.. (upper)
+    T* B = lower ? S + HB : S + HB * LDS;
+    if (act) {
+      if (lower) {  // T[i, j] = Σ_k B[i, k]·A⁻¹[k, j],  A⁻¹ unit lower: entries k > j stored, 1 at k = j
+        const T* own = S + j * LDS;
+#pragma unroll
+        for (int k = 0; k < HB; ++k) {
+          const T a = k > j ? own[k] : (k == j ? hs_one<T>() : hs_zero<T>());
+#pragma unroll
+          for (int ii = 0; ii < HH; ++ii)
+            if (2 * ii + 1 < HB || h == 0) acc[ii] = hs_fma(acc[ii], B[k * LDS + min(2 * ii + h, HB - 1)], a);
+        }
+      } else {      // T[i, j] = Σ_k B[i, k]·C⁻¹[k, j],  C⁻¹ upper: entries k ≤ j stored
+        const T* own = S + (HB + j) * LDS + HB;
+#pragma unroll
+        for (int k = 0; k < HB; ++k) {
+          const T a = k <= j ? own[k] : hs_zero<T>();
+#pragma unroll
+          for (int ii = 0; ii < HH; ++ii)
+            if (2 * ii + 1 < HB || h == 0) acc[ii] = hs_fma(acc[ii], B[k * LDS + min(2 * ii + h, HB - 1)], a);
+        }
+      }
+    }
+    __syncthreads();
+    if (act) {
+#pragma unroll
+      for (int ii = 0; ii < HH; ++ii) {
+        if (2 * ii + h < HB) B[j * LDS + 2 * ii + h] = acc[ii];
+        acc[ii] = hs_zero<T>();
+      }
+    }
+    __syncthreads();
+    if (act) {
+      const T* tcol = B + j * LDS;   // column j of T
+      if (lower) {  // −C⁻¹·T,  C⁻¹[i, k] unit lower at rows/columns HB..: stored for k < i
+        const T* Ci = S + HB * LDS + HB;
+#pragma unroll
+        for (int k = 0; k < HB; ++k) {
+          const T t = tcol[k];
+#pragma unroll
+          for (int ii = 0; ii < HH; ++ii) {
+            if (2 * ii + 1 < k) continue;   // rows 2·ii + h ≤ 2·ii + 1 < k: structurally zero
+            const int i = min(2 * ii + h, HB - 1);
+            const T c = k < i ? Ci[k * LDS + i] : (k == i ? hs_one<T>() : hs_zero<T>());
+            acc[ii] = hs_fma(acc[ii], c, t);
+          }
+        }
+      } else {      // −A⁻¹·T,  A⁻¹[i, k] upper at rows/columns 0..: stored for k ≥ i
+#pragma unroll
+        for (int k = 0; k < HB; ++k) {
+          const T t = tcol[k];
+#pragma unroll
+          for (int ii = 0; ii < HH; ++ii) {
+            if (2 * ii > k) continue;       // rows 2·ii + h ≥ 2·ii > k: structurally zero
+            const int i = min(2 * ii + h, HB - 1);
+            const T c = k >= i ? S[k * LDS + i] : hs_zero<T>();
+            acc[ii] = hs_fma(acc[ii], c, t);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (act) {
+#pragma unroll
+      for (int ii = 0; ii < HH; ++ii)
+        if (2 * ii + h < HB) B[j * LDS + 2 * ii + h] = hs_sub(hs_zero<T>(), acc[ii]);
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < db * db; e += 128) {
+    const int r = e % db, c = e / db;
+    G[(long long)c * ld + r] = S[c * LDS + r];
   }
 }
 
@@ -501,11 +591,24 @@ __global__ void __launch_bounds__(NTH) k_gemv_rect(const Front* __restrict__ fro
   }
 }
 
+template <typename T, int HB> static void launch_trtri(hs_fac* f, const Level& L, cudaStream_t st) {
+  constexpr int DBT = 2 * HB;
+  static bool attr = false;
+  if (!attr) {
+    CUDA_OK(cudaFuncSetAttribute(k_trtri_diag<T, HB>, cudaFuncAttributeMaxDynamicSharedMemorySize, DBT * (DBT + 1) * (int)sizeof(T)));
+    attr = true;
+  }
+  dim3 grid(L.f1 - L.f0, (L.max_ni + DBT - 1) / DBT);
+  k_trtri_diag<T, HB><<<grid, 128, (size_t)DBT * (DBT + 1) * sizeof(T), st>>>(f->d_fronts, (T*)f->pool, L.f0);
+}
+
 template <typename T> void prep_impl(hs_fac* f, const Level& L, cudaStream_t st) {
   if (L.max_ni == 0) return;
-  dim3 grid(L.f1 - L.f0, (L.max_ni + DB - 1) / DB);
-  const int dbm = std::min(DB, L.max_ni), lds = dbm | 1;
-  k_trtri_diag<T><<<grid, 128, (size_t)2 * lds * lds * sizeof(T), st>>>(f->d_fronts, (T*)f->pool, L.f0, lds);
+  // one smaller block per front where every pivot block of the level fits it; DB-blocked otherwise
+  if (L.max_ni <= 16) launch_trtri<T, 8>(f, L, st);
+  else if (L.max_ni <= 32) launch_trtri<T, 16>(f, L, st);
+  else if (L.max_ni <= 50) launch_trtri<T, 25>(f, L, st);
+  else launch_trtri<T, DB / 2>(f, L, st);
   CUDA_OK(cudaGetLastError());
   f->stats.launches_factor += 1;
 }
@@ -583,8 +686,6 @@ template <typename T> void run_impl(hs_fac* f, int64_t nrhs, void* xv, int which
 }  // namespace
 
 void hs_solve_setup() {
-  CUDA_OK(cudaFuncSetAttribute(k_trtri_diag<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (DB + 1) * (DB + 1) * (int)sizeof(double)));
-  CUDA_OK(cudaFuncSetAttribute(k_trtri_diag<cplx>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (DB + 1) * (DB + 1) * (int)sizeof(cplx)));
   CUDA_OK(cudaFuncSetAttribute(k_sv_tri_fwd<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tri_smem<double>()));
   CUDA_OK(cudaFuncSetAttribute(k_sv_tri_bwd<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tri_smem<double>()));
   CUDA_OK(cudaFuncSetAttribute(k_sv_tri_fwd<cplx>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tri_smem<cplx>()));
