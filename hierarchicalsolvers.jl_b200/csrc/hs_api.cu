@@ -60,7 +60,11 @@ extern "C" int32_t hs_create(hs_ctx** out, int32_t device) {
     CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     CUDA_OK(cudaStreamCreateWithPriority(&c->aux_stream, cudaStreamNonBlocking, hi));
     if (!getenv("HS_NO_PREP_OVERLAP")) CUDA_OK(cudaStreamCreateWithPriority(&c->prep_stream, cudaStreamNonBlocking, lo));
+    if (!getenv("HS_NO_BELOW_STREAM")) CUDA_OK(cudaStreamCreateWithPriority(&c->below_stream, cudaStreamNonBlocking, lo));
   }
+  CUDA_OK(cudaEventCreateWithFlags(&c->ev_pan, cudaEventDisableTiming));
+  CUDA_OK(cudaEventCreateWithFlags(&c->ev_urow, cudaEventDisableTiming));
+  CUDA_OK(cudaEventCreateWithFlags(&c->ev_below, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&c->ev_p0, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&c->ev_p1, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming));
@@ -109,6 +113,10 @@ extern "C" int32_t hs_destroy(hs_ctx* ctx) {
   cudaFree(ctx->gm_buf);
   if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
   if (ctx->prep_stream) cudaStreamDestroy(ctx->prep_stream);
+  if (ctx->below_stream) cudaStreamDestroy(ctx->below_stream);
+  if (ctx->ev_pan) cudaEventDestroy(ctx->ev_pan);
+  if (ctx->ev_urow) cudaEventDestroy(ctx->ev_urow);
+  if (ctx->ev_below) cudaEventDestroy(ctx->ev_below);
   if (ctx->ev_p0) cudaEventDestroy(ctx->ev_p0);
   if (ctx->ev_p1) cudaEventDestroy(ctx->ev_p1);
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
@@ -214,7 +222,7 @@ template <typename T> static void factor_level(hs_fac* f, const Level& L) {
   };
   auto gemm = [&](int nact, int J0, int j0, int mode, int mrows, int mcols, cudaStream_t stream) {
     if (nact <= 0 || mrows <= 0 || mcols <= 0) return;
-    const bool big = mode == 1 || mode >= 3;
+    const bool big = mode == 1 || mode == 3 || mode == 4;
     if (big) {   // flops of this trailing update, for the big / in-block split of the GEMM roofline
       const double cxf = f->dtype == HS_C64 ? 4.0 : 1.0;
       for (int i = L.f0; i < L.f0 + nact; ++i) {
@@ -242,6 +250,19 @@ template <typename T> static void factor_level(hs_fac* f, const Level& L) {
   // high-priority second stream.
   const bool lookahead = !f->ctx->profile && (L.f1 - L.f0) <= f->ctx->lookahead_max_fronts && L.max_ni > NB;
   cudaStream_t hi = f->ctx->aux_stream;
+  // Rows below the pivot rows (boundary rows) never enter a pivot search: their triangular solves and their share of the
+  // in-block updates run on the below-rows stream, one step behind the panel chain (few large fronts only — with many
+  // fronts per level the launches are throughput-bound and the extra events cost more than they hide).
+  cudaStream_t sb = f->ctx->below_stream;
+  const bool below2 = sb && !f->ctx->profile && !has_split && L.max_nb > 0 && (L.f1 - L.f0) <= f->ctx->lookahead_max_fronts;
+  bool below_pending = false;
+  auto join_below = [&](cudaStream_t s1, cudaStream_t s2) {   // these streams are about to read the boundary rows of the block's columns
+    if (!below_pending) return;
+    CUDA_OK(cudaEventRecord(f->ctx->ev_below, sb));
+    CUDA_OK(cudaStreamWaitEvent(s1, f->ctx->ev_below, 0));
+    if (s2) CUDA_OK(cudaStreamWaitEvent(s2, f->ctx->ev_below, 0));
+    below_pending = false;
+  };
   auto phaseA = [&](int J0, int JE, cudaStream_t s_) {
     // factor the block's columns; interchanges, solves and updates stay inside the block
     for (int j0 = J0; j0 < JE; j0 += W) {
@@ -253,6 +274,19 @@ template <typename T> static void factor_level(hs_fac* f, const Level& L) {
         hs_panel_launch(f, W, L.f0, nact, j0, pivot_rows(j0, nact), s_);
         ++f->stats.panel_launches;
         ++f->stats.launches_factor;
+      }
+      if (below2) {
+        CUDA_OK(cudaEventRecord(f->ctx->ev_pan, s_));
+        trsm_dispatch<T>(f, W, L.f0, nact, J0, j0, NB, 0, JE - J0, s_);
+        CUDA_OK(cudaEventRecord(f->ctx->ev_urow, s_));
+        gemm(nact, J0, j0, 5, L.max_ni - j0, JE - j0, s_);
+        CUDA_OK(cudaStreamWaitEvent(sb, f->ctx->ev_pan, 0));
+        hs_trsm_rows(f, W, L.f0, nact, j0, L.max_nb, sb);
+        ++f->stats.launches_factor;
+        CUDA_OK(cudaStreamWaitEvent(sb, f->ctx->ev_urow, 0));
+        gemm(nact, J0, j0, 6, L.max_nb, JE - j0, sb);
+        below_pending = true;
+        continue;
       }
       {
         PhaseTimer t(f, &f->stats.ms_trsm);
@@ -293,17 +327,20 @@ template <typename T> static void factor_level(hs_fac* f, const Level& L) {
       if (lookahead && JE < L.max_ni) {
         CUDA_OK(cudaEventRecord(f->ctx->ev_b, st));
         CUDA_OK(cudaStreamWaitEvent(hi, f->ctx->ev_b, 0));
+        join_below(hi, st);   // before the next block queues its own boundary-row work
         gemm(nactB, J0, J0, 3, mB, NB, hi);                     // the next block's own columns …
         phaseA(JE, std::min(JE + NB, L.max_ni), hi);            // … and its panels, on the look-ahead stream
         CUDA_OK(cudaEventRecord(f->ctx->ev_c2, hi));
         a_on_hi = true;
         gemm(nactB, J0, J0, 4, mB, mB, st);                     // everything right of the next block
       } else {
+        join_below(st, nullptr);
         gemm(nactB, J0, J0, 1, mB, mB, st);
       }
     }
   }
   if (a_on_hi) CUDA_OK(cudaStreamWaitEvent(st, f->ctx->ev_c2, 0));
+  join_below(st, nullptr);
   {  // flops the GEMM launches of this level issue: Σ_steps 2·(n−j0−wc)²·wc per front
     const double cx = f->dtype == HS_C64 ? 4.0 : 1.0;
     for (int i = L.f0; i < L.f1; ++i) {

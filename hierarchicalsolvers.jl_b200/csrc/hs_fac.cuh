@@ -41,6 +41,10 @@ struct hs_ctx {
   bool own_stream = false;
   cudaStream_t aux_stream = nullptr;  // look-ahead: the big trailing update overlaps the next block's panels
   cudaEvent_t ev_b = nullptr, ev_c2 = nullptr;
+  // boundary rows (the rows below the ones pivots are taken from) are solved and updated on their own stream: the chain
+  // panel → row interchanges + U row panel → update of the pivot rows → next panel does not wait for them
+  cudaStream_t below_stream = nullptr;
+  cudaEvent_t ev_pan = nullptr, ev_urow = nullptr, ev_below = nullptr;
   cudaStream_t prep_stream = nullptr;  // solve preparation of a finished level runs beside the next levels' factorization
   cudaEvent_t ev_p0 = nullptr, ev_p1 = nullptr;
   bool prep_pending = false;

@@ -252,6 +252,8 @@ __global__ void __launch_bounds__(128) k_laswp(const Front* __restrict__ fronts,
 //   mode 0: K = [j0, j0+wc),  C = rows [j0+wc, n)  × cols [j0+wc, BE)   (inside the block, while it is factored)
 //   mode 2: K = [j0, j0+wc),  C = rows [j0+wc, BE) × cols [BE, n)      (top strip of the outside columns, after it)
 //   mode 1: K = [J0, BE),     C = [BE, n)²                             (the big update, K up to NB)
+//   mode 5 / 6: mode 0 split by rows: [j0+wc, plim) — all the next panel needs — and [plim, n), plim = end of the rows
+//               pivots are taken from; mode 6 runs on the below-rows stream together with k_trsm_rows
 //   mode 3 / 4: the big update split for look-ahead: columns of the NEXT outer block [BE, BE2) / the rest [BE2, n),
 //               BE2 = min(BE+NB, ni); mode 4 runs on a second stream while the next block's panels are factored
 // ------------------------------------------------------------------------------------------------
@@ -325,7 +327,7 @@ __global__ void __launch_bounds__(GemmCfg<T>::TM / GemmCfg<T>::WM * GemmCfg<T>::
     const Front fr = fronts[f0 + blockIdx.x];
     const int n = fr.n, ni = fr.ni;
     const int BE = min(J0 + NB, ni);
-    if (mode == 1 || mode >= 3) {
+    if (mode == 1 || mode == 3 || mode == 4) {
       if (ni <= J0) return;
       const int BE2 = min(BE + NB, ni);
       kbase = J0; kcount = BE - J0; lo = BE; rhi = n;
@@ -335,7 +337,15 @@ __global__ void __launch_bounds__(GemmCfg<T>::TM / GemmCfg<T>::WM * GemmCfg<T>::
       if (ni <= j0) return;
       const int wc = min(W, ni - j0);
       kbase = j0; kcount = wc; lo = j0 + wc;
-      if (mode == 0) { rhi = n; clo = lo; chi = BE; } else { rhi = BE; clo = BE; chi = n; }
+      if (mode == 2) { rhi = BE; clo = BE; chi = n; }
+      else {
+        // mode 0 split by rows at the end of the rows pivots are taken from: 5 = the pivot rows (what the next panel
+        // waits for), 6 = the rows below (boundary rows; they ride on a second stream, off the panel chain)
+        const int plim = hs_plim(fr, j0);
+        clo = lo; chi = BE; rhi = n;
+        if (mode == 5) rhi = plim;
+        else if (mode == 6) lo = max(lo, plim);
+      }
     }
     // rows are loaded in aligned 16-byte pairs; a front whose base is not 16-byte aligned (only the root-boundary
     // pseudo front can be) takes the 8-byte copy path
