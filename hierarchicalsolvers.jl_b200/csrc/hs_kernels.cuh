@@ -228,14 +228,33 @@ __global__ void __launch_bounds__(128) k_laswp(const Front* __restrict__ fronts,
   if (fr.ni <= J0) return;
   const int BE = min(J0 + NB, fr.ni);
   const int ncols = J0 + fr.n - BE;
+  if ((int)(blockIdx.y * blockDim.x) >= ncols) return;
+  // the block's interchanges that really move a row, compacted in shared memory with one coalesced read (a thread
+  // walking ipiv itself pays one L2 latency per pivot: ~17 µs per launch on the panel chain of the top fronts)
+  __shared__ int s_j[128], s_p[128];
+  __shared__ int s_n;
+  const int* pv = ipiv + fr.ioff;
   const int cc = blockIdx.y * blockDim.x + threadIdx.x;
-  if (cc >= ncols) return;
   const int c = cc < J0 ? cc : BE + (cc - J0);
   T* col = pool + fr.off + (long long)c * fr.ld;
-  const int* pv = ipiv + fr.ioff;
-  for (int j = J0; j < BE; ++j) {
-    const int p = pv[j];
-    if (p != j) { const T t = col[j]; col[j] = col[p]; col[p] = t; }
+  for (int b = J0; b < BE; b += 128) {   // 128 pivots per pass, kept in order
+    const int j = b + threadIdx.x;
+    const int p = j < BE ? pv[j] : j;
+    const bool mv = p != j;
+    const unsigned m = __ballot_sync(0xffffffffu, mv);
+    __shared__ int s_wcnt[4];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) s_wcnt[w] = __popc(m);
+    __syncthreads();
+    int base = 0;
+    for (int q = 0; q < w; ++q) base += s_wcnt[q];
+    if (mv) { const int k = base + __popc(m & ((1u << lane) - 1u)); s_j[k] = j; s_p[k] = p; }
+    if (threadIdx.x == 0) s_n = s_wcnt[0] + s_wcnt[1] + s_wcnt[2] + s_wcnt[3];
+    __syncthreads();
+    const int nm = s_n;
+    if (cc < ncols)
+      for (int k = 0; k < nm; ++k) { const int jj = s_j[k], pp = s_p[k]; const T t = col[jj]; col[jj] = col[pp]; col[pp] = t; }
+    __syncthreads();
   }
 }
 
