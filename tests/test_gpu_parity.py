@@ -236,10 +236,17 @@ def test_single_dense_front(hs, ni, nb, cx):
 
 @pytest.mark.parametrize("ni,nb,cx", [(1, 0, False), (1, 1, True), (0, 5, False), (64, 10, False), (65, 10, False),
                                       (63, 65, True), (128, 0, False), (129, 0, False), (96, 0, True), (97, 3, True),
-                                      (256, 1, False), (257, 255, False)])
+                                      (256, 1, False), (257, 255, False),
+                                      # row-per-thread leaf kernel (real, n ≤ 64) and its 8-column rotation blocks
+                                      (8, 0, False), (9, 55, False), (16, 48, False), (49, 15, False), (64, 0, False), (33, 31, False),
+                                      (40, 25, False),
+                                      # block sizes of the diagonal-block inversion: ni ≤ 16 / 32 / 50 / 64, both scalar types
+                                      (14, 20, False), (16, 10, True), (17, 3, True), (30, 60, False), (32, 5, True), (33, 10, True),
+                                      (50, 10, False), (50, 30, True), (51, 5, False), (51, 40, True)])
 def test_front_size_thresholds(hs, ni, nb, cx):
-    """Sizes that sit on the switch points of the kernels: fused register kernel (n ≤ 128 f64 / 96 c64), solve block
-    (64), panel width (64 / 32), outer block (256), one CTA vs cluster (256 rows); plus empty interior / boundary."""
+    """Sizes that sit on the switch points of the kernels: fused register kernels (n ≤ 64 rows-per-thread, n ≤ 128 f64 /
+    96 c64 tiles), solve block (64) and the smaller inversion blocks of the bottom levels, panel width (64 / 32), outer
+    block (256), one CTA vs cluster (256 rows); plus empty interior / boundary."""
     prob, A = _single_front_problem(hs, ni, nb, cx, seed=ni + 7 * nb)
     Ap, nd, nd_loc, perm = hs.prepare(prob.A, prob.elim_tree)
     F = hs.factor(Ap, nd, nd_loc, swlevel=0)
