@@ -169,6 +169,16 @@ template <> struct PanelW<double> { static constexpr int W0 = 64; };
 template <> struct PanelW<cplx> { static constexpr int W0 = 32; };
 
 template <typename T, int W> static void launch_trsm_w(hs_fac* f, int f0, int nact, int J0, int j0, int NB, int cmode, int max_cols, cudaStream_t st) {
+  if constexpr (W == 32 || W == 64) {
+    // few columns in all (the panel chain of the upper levels): one warp per column
+    static const long long wmax = getenv("HS_TRSM_WARP_COLS") ? atoll(getenv("HS_TRSM_WARP_COLS")) : 148 * 8 * 4;
+    if ((long long)nact * max_cols <= wmax) {
+      dim3 gw(nact, (max_cols + 7) / 8);
+      k_swap_trsm_warp<T, W><<<gw, 256, 0, st>>>(f->d_fronts, (T*)f->pool, f->d_ipiv, f0, J0, j0, NB, cmode);
+      CUDA_OK(cudaGetLastError());
+      return;
+    }
+  }
   dim3 grid(nact, (max_cols + 127) / 128);
   k_swap_trsm<T, W><<<grid, 128, 0, st>>>(f->d_fronts, (T*)f->pool, f->d_ipiv, f0, J0, j0, NB, cmode);
   CUDA_OK(cudaGetLastError());

@@ -220,6 +220,91 @@ __global__ void __launch_bounds__(128) k_swap_trsm(const Front* __restrict__ fro
     if (i < wc) col[j0 + i] = x[i];
 }
 
+// The same operation with ONE WARP PER COLUMN, for the launches on the panel chain of the upper levels (a few hundred
+// columns in all): lane i keeps x[i] (and x[32+i]), step k broadcasts x[k] with a shuffle.  400 warp instructions per column
+// in a rolled loop instead of 4 000 straight-line ones per 32 columns — three times the work of the thread-per-column
+// kernel, but a small launch finishes in ~1/2 of the time because it is not bound by fetching 64 KB of cold code.
+template <typename T, int W>
+__global__ void __launch_bounds__(256) k_swap_trsm_warp(const Front* __restrict__ fronts, T* __restrict__ pool,
+                                                         const int* __restrict__ ipiv, int f0, int J0, int j0, int NB,
+                                                         int cmode) {
+  static_assert(W == 32 || W == 64, "one or two rows per lane");
+  constexpr int NT = 256, WPC = NT / 32;
+  const int fi = f0 + blockIdx.x;
+  const Front fr = fronts[fi];
+  if (fr.ni <= j0) return;
+  const int wc = min(W, fr.ni - j0);
+  const int BE = min(J0 + NB, fr.ni);
+  const int nleft = cmode == 0 ? j0 - J0 : 0;
+  const int ncols = cmode == 0 ? nleft + (BE - j0 - wc) : fr.n - BE;
+  if ((int)(blockIdx.y * WPC) >= ncols) return;
+  T* F = pool + fr.off;
+  __shared__ T sL[W * W];
+  __shared__ int spiv[W];
+  {
+    constexpr int NE = (W * W + NT - 1) / NT;
+    T tmp[NE];
+#pragma unroll
+    for (int q = 0; q < NE; ++q) {
+      const int e = threadIdx.x + q * NT;
+      const int i = e % W, k = e / W;
+      tmp[q] = (e < W * W && i < wc && k < wc && i > k) ? F[(long long)(j0 + k) * fr.ld + (j0 + i)] : hs_zero<T>();
+    }
+#pragma unroll
+    for (int q = 0; q < NE; ++q) {
+      const int e = threadIdx.x + q * NT;
+      if (e < W * W) sL[e] = tmp[q];
+    }
+  }
+  if (threadIdx.x < W) spiv[threadIdx.x] = threadIdx.x < wc ? ipiv[fr.ioff + j0 + threadIdx.x] : j0 + threadIdx.x;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cc = blockIdx.y * WPC + warp;
+  if (cc >= ncols) return;
+  int c;
+  bool solve = true;
+  if (cmode == 0) {
+    solve = cc >= nleft;
+    c = solve ? j0 + wc + (cc - nleft) : J0 + cc;
+  } else {
+    c = BE + cc;
+  }
+  T* col = F + (long long)c * fr.ld;
+  if (cmode == 0) {
+    // interchanges are sequential; skipped altogether when the panel moved no row
+    bool moved = spiv[lane] != j0 + lane;
+    if (W == 64) moved = moved || spiv[32 + lane] != j0 + 32 + lane;
+    if (__any_sync(0xffffffffu, moved)) {
+      if (lane == 0) {
+        for (int j = 0; j < wc; ++j) {
+          const int p = spiv[j];
+          if (p != j0 + j) { const T t = col[j0 + j]; col[j0 + j] = col[p]; col[p] = t; }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  if (!solve) return;
+  T x0 = lane < wc ? col[j0 + lane] : hs_zero<T>();
+  T x1 = hs_zero<T>();
+  if (W == 64 && 32 + lane < wc) x1 = col[j0 + 32 + lane];
+#pragma unroll 4
+  for (int k = 0; k < 32; ++k) {
+    const T xk = hs_shfl(x0, k);
+    if (lane > k) x0 = hs_fnma(x0, sL[k * W + lane], xk);
+    if (W == 64) x1 = hs_fnma(x1, sL[k * W + 32 + lane], xk);
+  }
+  if (W == 64) {
+#pragma unroll 4
+    for (int k = 32; k < 64; ++k) {
+      const T xk = hs_shfl(x1, k - 32);
+      if (lane > k - 32) x1 = hs_fnma(x1, sL[k * W + 32 + lane], xk);
+    }
+  }
+  if (lane < wc) col[j0 + lane] = x0;
+  if (W == 64 && 32 + lane < wc) col[j0 + 32 + lane] = x1;
+}
+
 // interchanges of a whole outer block [J0, BE) applied to the columns outside it, [0, J0) ∪ [BE, n)
 template <typename T>
 __global__ void __launch_bounds__(128) k_laswp(const Front* __restrict__ fronts, T* __restrict__ pool,
