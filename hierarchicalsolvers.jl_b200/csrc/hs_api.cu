@@ -81,7 +81,6 @@ extern "C" int32_t hs_create(hs_ctx** out, int32_t device) {
   if (getenv("HS_OUTER_BLOCK")) c->outer_block = std::max(1, atoi(getenv("HS_OUTER_BLOCK")));
   CUDA_OK(cudaFuncSetAttribute(k_gemm<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes<double>()));
   CUDA_OK(cudaFuncSetAttribute(k_gemm<cplx>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes<cplx>()));
-  CUDA_OK(cudaFuncSetAttribute(k_rperm, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   *out = c;
   return HS_OK;
   HS_TRY_END
@@ -217,6 +216,12 @@ template <typename T> static void factor_level(hs_fac* f, const Level& L) {
   }
   const int W = hs_panel_width(f, max_prow, L.f1 - L.f0);
   if (W < 0) throw hs_error(HS_ESIZE, "pivot block with " + std::to_string(max_prow) + " rows exceeds the panel kernels");
+  if (L.max_ni > 0) {   // pivot order: the identity now, permuted by every panel's row moves
+    dim3 g(L.f1 - L.f0, (L.max_ni + 255) / 256);
+    k_rperm_init<<<g, 256, 0, st>>>(f->d_fronts, f->d_rperm, L.f0);
+    CUDA_OK(cudaGetLastError());
+    f->stats.launches_factor += 1;
+  }
   auto pivot_rows = [&](int j0, int nact) {   // tallest panel among the active fronts
     if (!has_split) return L.max_ni - j0;
     int m = 0;
@@ -361,15 +366,8 @@ template <typename T> static void factor_level(hs_fac* f, const Level& L) {
       }
     }
   }
-  if (L.max_ni > 0) {
-    const size_t sm = (size_t)L.max_ni * sizeof(int);
-    if (sm > 200 * 1024) throw hs_error(HS_ESIZE, "pivot block too large for k_rperm");
-    k_rperm<<<L.f1 - L.f0, 256, sm, st>>>(f->d_fronts, f->d_ipiv, f->d_rperm, L.f0);
-    CUDA_OK(cudaGetLastError());
-    f->stats.launches_factor += 1;
-    // solve preparation: invert the diagonal blocks of L11/U11 in place (see hs_solve.cu)
-    solve_prep(f, L);
-  }
+  // solve preparation: invert the diagonal blocks of L11/U11 in place (see hs_solve.cu)
+  if (L.max_ni > 0) solve_prep(f, L);
 }
 
 template <typename T> static void numeric(hs_fac* f) {

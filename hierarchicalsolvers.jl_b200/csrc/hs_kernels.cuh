@@ -125,23 +125,12 @@ __global__ void __launch_bounds__(256) k_extend_add(const Front* __restrict__ fr
   }
 }
 
-// rperm[k] = local row of the ORIGINAL pivot block that ends at row k after all interchanges (so P·x is a gather)
-static __global__ void k_rperm(const Front* __restrict__ fronts, const int* __restrict__ ipiv, int* __restrict__ rperm,
-                        int f0) {
-  extern __shared__ int s_p[];
+// rperm[k] = local row of the ORIGINAL pivot block that ends at row k after all interchanges (so P·x is a gather).
+// The identity before the first panel; every k_panel applies its row moves to it.
+static __global__ void k_rperm_init(const Front* __restrict__ fronts, int* __restrict__ rperm, int f0) {
   const Front fr = fronts[f0 + blockIdx.x];
-  const int ni = fr.ni;
-  for (int k = threadIdx.x; k < ni; k += blockDim.x) s_p[k] = k;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const int* pv = ipiv + fr.ioff;
-    for (int k = 0; k < ni; ++k) {
-      const int p = pv[k];
-      if (p != k) { const int t = s_p[k]; s_p[k] = s_p[p]; s_p[p] = t; }
-    }
-  }
-  __syncthreads();
-  for (int k = threadIdx.x; k < ni; k += blockDim.x) rperm[fr.ioff + k] = s_p[k];
+  const int k = blockIdx.y * blockDim.x + threadIdx.x;
+  if (k < fr.ni) rperm[fr.ioff + k] = k;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -52,7 +52,8 @@ __device__ __forceinline__ void hs_st_async64(unsigned dst, unsigned long long v
 
 template <typename T, int W, int R, bool CL>
 __global__ void __launch_bounds__(256, 1) k_panel(const Front* __restrict__ fronts, T* __restrict__ pool,
-                                                   int* __restrict__ ipiv, int f0, int j0, int* __restrict__ info) {
+                                                   int* __restrict__ ipiv, int* __restrict__ rperm, int f0, int j0,
+                                                   int* __restrict__ info) {
   constexpr int NT = 256, TR = 32, TC = 8;
   constexpr int RPT = 8 * R, CPT = W / TC, ROWS = TR * RPT;
   static_assert(W % TC == 0 && RPT <= 64, "unsupported panel shape");
@@ -259,11 +260,16 @@ __global__ void __launch_bounds__(256, 1) k_panel(const Front* __restrict__ fron
   __syncthreads();
   const int nm = s_nmv;
   if (nm == 0) return;
+  // rperm (original row of every position, identity before the first panel) takes the same moves as the rows: the
+  // pivot order is complete when the last panel is, no serial replay of ipiv afterwards
+  int rsave = 0;
+  if (tid < nm) rsave = rperm[fr.ioff + j0 + s_msrc[tid]];
   for (int e = tid; e < nm * wc; e += NT) {
     const int i = e % nm, c = e / nm;
     stage[e] = F[(long long)(j0 + c) * ld + (j0 + s_msrc[i])];
   }
   __syncthreads();
+  if (tid < nm) rperm[fr.ioff + j0 + s_mdst[tid]] = rsave;
   for (int e = tid; e < nm * wc; e += NT) {
     const int i = e % nm, c = e / nm;
     F[(long long)(j0 + c) * ld + (j0 + s_mdst[i])] = stage[e];
@@ -284,7 +290,7 @@ template <typename T, int W, int R>
 static void launch_panel(hs_fac* f, int f0, int nact, int j0, int C, cudaStream_t st) {
   T* pool = (T*)f->pool;
   if (C == 1) {
-    k_panel<T, W, R, false><<<nact, 256, panel_smem<T, W, R>(), st>>>(f->d_fronts, pool, f->d_ipiv, f0, j0, f->d_info);
+    k_panel<T, W, R, false><<<nact, 256, panel_smem<T, W, R>(), st>>>(f->d_fronts, pool, f->d_ipiv, f->d_rperm, f0, j0, f->d_info);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(nact * C));
@@ -300,8 +306,9 @@ static void launch_panel(hs_fac* f, int f0, int nact, int j0, int C, cudaStream_
     cfg.numAttrs = 1;
     const Front* fr = f->d_fronts;
     int* ipiv = f->d_ipiv;
+    int* rperm = f->d_rperm;
     int* info = f->d_info;
-    CUDA_OK(cudaLaunchKernelEx(&cfg, k_panel<T, W, R, true>, fr, pool, ipiv, f0, j0, info));
+    CUDA_OK(cudaLaunchKernelEx(&cfg, k_panel<T, W, R, true>, fr, pool, ipiv, rperm, f0, j0, info));
   }
   CUDA_OK(cudaGetLastError());
 }
