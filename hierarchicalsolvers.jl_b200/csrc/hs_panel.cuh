@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256, 1) k_panel(const Front* __restrict__ fron
   const int plim = hs_plim(fr, j0);
   const int wc = min(W, plim - j0);
   const int m = plim - j0;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int tr = tid % TR, tc = tid / TR;
   const int rbase = crank * ROWS;
   T* F = pool + fr.off;
