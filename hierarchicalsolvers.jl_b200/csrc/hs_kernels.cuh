@@ -3,10 +3,12 @@
 //   assembly   k_fill_owner / k_scatter_A / k_extend_add      (factorization.jl:33-40,115-123)  HBM-bound
 //   LU panel   k_panel   — register-resident panel, one thread-block cluster per front,
 //                          pivot search over distributed shared memory                (blockmatrix.jl:118, `\`)
-//   row ops    k_swap_trsm — row interchanges + unit-lower triangular solve of the U row panel
+//   row ops    k_swap_trsm / k_swap_trsm_warp / k_laswp — row interchanges + unit-lower triangular solve of the U row
+//                          panel (thread per column for the wide launches, warp per column on the panel chain)
 //   update     k_gemm    — FP64 / complex-FP64 tensor-core (DMMA m8n8k4) Schur update C -= A·B
 //                                                                                  (factorization.jl:40,72)
-//   solve      hs_solve.cu: k_trtri_diag, k_sv_small_*, k_sv_big_*, k_gemv_rect  (factornode.jl:77-99)  HBM-bound
+//   elsewhere  hs_panel.cuh: k_panel, k_trsm_rows; hs_small.cu: k_front_small, k_front_rows (whole small fronts);
+//              hs_solve.cu: k_trtri_diag, k_sv_small_*, k_sv_tri_*, k_gemv_rect  (factornode.jl:77-99)  HBM-bound
 #pragma once
 
 #include <cooperative_groups.h>

@@ -542,7 +542,7 @@ __global__ void __launch_bounds__(TRI_T) k_sv_tri_bwd(const Front* __restrict__ 
 }
 
 // Rectangular part of a large front as ONE streamed mat-vec over the whole GPU (it holds 2/3 of the front's bytes and
-// has no dependency chain, so it does not belong inside the block-step loop of the cluster kernels):
+// has no dependency chain, so it does not belong inside the super-block step kernels):
 //   FWD:  x[bnd] −= L21·t,            t = x[int] after the triangular solve         (rows ni..n, columns 0..ni)
 //   BWD:  work[0:ni] = x[int] − U12·x[bnd]                                            (rows 0..ni, columns ni..n)
 // One CTA per (front, 32-row tile, rhs): lane = row, the 8 warps split the columns, partial sums meet in shared memory.
