@@ -514,7 +514,7 @@ def resident_single(args, hs, torch, ctx, stream, local_rank, Ap, nd, nd_loc, b,
     if with_e2e:
         ts, tf_, tg_ = [], [], []
         st2 = None
-        for rep in range(1 + max(1, min(steps, 3))):     # one untimed warm-up pass (first-touch of host staging pages), then ≤ 3 timed
+        for rep in range(1 + max(3, min(steps, 5))):     # one untimed warm-up pass (first-touch of host staging pages), then 3 to 5 timed
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             F2 = hs.factor(Ap, nd, nd_loc, swlevel=0, device=local_rank)
